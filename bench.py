@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py - throughput of the fused DSWx-HLS classification pass on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N \
+        --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on):
+synthetic HLS S30 tiles, 3660 x 3660, full product - 6 int16 bands + Fmask +
+float32 DEM (50-px margin) + LAND + ocean mask -> WTR, BWTR, CONF, DIAG and the
+coverage counters.  One *step* = one launch of the fused kernel over a batch of
+``--tiles`` distinct device-resident tiles per GPU (default 16 = 5.1 GB of
+traffic per step, far larger than the 126 MB L2, so nothing is cache-hot
+between steps).  Tiles are sharded by tile over the ranks with no data-path
+communication (weak scaling: the per-GPU batch is fixed).
+
+One JSON line on stdout (rank 0).  ``value`` = Mpixel/s with inputs resident in
+HBM; ``e2e`` = the same metric through the host-buffer API
+(proteus_b200.classify_tile: pinned numpy arrays in, numpy layers out, H2D and
+D2H inside the timed region); ``roofline`` = algorithmic bytes / kernel time
+against the measured HBM copy peak; ``cpu_baseline`` = the numpy restatement of
+the reference chain (oracle/, kind "port") timed on one host core on one tile.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TILE = 3660
+PIXELS_PER_TILE = TILE * TILE
+BYTES_IN_PER_PX = 6 * 2 + 1 + 4 + 1 + 1      # bands + fmask + DEM + LAND + ocean  
+BYTES_OUT_PER_PX = 1 + 1 + 1 + 2             # WTR + BWTR + CONF + DIAG
+ALGO_BYTES_PER_PX = BYTES_IN_PER_PX + BYTES_OUT_PER_PX      # 24
+METRIC = 'dswx_hls_classification_throughput'
+UNIT = 'Mpixel/s'
+FALLBACK_HBM_GBS = 6650.0                    # /opt/skills/guides/B200_PROFILING.md
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', choices=('ours', 'reference'), default='ours')
+    ap.add_argument('--tiles', type=int, default=16, help='tiles per GPU per step')
+    ap.add_argument('--size', type=int, default=TILE, help='tile edge in pixels (default 3660)')
+    ap.add_argument('--e2e-steps', type=int, default=0, help='host-path steps (default: min(steps, 20))')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--cpu-rows', type=int, default=0,
+                    help='rows of the tile the CPU baseline processes (default: whole tile)')
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------
+# clocks (pynvml; sampled DURING the timed regions)
+# ---------------------------------------------------------------------------
+_REASONS = {0x4: 'sw_power_cap', 0x8: 'hw_slowdown', 0x20: 'sw_thermal_slowdown',
+            0x40: 'hw_thermal_slowdown', 0x80: 'hw_power_brake_slowdown',
+            0x2: 'applications_clocks_setting', 0x10: 'sync_boost'}
+
+
+class ClockSampler:
+    def __init__(self, device_index, period_s=0.004):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._active = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            uuid = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            except Exception:
+                pass
+            self.h = None
+            if uuid:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    u = pynvml.nvmlDeviceGetUUID(h)
+                    u = u.decode() if isinstance(u, bytes) else u
+                    if uuid in u:
+                        self.h = h
+            if self.h is None:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.period = period_s
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        except Exception as e:                       # pragma: no cover
+            self.nv = None
+            self.error = repr(e)
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            if self._active.is_set():
+                try:
+                    self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                    try:
+                        mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for bit, name in _REASONS.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            time.sleep(self.period)
+
+    def start(self):
+        self._active.set()
+
+    def pause(self):
+        self._active.clear()
+
+    def summary(self):
+        self._stop.set()
+        if not self.nv or not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+                    'samples': 0}
+        return {'sm_mhz': statistics.median(self.samples), 'sm_max_mhz': self.max_mhz,
+                'reasons': sorted(self.reasons), 'samples': len(self.samples)}
+
+
+# ---------------------------------------------------------------------------
+# CPU baseline: the numpy restatement of the reference chain (oracle/, "port")
+# ---------------------------------------------------------------------------
+def _oracle_chain_on_rows(tile, r0, r1):
+    from oracle import dswx_oracle as O              # allowed here: cpu_baseline / reference arm only
+    m = tile['dem_margin']
+    return O.reference_chain(
+        [b[r0:r1] for b in tile['bands']], tile['fmask'][r0:r1],
+        tile['dem'][r0:r1 + 2 * m] if tile['dem'] is not None else None,
+        tile['land'][r0:r1] if tile['land'] is not None else None,
+        tile['ocean'][r0:r1] if tile['ocean'] is not None else None,
+        tile['sun_azimuth'], tile['sun_elevation'])
+
+
+def cpu_baseline_one_core(tile, rows):
+    """Time the port on one core over the first ``rows`` rows of the tile."""
+    h, w = tile['fmask'].shape
+    rows = min(rows or h, h)
+    t0 = time.perf_counter()
+    out = _oracle_chain_on_rows(tile, 0, rows)
+    dt = time.perf_counter() - t0
+    mpx = rows * w / 1e6
+    return out, {'value': mpx / dt, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+                 'seconds': dt,
+                 'sample': f'rows 0..{rows} of one synthetic S30 tile ({rows}x{w} px, full product), '
+                           'numpy restatement of dswx_hls.py:5088-5369 (oracle/dswx_oracle.py), 1 process'}
+
+
+_G_TILE = None
+
+
+def _pool_job(args):
+    r0, r1 = args
+    out = _oracle_chain_on_rows(_G_TILE, r0, r1)
+    return int(out['counters'][0]), int(out['WTR'].astype('int64').sum())
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU algorithm (numpy port; the
+    reference itself is not installable here and does not exist on the GPU
+    box) on all host cores, one tile per step split into row strips."""
+    global _G_TILE
+    import multiprocessing as mp
+    import numpy as np
+    from proteus_b200 import synth
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    size = args.size
+    # bounded sample: a band of rows sized so that one step is ~2-4 s on this box
+    rows = min(size, max(64, int(150 * cores)))
+    rows = args.cpu_rows or rows
+    tile = synth.make_tile(0, size, size)
+    _G_TILE = tile
+    n_jobs = min(cores, max(1, rows // 32))
+    bounds = np.linspace(0, rows, n_jobs + 1).astype(int)
+    jobs = [(int(bounds[i]), int(bounds[i + 1])) for i in range(n_jobs) if bounds[i + 1] > bounds[i]]
+    steps = max(1, min(args.steps, 5))
+    warm = 1 if args.warmup > 0 else 0
+    ctx = mp.get_context('fork')
+    with ctx.Pool(len(jobs)) as pool:
+        for _ in range(warm):
+            pool.map(_pool_job, jobs)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            pool.map(_pool_job, jobs)
+        dt = time.perf_counter() - t0
+    mpx = rows * size / 1e6
+    value = mpx * steps / dt
+    sample = (f'{steps} steps x rows 0..{rows} of one synthetic S30 {size}x{size} tile (full product) split into '
+              f'{len(jobs)} row strips over {len(jobs)} processes; numpy port of dswx_hls.py:5088-5369')
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': steps, 'warmup': warm, 'ms_per_step': 1e3 * dt / steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int16', 'data': 'synthetic',
+        'tiles_per_s': value * 1e6 / (size * size),
+        'config': {'workload': 'configs[1]: synthetic HLS S30 tile 3660x3660 full product (bounded CPU sample)',
+                   'tile': [size, size], 'layers_out': ['WTR', 'BWTR', 'CONF', 'DIAG'],
+                   'bytes_per_pixel': ALGO_BYTES_PER_PX},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': len(jobs), 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+        'note': 'reference is pure Python + GDAL; GDAL/yamale are absent so it cannot be pip-installed; '
+                'its per-pixel numpy chain is timed through the validated port (oracle/)',
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device - the product has no CPU path to time')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    import proteus_b200 as pb
+    from proteus_b200 import synth
+
+    size, n_tiles = args.size, args.tiles
+    px_per_tile = size * size
+    sampler = ClockSampler(local_rank)
+
+    # ---- device-resident batch (weak scaling: n_tiles per rank) -------------
+    tiles = synth.make_device_batch(n_tiles, size, size, device=f'cuda:{local_rank}',
+                                    seed=1000 + rank, n_distinct=min(4, n_tiles))
+    params = pb.make_params(collapse_wtr_classes=True)
+    plan = pb.Plan(tiles, params, pb.GRADED_LAYERS)
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        plan.run(stream)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        plan.run(stream)
+    ev1.record(stream)
+    barrier()
+    sampler.pause()
+    ms_total = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total_max = float(t.item())
+    ms_per_step = ms_total_max / args.steps
+    mpx_per_step_all = world * n_tiles * px_per_tile / 1e6
+    value = mpx_per_step_all / (ms_per_step / 1e3)
+
+    # kernel-only roofline on this rank (the step IS one kernel launch)
+    kernel_ms = ms_total / args.steps
+    algo_bytes = n_tiles * px_per_tile * ALGO_BYTES_PER_PX
+    achieved = algo_bytes / (kernel_ms / 1e3) / 1e9
+    peak, peak_src = FALLBACK_HBM_GBS, 'fallback (B200_PROFILING.md)'
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            peak = float(json.load(f)['hbm_gbs'])
+            peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs, burst copy)'
+    except Exception:
+        pass
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            tj = json.load(f)
+            traffic = tj['dram_bytes_per_pixel'] * n_tiles * px_per_tile
+    except Exception:
+        pass
+
+    # ---- end to end through the host-buffer API ------------------------------
+    e2e = None
+    parity = None
+    cpu_baseline = None
+    host_tile = None
+    if not args.no_e2e or not args.no_cpu_baseline:
+        host_tile = synth.make_tile(rank, size, size)
+    if not args.no_e2e:
+        pin = dict(bands=[pb.pinned_copy(b) for b in host_tile['bands']],
+                   fmask=pb.pinned_copy(host_tile['fmask']), dem=pb.pinned_copy(host_tile['dem']),
+                   land=pb.pinned_copy(host_tile['land']), ocean=pb.pinned_copy(host_tile['ocean']))
+        outbuf = {n: pb.pinned_empty((size, size), np.uint16 if n == 'DIAG' else np.uint8)
+                  for n in pb.GRADED_LAYERS}
+        outbuf['counters'] = pb.pinned_empty((12,), np.uint64)
+
+        def host_step():
+            return pb.classify_tile(pin['bands'], pin['fmask'], pin['dem'], pin['land'], pin['ocean'],
+                                    host_tile['sun_azimuth'], host_tile['sun_elevation'],
+                                    params=params, outputs=pb.GRADED_LAYERS, out=outbuf)
+        e2e_steps = args.e2e_steps or min(args.steps, 20)
+        for _ in range(3):
+            host_res = host_step()
+        barrier()
+        sampler.start()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            host_res = host_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        sampler.pause()
+        tt = torch.tensor([dt], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        dem_rows_copied = size + 2
+        h2d = px_per_tile * (12 + 1 + 1 + 1) + dem_rows_copied * (size + 100) * 4
+        d2h = px_per_tile * BYTES_OUT_PER_PX + 12 * 8
+        e2e = {'value': world * e2e_steps * px_per_tile / 1e6 / dt, 'unit': UNIT,
+               'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+               'steps': e2e_steps, 'ms_per_tile': 1e3 * dt / e2e_steps,
+               'api': 'proteus_b200.classify_tile (pb200_classify_host): pinned numpy in, numpy out, '
+                      '1 tile per step per GPU'}
+
+    # ---- CPU baseline (rank 0, N = 1 only) + parity in the same run ----------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_out, cpu_baseline = cpu_baseline_one_core(host_tile, args.cpu_rows)
+        if not args.no_e2e:
+            rows = cpu_out['WTR'].shape[0]
+            keymap = {'WTR': 'WTR_COLLAPSED', 'BWTR': 'BWTR', 'CONF': 'CONF', 'DIAG': 'DIAG'}
+            mism = {n: int((host_res[n][:rows] != cpu_out[k]).sum()) for n, k in keymap.items()}
+            parity = {'checked_pixels': int(rows * size), 'mismatches': mism,
+                      'bit_exact': all(v == 0 for v in mism.values())}
+
+    clocks = sampler.summary()
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int16', 'data': 'synthetic',
+            'tiles_per_s': value * 1e6 / px_per_tile,
+            'config': {
+                'workload': f'configs[1]: synthetic HLS S30 tile {size}x{size} full product '
+                            f'(6 int16 bands + Fmask + DEM + LAND + ocean -> WTR/BWTR/CONF/DIAG + counters), '
+                            f'{n_tiles} distinct device-resident tiles per GPU per step, sharded by tile',
+                'tile': [size, size], 'tiles_per_gpu_per_step': n_tiles,
+                'layers_out': list(pb.GRADED_LAYERS), 'bytes_per_pixel': ALGO_BYTES_PER_PX,
+                'l2_policy': f'inputs per step {n_tiles * px_per_tile * BYTES_IN_PER_PX / 1e9:.2f} GB >> 126 MB L2; no flush needed',
+                'parallelism': f'tile-sharded x{world}, no data-path collective'},
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                         'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                         'algorithmic_bytes_per_launch': algo_bytes, 'kernel_ms': kernel_ms,
+                         'frac_of_nominal_8TBs': achieved / 8000.0,
+                         'kernel': 'pb200::dswx_fused_kernel<true>'},
+            'e2e': e2e, 'cpu_baseline': cpu_baseline, 'parity': parity,
+            'gpu_launches': args.steps, 'clocks': clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

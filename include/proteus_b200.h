@@ -1,0 +1,233 @@
+/*
+ * proteus_b200.h - C ABI of libproteus_b200.so
+ *
+ * B200-native (sm_100a) implementation of the per-pixel DSWx-HLS
+ * classification path of nasa/PROTEUS v1.0.2.  The reference has no FFI layer
+ * of its own (it is pure Python/numpy): the seam this library replaces is the
+ * set of module-level functions of src/proteus/dswx_hls.py ("D:" below) that
+ * generate_dswx_layers (D:4610) calls between loading the rasters and saving
+ * the layers.  Each entry point cites the reference statement(s) it replaces.
+ *
+ * Conventions
+ *   - plain C types only; every raster pointer is a DEVICE pointer unless the
+ *     function name ends in _host;
+ *   - the caller owns every buffer (inputs, outputs, counters); the library
+ *     allocates nothing per call except inside a plan / the host pipeline;
+ *   - every function returns 0 on success, <0 for an invalid argument
+ *     (PB200_E_*), >0 for a cudaError_t; pb200_last_error() gives the text
+ *     (thread-local);
+ *   - calls are asynchronous on the given CUDA stream (a cudaStream_t passed
+ *     as void*; NULL = legacy default stream) unless stated otherwise;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     point fails with a cudaError_t.
+ */
+#ifndef PROTEUS_B200_H
+#define PROTEUS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB200_ABI_VERSION 1
+
+/* error codes (<0) */
+#define PB200_E_INVALID_ARG   (-1)
+#define PB200_E_BAD_MODE      (-2)   /* D:1977-1981 raise Exception(...) */
+#define PB200_E_UNSUPPORTED   (-3)
+#define PB200_E_NO_DRIVER_API (-4)
+#define PB200_E_ALIGNMENT     (-5)
+
+/* "this raster has no fill value" (D:2196-2199 always yields one, but the
+ * function-granular entry points are also used on already-clean data) */
+#define PB200_NO_FILL INT32_MIN
+
+/* mask_adjacent_to_cloud_mode (D:1929-1935) */
+#define PB200_ADJ_MASK   0
+#define PB200_ADJ_IGNORE 1
+#define PB200_ADJ_COVER  2   /* only pb200_preliminary_cloud / pb200_snow_to_cloud accept it
+                                (the dilation itself is SURVEY 8f "next #2") */
+
+/* counters slot layout (uint64 each) */
+#define PB200_CNT_VALID           0  /* D:5110  n_valid                     */
+#define PB200_CNT_CLOUD_AND_VALID 1  /* D:5111  n_cloud_and_valid           */
+#define PB200_CNT_NOT_OCEAN       2  /* D:5105  sum(ocean_mask)             */
+#define PB200_CNT_CLASS0          3  /* extension: histogram of the UNCOLLAPSED WTR layer,
+                                        9 bins in the order 0,1,2,3,4,252,253,254,255 */
+#define PB200_N_COUNTERS          12
+
+/* Mirror of class HlsThresholds (D:274-318); values as in the runconfig
+ * (defaults: src/proteus/defaults/dswx_hls.yaml:176-212). */
+typedef struct pb200_thresholds {
+    double wigt, awgt;
+    double pswt_1_mndwi, pswt_1_nir, pswt_1_swir1, pswt_1_ndvi;
+    double pswt_2_mndwi, pswt_2_blue, pswt_2_nir, pswt_2_swir1, pswt_2_swir2;
+    double lcmask_nir;
+} pb200_thresholds;
+
+/* Everything generate_dswx_layers passes down the hot path besides rasters. */
+typedef struct pb200_params {
+    pb200_thresholds th;
+    int32_t band_fill[6];        /* D:2176/2196-2199, blue..swir2; PB200_NO_FILL = none */
+    int32_t fmask_fill;          /* HLS v2 Fmask: 255 */
+    int32_t adjacent_mode;       /* PB200_ADJ_* */
+    int32_t apply_aerosol_class_remapping;       /* D:5260 */
+    /* bit k of aerosol_class_bits[v] is set when Fmask value v is in the
+     * list that remaps WTR-1 class k to 1 (k = 0, 2, 3, 4; D:1283-1296). */
+    uint8_t aerosol_class_bits[256];
+    double  min_slope_angle;           /* degrees, D:4279 */
+    double  max_sun_local_inc_angle;   /* degrees, D:4280 */
+    /* Decision thresholds of the two angle tests in the cosine / tangent
+     * domain:  degrees(arccos(x)) <= max_inc  <=>  x >= cos_inc_threshold,
+     *          degrees(arctan(s)) <= min_slope <=> s <= tan_slope_threshold.
+     * Set both to NaN to let the library derive them with libm; the Python
+     * host derives them by bisection on numpy's own arccos/arctan so that the
+     * boundary is the reference's boundary to the last bit. */
+    double  cos_inc_threshold;
+    double  tan_slope_threshold;
+    double  pixel_spacing_x, pixel_spacing_y;    /* D:4217: always 30, 30 */
+    int32_t collapse_wtr_classes;  /* write WTR / WTR-1 / WTR-2 collapsed (D:2688-2689) */
+    int32_t class_histogram;       /* also fill counters[3..11] */
+} pb200_params;
+
+/* One raster tile (an MGRS tile, one acquisition of a time series, or one row
+ * strip of a mosaic).  Inputs are planar, C-contiguous, row pitch = width.
+ * NULL outputs are skipped.  The DEM is addressed as
+ *   dem[(dem_off_y + row) * dem_pitch + (dem_off_x + col)]
+ * and must have at least one valid element on every side of the tile
+ * (the reference warps it with a 50-px margin, D:58, D:5145-5150). */
+typedef struct pb200_tile {
+    int32_t height, width;
+    const int16_t *band[6];      /* RAW blue, green, red, nir, swir1, swir2 (before D:2299) */
+    const uint8_t *fmask;
+    const float   *dem;          /* NULL: no terrain-shadow masking */
+    int32_t dem_pitch;           /* elements per DEM row */
+    int32_t dem_rows;            /* rows in the DEM array */
+    int32_t dem_off_y, dem_off_x;
+    const uint8_t *land;         /* NULL: no land-cover masking (D:1346) */
+    const uint8_t *ocean;        /* NULL: no shoreline given (D:5096) */
+    double sun_azimuth, sun_elevation;   /* degrees (D:5044-5059) */
+    /* Optional: the five float64 scalars D:4245-4252, 4276-4277 derive from
+     * the two angles, in this order: sun_x, sun_y, sun_z, sin(az), cos(az).
+     * sun_terms[0] = NaN: the library derives them with libm.  The Python host
+     * fills them with numpy so that they are the reference's own values. */
+    double sun_terms[5];
+    uint16_t *diag;              /* DIAG  (D:5231) */
+    uint8_t  *wtr1;              /* WTR-1 as saved, i.e. BEFORE aerosol remapping (D:5251) */
+    uint8_t  *wtr1_remapped;     /* WTR-1 after D:5261 (band of the combined file, D:5390) */
+    uint8_t  *wtr2;              /* WTR-2 (D:5268) */
+    uint8_t  *cloud;             /* CLOUD (D:5282) */
+    uint8_t  *shad;              /* SHAD, 1 = not shadow (D:5166) */
+    uint8_t  *wtr;               /* WTR   (D:5286) */
+    uint8_t  *bwtr;              /* BWTR  (D:5358) */
+    uint8_t  *conf;              /* CONF  (D:5368) */
+    uint64_t *counters;          /* PB200_N_COUNTERS slots, ADDED to (caller zeroes) */
+} pb200_tile;
+
+typedef struct pb200_ctx  pb200_ctx;
+typedef struct pb200_plan pb200_plan;
+
+/* ---- library / context ------------------------------------------------ */
+int         pb200_version(void);
+const char *pb200_last_error(void);
+int  pb200_ctx_create(int device, pb200_ctx **out);
+int  pb200_ctx_destroy(pb200_ctx *ctx);
+/* defaults of src/proteus/defaults/dswx_hls.yaml:64-109,176-212 */
+int  pb200_params_default(pb200_params *p);
+
+/* ---- fused path: D:5088-5369 in one pass -------------------------------- */
+/* One launch over n_tiles tile descriptors (host array of device pointers). */
+int  pb200_classify(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles,
+                    const pb200_params *params, void *stream);
+/* Plan = descriptors + TMA tensor maps resident on the device; run many times
+ * (time series, benchmarks, CUDA-graph capture). */
+int  pb200_plan_create(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles,
+                       const pb200_params *params, pb200_plan **out);
+int  pb200_plan_run(pb200_plan *plan, void *stream);
+int  pb200_plan_destroy(pb200_plan *plan);
+/* Same contract as pb200_classify for ONE tile whose pointers are HOST
+ * pointers (what generate_dswx_layers holds after gdal.ReadAsArray, D:2192).
+ * Row strips are copied in, classified and copied out on three streams so
+ * H2D, the kernel and D2H overlap; returns when the outputs are in host
+ * memory.  Buffers from pb200_host_alloc (pinned) copy at full PCIe rate. */
+int  pb200_classify_host(pb200_ctx *ctx, const pb200_tile *host_tile,
+                         const pb200_params *params, int strip_rows);
+int  pb200_host_alloc(size_t bytes, void **out);
+int  pb200_host_free(void *p);
+
+/* ---- function-granular entry points (parity with one reference function) */
+/* D:2203-2209 + D:2298-2299: invalid |= raw == fill ; band = max(band, 1) */
+int  pb200_invalid_and_clip(pb200_ctx *ctx, const int16_t *const raw[6],
+                            const uint8_t *fmask, const pb200_params *params,
+                            int64_t n, int16_t *const clipped[6],
+                            uint8_t *invalid, void *stream);
+/* D:1840-1916 _compute_diagnostic_tests (int16 bands, used as given) */
+int  pb200_diagnostic_tests(pb200_ctx *ctx, const int16_t *const band[6],
+                            const pb200_thresholds *th, int64_t n,
+                            uint16_t *diag_decimal, void *stream);
+/* D:1687-1707 generate_interpreted_layer */
+int  pb200_interpreted_layer(pb200_ctx *ctx, const uint16_t *diag_decimal,
+                             int64_t n, uint8_t *wtr1, void *stream);
+/* D:4286-4317 _get_binary_representation (nbits = 6) */
+int  pb200_binary_representation(pb200_ctx *ctx, const uint16_t *diag_decimal,
+                                 int64_t n, uint16_t *diag, void *stream);
+/* D:1919-1993 _compute_preliminary_cloud_layer */
+int  pb200_preliminary_cloud(pb200_ctx *ctx, const uint8_t *fmask, int mode,
+                             int64_t n, uint8_t *cloud, void *stream);
+/* D:1249-1302 _apply_aerosol_class_remapping: wtr1 and cloud IN PLACE */
+int  pb200_aerosol_remap(pb200_ctx *ctx, uint8_t *wtr1, const int16_t *nir,
+                         uint8_t *cloud, const uint8_t *fmask,
+                         const uint8_t aerosol_class_bits[256], int64_t n,
+                         void *stream);
+/* D:1305-1378 _apply_landcover_and_shadow_masks; land / shad may be NULL */
+int  pb200_landcover_shadow_masks(pb200_ctx *ctx, const uint8_t *wtr1,
+                                  const int16_t *nir, const uint8_t *land,
+                                  const uint8_t *shad, double lcmask_nir,
+                                  int64_t n, uint8_t *wtr2, void *stream);
+/* D:1996-2086 _add_snow_to_cloud_layer, modes mask / ignore; cloud IN PLACE */
+int  pb200_snow_to_cloud(pb200_ctx *ctx, const uint8_t *wtr2, uint8_t *cloud,
+                         const uint8_t *fmask, int mode, int64_t n,
+                         void *stream);
+/* D:2089-2133 _apply_cloud_masking */
+int  pb200_cloud_masking(pb200_ctx *ctx, const uint8_t *wtr2,
+                         const uint8_t *cloud, int64_t n, uint8_t *wtr,
+                         void *stream);
+/* D:1710-1730 _get_binary_water_layer */
+int  pb200_binary_water(pb200_ctx *ctx, const uint8_t *wtr, int64_t n,
+                        uint8_t *bwtr, void *stream);
+/* D:1733-1837 _get_confidence_layer */
+int  pb200_confidence(pb200_ctx *ctx, const uint8_t *wtr2,
+                      const uint8_t *cloud, int64_t n, uint8_t *conf,
+                      void *stream);
+/* D:2578-2598 _collapse_wtr_classes */
+int  pb200_collapse(pb200_ctx *ctx, const uint8_t *layer, int64_t n,
+                    uint8_t *collapsed, void *stream);
+/* D:4215-4283 _compute_opera_shadow_layer over a whole float32 DEM
+ * (rows x cols, pitch = cols), one-sided differences on the array border
+ * exactly like np.gradient; out[rows*cols] uint8 1 = not shadow. */
+int  pb200_shadow(pb200_ctx *ctx, const float *dem, int rows, int cols,
+                  double sun_azimuth, double sun_elevation,
+                  const double *sun_terms /* 5 doubles as in pb200_tile, or NULL */,
+                  const pb200_params *params, uint8_t *out, void *stream);
+
+/* ---- helpers exported for tests ---------------------------------------- */
+/* The exact integer form of "float64(n)/float64(d) > t" (is_less = 0) or
+ * "< t" (is_less = 1) for int16 n, d:  with p/q = n/d, q > 0,
+ *   >  t  <=>  p * b >= a * q          <  t  <=>  p * b <= a * q
+ * b == 0 encodes always (a = -1 / +1) or never (a = +1 / -1). */
+int  pb200_ratio_bound(double t, int is_less, int32_t *a, int32_t *b);
+/* Exhaustive check of that form against IEEE float64 division over all
+ * 2^32 (n, d) int16 pairs on the GPU; *mismatches = number of disagreeing
+ * pairs (d == 0 included: inf / nan semantics). Synchronous. */
+int  pb200_ratio_sweep(pb200_ctx *ctx, double t, int is_less,
+                       uint64_t *mismatches);
+/* Derived angle thresholds the library would use for these params (libm). */
+int  pb200_angle_thresholds(const pb200_params *params, double *cos_inc,
+                            double *tan_slope);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PROTEUS_B200_H */

@@ -1,0 +1,71 @@
+"""TEST INFRASTRUCTURE ONLY - live import of the unmodified reference module.
+
+Imports ``proteus.dswx_hls`` from ``/root/reference/src`` with stand-in modules
+for the GDAL / yamale / ruamel imports the reference does at module scope
+(``src/proteus/dswx_hls.py:8-13``; none of them is touched by the per-pixel
+functions of SURVEY.md section 8a).  Nothing under ``/root/reference`` is
+modified or copied.
+
+``/root/reference`` exists only in the build container.  On the GPU box
+``available()`` returns False and everything that needs the live reference is
+skipped; the committed fixtures under ``tests/golden/`` (made by
+``oracle/make_golden.py`` with this module) carry the reference's outputs there.
+
+Only ``tests/`` and ``oracle/make_golden.py`` may import this file.
+"""
+import logging
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get('PROTEUS_REFERENCE_ROOT', '/root/reference')
+_REF = None
+
+
+def available():
+    return os.path.isfile(
+        os.path.join(REFERENCE_ROOT, 'src', 'proteus', 'dswx_hls.py'))
+
+
+def _stub(name, **attrs):
+    mod = types.ModuleType(name)
+    mod.__dict__.update(attrs)
+    sys.modules[name] = mod
+    return mod
+
+
+def load():
+    """Return the reference module object (cached)."""
+    global _REF
+    if _REF is not None:
+        return _REF
+    if not available():
+        raise RuntimeError(f'reference tree not found at {REFERENCE_ROOT}')
+    if 'osgeo' not in sys.modules:
+        osgeo = _stub('osgeo')
+        osgeo.gdal = _stub('osgeo.gdal', GDT_Byte=1, GDT_UInt16=2,
+                           GDT_Float32=6)
+        osgeo.osr = _stub('osgeo.osr')
+        osgeo.ogr = _stub('osgeo.ogr')
+        osgeo.gdalconst = _stub('osgeo.gdalconst', GDT_Float32=6, GDT_Byte=1)
+    if 'yamale' not in sys.modules:
+        _stub('yamale')
+    if 'ruamel.yaml' not in sys.modules:
+        ruamel = sys.modules.get('ruamel') or _stub('ruamel')
+        ruamel.yaml = _stub('ruamel.yaml', YAML=object)
+    src = os.path.join(REFERENCE_ROOT, 'src')
+    if src not in sys.path:
+        sys.path.insert(0, src)
+    import proteus.dswx_hls as ref
+    logging.getLogger('dswx_hls').setLevel(logging.CRITICAL)
+    _REF = ref
+    return ref
+
+
+def default_runconfig_groups():
+    """The 'groups' dict of the reference's packaged default runconfig."""
+    import yaml
+    path = os.path.join(REFERENCE_ROOT, 'src', 'proteus', 'defaults',
+                        'dswx_hls.yaml')
+    with open(path) as f:
+        return yaml.safe_load(f)['runconfig']['groups']

@@ -1,0 +1,889 @@
+// pb200_api.cu - C ABI of libproteus_b200.so (see include/proteus_b200.h).
+//
+// Host side of the B200 DSWx-HLS classification path: parameter derivation
+// (exact rational bounds, integer thresholds, look-up tables), tile
+// descriptors + TMA tensor maps, kernel launches, and the strip-pipelined
+// host-buffer entry point.  No CPU implementation of the pixel math lives
+// here: every compute entry point launches a CUDA kernel or fails.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/proteus_b200.h"
+#include "pb200_kernels.cuh"
+
+using namespace pb200;
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+static int fail_cuda(cudaError_t e, const char *what) {
+    g_err = std::string(what) + ": " + cudaGetErrorName(e) + " - " + cudaGetErrorString(e);
+    return (int)e > 0 ? (int)e : 999;
+}
+#define CK(call)                                          \
+    do {                                                  \
+        cudaError_t e_ = (call);                          \
+        if (e_ != cudaSuccess) return fail_cuda(e_, #call); \
+    } while (0)
+
+extern "C" int pb200_version(void) { return PB200_ABI_VERSION; }
+extern "C" const char *pb200_last_error(void) { return g_err.c_str(); }
+
+// ---------------------------------------------------------------------------
+// exact rational bound for  float64(n)/float64(d) {>,<} t,  n, d int16
+// ---------------------------------------------------------------------------
+// RN(n/d) > t  <=>  n/d > M, M = midpoint(t, succ(t))   (n/d is never a
+// midpoint: it would need a 54-bit significand, |d| < 2^16).  Among all p/q
+// with |p| <= 32768, 1 <= q <= 32768 the smallest one above M is a/b, so
+// n/d > M <=> p/q >= a/b <=> p*b >= a*q.  Mirror image for "<".
+typedef __int128 i128;
+
+// value = mant * 2^exp2, mant odd or zero
+static void decompose(double v, long long *mant, int *exp2) {
+    if (v == 0.0) { *mant = 0; *exp2 = 0; return; }
+    int e;
+    const double f = std::frexp(v, &e);          // v = f * 2^e, 0.5 <= |f| < 1
+    *mant = (long long)std::ldexp(f, 53);        // exact: 53-bit integer
+    *exp2 = e - 53;
+}
+
+// floor(M * q) for M = (m1*2^e1 + m2*2^e2) / 2 and 1 <= q <= 32768
+static long long floor_mid_times(long long m1, int e1, long long m2, int e2, long long q) {
+    const int k = std::min(e1, e2);
+    const i128 sum = ((i128)m1 << (e1 - k)) + ((i128)m2 << (e2 - k));    // shifts <= 2 for neighbours / zero
+    const i128 prod = sum * (i128)q;                                     // |prod| < 2^72
+    const int sh = -(k - 1);                                             // M*q = prod / 2^sh
+    if (sh <= 0) return (long long)(prod << (-sh));
+    if (sh >= 120) return prod < 0 ? -1 : 0;
+    return (long long)(prod >> sh);                                      // arithmetic shift = floor
+}
+
+extern "C" int pb200_ratio_bound(double t, int is_less, int32_t *a_out, int32_t *b_out) {
+    if (!a_out || !b_out) return fail(PB200_E_INVALID_ARG, "pb200_ratio_bound: null output");
+    const int never_a = is_less ? -1 : 1, always_a = is_less ? 1 : -1;
+    if (std::isnan(t)) { *a_out = never_a; *b_out = 0; return 0; }
+    if (t >= 1048576.0) { *a_out = is_less ? always_a : never_a; *b_out = 0; return 0; }
+    if (t <= -1048576.0) { *a_out = is_less ? never_a : always_a; *b_out = 0; return 0; }
+    const double nb = is_less ? std::nextafter(t, -INFINITY) : std::nextafter(t, INFINITY);
+    long long m1, m2;
+    int e1, e2;
+    decompose(t, &m1, &e1);
+    decompose(nb, &m2, &e2);
+    if (m1 == 0) e1 = e2;
+    if (m2 == 0) e2 = e1;
+    long long best_a = 0, best_b = 0;
+    for (long long q = 1; q <= 32768; ++q) {
+        long long a;
+        if (!is_less) {
+            a = floor_mid_times(m1, e1, m2, e2, q) + 1;       // smallest integer a with a/q > M
+            if (a > 32768) continue;
+            if (a < -32768) a = -32768;
+            if (best_b == 0 || a * best_b < best_a * q) { best_a = a; best_b = q; }
+        } else {
+            // largest integer a with a/q < M:  a = ceil(M q) - 1 = -floor(-M q) - 1
+            a = -floor_mid_times(-m1, e1, -m2, e2, q) - 1;
+            if (a < -32768) continue;
+            if (a > 32768) a = 32768;
+            if (best_b == 0 || a * best_b > best_a * q) { best_a = a; best_b = q; }
+        }
+    }
+    if (best_b == 0) { *a_out = never_a; *b_out = 0; return 0; }
+    *a_out = (int32_t)best_a;
+    *b_out = (int32_t)best_b;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// angle thresholds in the cosine / tangent domain (libm flavour)
+// ---------------------------------------------------------------------------
+static inline long long dkey(double x) {            // order-preserving double -> int64
+    long long k;
+    std::memcpy(&k, &x, 8);
+    return k < 0 ? (long long)0x8000000000000000ULL - k : k;
+}
+static inline double dunkey(long long k) {
+    long long b = k < 0 ? (long long)0x8000000000000000ULL - k : k;
+    double x;
+    std::memcpy(&x, &b, 8);
+    return x;
+}
+static const double RAD2DEG = 180.0 / 3.14159265358979323846;
+
+// smallest x in [-1, 1] with degrees(acos(x)) <= max_inc; 2.0 if none
+static double derive_cos_threshold(double max_inc) {
+    auto pred = [&](double x) { return std::acos(x) * RAD2DEG <= max_inc; };
+    if (!pred(1.0)) return 2.0;
+    if (pred(-1.0)) return -1.0;
+    long long lo = dkey(-1.0), hi = dkey(1.0);      // pred(lo) false, pred(hi) true
+    while (lo + 1 < hi) {
+        const long long mid = (lo >> 1) + (hi >> 1) + (lo & hi & 1);    // no overflow
+        if (pred(dunkey(mid))) hi = mid; else lo = mid;
+    }
+    return dunkey(hi);
+}
+// largest s with degrees(atan(s)) <= min_slope; +inf if all, NaN if none
+static double derive_tan_threshold(double min_slope) {
+    auto pred = [&](double s) { return std::atan(s) * RAD2DEG <= min_slope; };
+    if (pred(INFINITY)) return INFINITY;
+    if (!pred(-INFINITY)) return std::numeric_limits<double>::quiet_NaN();
+    long long lo = dkey(-INFINITY), hi = dkey(INFINITY);   // pred(lo) true, pred(hi) false
+    while (lo + 1 < hi) {
+        const long long mid = (lo >> 1) + (hi >> 1) + (lo & hi & 1);    // no overflow
+        if (pred(dunkey(mid))) lo = mid; else hi = mid;
+    }
+    return dunkey(lo);
+}
+
+extern "C" int pb200_angle_thresholds(const pb200_params *p, double *cos_inc, double *tan_slope) {
+    if (!p || !cos_inc || !tan_slope) return fail(PB200_E_INVALID_ARG, "pb200_angle_thresholds: null argument");
+    // NaN in cos_inc_threshold = "derive both"; otherwise both are taken as given
+    // (NaN is a legitimate tan_slope_threshold: "no pixel is a back slope").
+    if (std::isnan(p->cos_inc_threshold)) {
+        *cos_inc = derive_cos_threshold(p->max_sun_local_inc_angle);
+        *tan_slope = derive_tan_threshold(p->min_slope_angle);
+    } else {
+        *cos_inc = p->cos_inc_threshold;
+        *tan_slope = p->tan_slope_threshold;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// parameter derivation
+// ---------------------------------------------------------------------------
+extern "C" int pb200_params_default(pb200_params *p) {
+    if (!p) return fail(PB200_E_INVALID_ARG, "pb200_params_default: null");
+    std::memset(p, 0, sizeof(*p));
+    p->th.wigt = 0.124; p->th.awgt = 0.0;
+    p->th.pswt_1_mndwi = -0.44; p->th.pswt_1_nir = 1500; p->th.pswt_1_swir1 = 900; p->th.pswt_1_ndvi = 0.7;
+    p->th.pswt_2_mndwi = -0.5; p->th.pswt_2_blue = 1000; p->th.pswt_2_nir = 2500;
+    p->th.pswt_2_swir1 = 3000; p->th.pswt_2_swir2 = 1000;
+    p->th.lcmask_nir = 1200;
+    for (int k = 0; k < 6; ++k) p->band_fill[k] = -9999;
+    p->fmask_fill = 255;
+    p->adjacent_mode = PB200_ADJ_MASK;
+    p->apply_aerosol_class_remapping = 1;
+    const int l3[] = {224, 160, 96}, l5[] = {224, 192, 160, 128, 96};
+    for (int v : l3) p->aerosol_class_bits[v] |= (1u << 0) | (1u << 2);
+    for (int v : l5) p->aerosol_class_bits[v] |= (1u << 3) | (1u << 4);
+    p->min_slope_angle = -5; p->max_sun_local_inc_angle = 40;
+    p->cos_inc_threshold = p->tan_slope_threshold = std::numeric_limits<double>::quiet_NaN();
+    p->pixel_spacing_x = p->pixel_spacing_y = 30;
+    p->collapse_wtr_classes = 1;
+    p->class_histogram = 0;
+    return 0;
+}
+
+static int32_t clamp_i32(double v, double lo, double hi) { return (int32_t)std::max(lo, std::min(hi, v)); }
+// integer x:  x < t <=> x < ceil(t);  NaN -> never
+static int32_t lt_threshold(double t) { return std::isnan(t) ? -40000 : clamp_i32(std::ceil(t), -40000, 40000); }
+// integer x:  x > t <=> x > floor(t); NaN -> never
+static int32_t gt_threshold(double t) { return std::isnan(t) ? 40000 : clamp_i32(std::floor(t), -40000, 40000); }
+
+static int derive_thresholds(const pb200_thresholds &th, DevParams *D) {
+    int rc;
+    if ((rc = pb200_ratio_bound(th.wigt, 0, &D->r_a[RB_WIGT], &D->r_b[RB_WIGT]))) return rc;
+    if ((rc = pb200_ratio_bound(th.pswt_1_mndwi, 0, &D->r_a[RB_P1_MNDWI], &D->r_b[RB_P1_MNDWI]))) return rc;
+    if ((rc = pb200_ratio_bound(th.pswt_2_mndwi, 0, &D->r_a[RB_P2_MNDWI], &D->r_b[RB_P2_MNDWI]))) return rc;
+    if ((rc = pb200_ratio_bound(th.pswt_1_ndvi, 1, &D->r_a[RB_P1_NDVI], &D->r_b[RB_P1_NDVI]))) return rc;
+    // awesh > awgt <=> 4*awesh > 4*awgt <=> (int)4*awesh > floor(4*awgt)
+    D->awesh4_thr = std::isnan(th.awgt) ? (1 << 30)
+                                        : clamp_i32(std::floor(4.0 * th.awgt), -(double)(1 << 30), (double)(1 << 30));
+    D->p1_swir1 = lt_threshold(th.pswt_1_swir1);
+    D->p1_nir = lt_threshold(th.pswt_1_nir);
+    D->p2_blue = lt_threshold(th.pswt_2_blue);
+    D->p2_swir1 = lt_threshold(th.pswt_2_swir1);
+    D->p2_swir2 = lt_threshold(th.pswt_2_swir2);
+    D->p2_nir = lt_threshold(th.pswt_2_nir);
+    D->lc_nir = gt_threshold(th.lcmask_nir);
+    return 0;
+}
+
+static int derive_params(const pb200_params *p, DevParams *D, bool fused) {
+    std::memset(D, 0, sizeof(*D));
+    if (p->adjacent_mode != PB200_ADJ_MASK && p->adjacent_mode != PB200_ADJ_IGNORE &&
+        p->adjacent_mode != PB200_ADJ_COVER)
+        return fail(PB200_E_BAD_MODE, "ERROR mask adjacent to cloud/cloud-shadow mode: %d", p->adjacent_mode);
+    if (fused && p->adjacent_mode == PB200_ADJ_COVER)
+        return fail(PB200_E_UNSUPPORTED,
+                    "mask_adjacent_to_cloud_mode 'cover' (masked dilation, D:2055-2078) is not part of the fused pass");
+    int rc = derive_thresholds(p->th, D);
+    if (rc) return rc;
+    for (int k = 0; k < 6; ++k) D->band_fill[k] = p->band_fill[k];
+    D->fmask_fill = p->fmask_fill;
+    D->flags = (p->apply_aerosol_class_remapping ? PF_AEROSOL : 0u) | (p->collapse_wtr_classes ? PF_COLLAPSE : 0u) |
+               (p->class_histogram ? PF_HISTOGRAM : 0u);
+    D->dxf = (float)p->pixel_spacing_x;
+    D->dyf = -std::fabs((float)p->pixel_spacing_y);
+    double c, t;
+    pb200_angle_thresholds(p, &c, &t);
+    D->cos_thr = c;
+    D->tan_thr = t;
+    const int mode = p->adjacent_mode == PB200_ADJ_MASK ? 0 : 1;
+    for (uint32_t v = 0; v < 256; ++v) {
+        uint32_t e = preliminary_cloud(v, mode);
+        if (v & 16u) e |= 8u;
+        e |= (uint32_t)(p->aerosol_class_bits[v] & 0x1Du) << 4;
+        if ((int)v == p->fmask_fill) e |= 0x8000u;
+        D->fmask_lut[v] = (uint16_t)e;
+    }
+    for (uint32_t d = 0; d < 32; ++d) {
+        const uint32_t rep = (d & 1u) + ((d >> 1) & 1u) * 10u + ((d >> 2) & 1u) * 100u + ((d >> 3) & 1u) * 1000u +
+                             ((d >> 4) & 1u) * 10000u;
+        D->diag_lut[d] = rep | (interpreted_class(d) << 16);
+    }
+    const bool collapse = p->collapse_wtr_classes != 0;
+    for (uint32_t k = 0; k < 8; ++k) {
+        const uint32_t w2 = k < 5u ? k : (k == 5u ? 255u : 248u + k);
+        D->cls_lut[k] = (uint8_t)(collapse ? collapse_class(w2) : w2);
+        for (uint32_t c4 = 0; c4 < 16; ++c4) {
+            uint32_t wtr = cloud_masking(w2, c4);
+            const uint32_t bw = binary_water(wtr);
+            const uint32_t cf = confidence(w2, c4);
+            const uint32_t cl = (w2 == 255u) ? 255u : c4;
+            if (collapse) wtr = collapse_class(wtr);
+            D->out_lut[k * 16 + c4] = wtr | (bw << 8) | (cf << 16) | (cl << 24);
+        }
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct HostPipe {               // device mirror of one host tile (pb200_classify_host)
+    size_t cap_px = 0, cap_dem = 0;
+    int16_t *band[6] = {};
+    uint8_t *fmask = nullptr, *land = nullptr, *ocean = nullptr;
+    float *dem = nullptr;
+    uint16_t *diag = nullptr;
+    uint8_t *u8out[8] = {};
+    unsigned long long *counters = nullptr;
+    cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_k;
+};
+
+struct pb200_ctx {
+    int device = 0;
+    int sm_count = 0;
+    EncodeTiledFn encode = nullptr;
+    HostPipe pipe;
+    std::mutex mu;
+};
+
+struct pb200_plan {
+    pb200_ctx *ctx = nullptr;
+    DevParams P;
+    TileDev *d_tiles[2] = {nullptr, nullptr};        // [0] vectorised tiles, [1] generic tiles
+    CUtensorMap *d_maps[2] = {nullptr, nullptr};
+    int n[2] = {0, 0};
+    int max_ctas[2] = {0, 0};
+    bool stream_ordered = false;                     // allocated with cudaMallocAsync
+};
+
+extern "C" int pb200_ctx_create(int device, pb200_ctx **out) {
+    if (!out) return fail(PB200_E_INVALID_ARG, "pb200_ctx_create: null output");
+    *out = nullptr;
+    int n = 0;
+    CK(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return fail(PB200_E_INVALID_ARG, "pb200_ctx_create: device %d of %d", device, n);
+    CK(cudaSetDevice(device));
+    CK(cudaFree(0));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(PB200_E_UNSUPPORTED, "pb200_ctx_create: device %d is sm_%d%d; this library is sm_100a only", device,
+                    prop.major, prop.minor);
+    pb200_ctx *c = new pb200_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        delete c;
+        return fail(PB200_E_NO_DRIVER_API, "cuTensorMapEncodeTiled not available from the driver");
+    }
+    c->encode = (EncodeTiledFn)fn;
+    *out = c;
+    return 0;
+}
+
+static void pipe_free(HostPipe &p) {
+    for (auto &b : p.band) { cudaFree(b); b = nullptr; }
+    cudaFree(p.fmask); cudaFree(p.land); cudaFree(p.ocean); cudaFree(p.dem); cudaFree(p.diag);
+    p.fmask = p.land = p.ocean = nullptr; p.dem = nullptr; p.diag = nullptr;
+    for (auto &b : p.u8out) { cudaFree(b); b = nullptr; }
+    p.cap_px = p.cap_dem = 0;
+}
+
+extern "C" int pb200_ctx_destroy(pb200_ctx *ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    HostPipe &p = ctx->pipe;
+    pipe_free(p);
+    cudaFree(p.counters);
+    if (p.s_in) cudaStreamDestroy(p.s_in);
+    if (p.s_k) cudaStreamDestroy(p.s_k);
+    if (p.s_out) cudaStreamDestroy(p.s_out);
+    for (auto e : p.ev_in) cudaEventDestroy(e);
+    for (auto e : p.ev_k) cudaEventDestroy(e);
+    delete ctx;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// tile descriptors
+// ---------------------------------------------------------------------------
+static bool aligned(const void *p, size_t a) { return p == nullptr || ((uintptr_t)p % a) == 0; }
+
+static void sun_terms(const pb200_tile &t, TileDev *d) {
+    if (!std::isnan(t.sun_terms[0])) {
+        d->sx = t.sun_terms[0]; d->sy = t.sun_terms[1]; d->sz = t.sun_terms[2];
+        d->sin_az = t.sun_terms[3]; d->cos_az = t.sun_terms[4];
+        return;
+    }
+    const double deg2rad = 3.14159265358979323846 / 180.0;          // np.radians: x * (pi / 180)
+    const double az = t.sun_azimuth * deg2rad;                       // D:4245
+    const double zen = (90 - t.sun_elevation) * deg2rad;             // D:4246-4247
+    d->sx = std::sin(az) * std::sin(zen);                            // D:4250-4252
+    d->sy = std::cos(az) * std::sin(zen);
+    d->sz = std::cos(zen);
+    d->sin_az = std::sin(az);                                        // D:4276-4277
+    d->cos_az = std::cos(az);
+}
+
+static int make_tile_dev(pb200_ctx *ctx, const pb200_tile &t, int index, TileDev *d, CUtensorMap *map) {
+    std::memset(d, 0, sizeof(*d));
+    if (t.height <= 0 || t.width <= 0)
+        return fail(PB200_E_INVALID_ARG, "tile %d: empty raster %d x %d", index, t.height, t.width);
+    for (int k = 0; k < 6; ++k) {
+        if (!t.band[k]) return fail(PB200_E_INVALID_ARG, "tile %d: band %d is NULL", index, k);
+        if (!aligned(t.band[k], 2)) return fail(PB200_E_ALIGNMENT, "tile %d: band %d not 2-byte aligned", index, k);
+        d->band[k] = t.band[k];
+    }
+    if (!t.fmask) return fail(PB200_E_INVALID_ARG, "tile %d: fmask is NULL", index);
+    d->fmask = t.fmask; d->dem = t.dem; d->land = t.land; d->ocean = t.ocean;
+    d->diag = t.diag; d->wtr1 = t.wtr1; d->wtr1r = t.wtr1_remapped; d->wtr2 = t.wtr2; d->cloud = t.cloud;
+    d->shad = t.shad; d->wtr = t.wtr; d->bwtr = t.bwtr; d->conf = t.conf;
+    d->counters = (unsigned long long *)t.counters;
+    d->height = t.height; d->width = t.width;
+    d->tiles_x = (t.width + TW - 1) / TW;
+    d->n_ctas = d->tiles_x * ((t.height + TH - 1) / TH);
+    if (!aligned(t.diag, 2) || !aligned(t.counters, 8))
+        return fail(PB200_E_ALIGNMENT, "tile %d: diag / counters misaligned", index);
+    if (t.shad && !t.dem) return fail(PB200_E_INVALID_ARG, "tile %d: SHAD output requested without a DEM", index);
+    if (t.dem) {
+        if (!aligned(t.dem, 4)) return fail(PB200_E_ALIGNMENT, "tile %d: dem not 4-byte aligned", index);
+        if (t.dem_off_y < 1 || t.dem_off_x < 1 || t.dem_off_y + t.height + 1 > t.dem_rows ||
+            t.dem_off_x + t.width + 1 > t.dem_pitch)
+            return fail(PB200_E_INVALID_ARG,
+                        "tile %d: the DEM (%d rows x %d, offset %d,%d) must cover the %d x %d tile plus one element on "
+                        "every side",
+                        index, t.dem_rows, t.dem_pitch, t.dem_off_y, t.dem_off_x, t.height, t.width);
+        d->dem_pitch = t.dem_pitch; d->dem_rows = t.dem_rows; d->dem_off_y = t.dem_off_y; d->dem_off_x = t.dem_off_x;
+        sun_terms(t, d);
+    }
+    // vector path: 8-B band loads, 4-B byte-raster loads/stores, 8-B DIAG stores on every row
+    bool vec = (t.width % 4) == 0 && aligned(t.fmask, 4) && aligned(t.land, 4) && aligned(t.ocean, 4) &&
+               aligned(t.diag, 8) && aligned(t.wtr1, 4) && aligned(t.wtr1_remapped, 4) && aligned(t.wtr2, 4) &&
+               aligned(t.cloud, 4) && aligned(t.shad, 4) && aligned(t.wtr, 4) && aligned(t.bwtr, 4) &&
+               aligned(t.conf, 4);
+    for (int k = 0; k < 6; ++k) vec = vec && aligned(t.band[k], 8);
+    if (vec) d->flags |= TF_VEC;
+    // TMA needs a 16-B aligned base and a row pitch that is a multiple of 16 B
+    if (t.dem && aligned(t.dem, 16) && (t.dem_pitch % 4) == 0) {
+        const cuuint64_t gdim[2] = {(cuuint64_t)t.dem_pitch, (cuuint64_t)t.dem_rows};
+        const cuuint64_t gstr[1] = {(cuuint64_t)t.dem_pitch * sizeof(float)};
+        const cuuint32_t box[2] = {(cuuint32_t)SMW, (cuuint32_t)SMH};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = ctx->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)t.dem, gdim, gstr, box, estr,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS) d->flags |= TF_TMA;
+    }
+    return 0;
+}
+
+static int plan_build(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles, const pb200_params *params,
+                      pb200_plan *pl, cudaStream_t stream, bool stream_ordered) {
+    if (!ctx || !tiles || n_tiles <= 0 || !params)
+        return fail(PB200_E_INVALID_ARG, "classify: null argument or n_tiles <= 0");
+    if (n_tiles > 65535) return fail(PB200_E_INVALID_ARG, "classify: at most 65535 tiles per launch");
+    int rc = derive_params(params, &pl->P, true);
+    if (rc) return rc;
+    pl->ctx = ctx;
+    pl->stream_ordered = stream_ordered;
+    std::vector<TileDev> td[2];
+    std::vector<CUtensorMap> tm[2];
+    for (int i = 0; i < n_tiles; ++i) {
+        TileDev d;
+        alignas(64) CUtensorMap m;
+        std::memset(&m, 0, sizeof(m));
+        rc = make_tile_dev(ctx, tiles[i], i, &d, &m);
+        if (rc) return rc;
+        const int g = (d.flags & TF_VEC) ? 0 : 1;
+        td[g].push_back(d);
+        tm[g].push_back(m);
+        pl->max_ctas[g] = std::max(pl->max_ctas[g], d.n_ctas);
+    }
+    CK(cudaSetDevice(ctx->device));
+    for (int g = 0; g < 2; ++g) {
+        pl->n[g] = (int)td[g].size();
+        if (!pl->n[g]) continue;
+        const size_t bt = td[g].size() * sizeof(TileDev), bm = tm[g].size() * sizeof(CUtensorMap);
+        if (stream_ordered) {
+            CK(cudaMallocAsync((void **)&pl->d_tiles[g], bt, stream));
+            CK(cudaMallocAsync((void **)&pl->d_maps[g], bm, stream));
+        } else {
+            CK(cudaMalloc((void **)&pl->d_tiles[g], bt));
+            CK(cudaMalloc((void **)&pl->d_maps[g], bm));
+        }
+        // pageable source: the copy is staged before the call returns
+        CK(cudaMemcpyAsync(pl->d_tiles[g], td[g].data(), bt, cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(pl->d_maps[g], tm[g].data(), bm, cudaMemcpyHostToDevice, stream));
+    }
+    return 0;
+}
+
+static int plan_launch(pb200_plan *pl, cudaStream_t stream) {
+    if (pl->n[0]) {
+        dim3 grid(pl->max_ctas[0], pl->n[0]);
+        dswx_fused_kernel<true><<<grid, NTHREADS, 0, stream>>>(pl->d_tiles[0], pl->d_maps[0], pl->P);
+    }
+    if (pl->n[1]) {
+        dim3 grid(pl->max_ctas[1], pl->n[1]);
+        dswx_fused_kernel<false><<<grid, NTHREADS, 0, stream>>>(pl->d_tiles[1], pl->d_maps[1], pl->P);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static void plan_release(pb200_plan *pl, cudaStream_t stream) {
+    for (int g = 0; g < 2; ++g) {
+        if (pl->stream_ordered) {
+            if (pl->d_tiles[g]) cudaFreeAsync(pl->d_tiles[g], stream);
+            if (pl->d_maps[g]) cudaFreeAsync(pl->d_maps[g], stream);
+        } else {
+            cudaFree(pl->d_tiles[g]);
+            cudaFree(pl->d_maps[g]);
+        }
+        pl->d_tiles[g] = nullptr;
+        pl->d_maps[g] = nullptr;
+    }
+}
+
+extern "C" int pb200_classify(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles, const pb200_params *params,
+                              void *stream) {
+    pb200_plan pl;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = plan_build(ctx, tiles, n_tiles, params, &pl, st, true);
+    if (rc == 0) rc = plan_launch(&pl, st);
+    plan_release(&pl, st);
+    return rc;
+}
+
+extern "C" int pb200_plan_create(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles, const pb200_params *params,
+                                 pb200_plan **out) {
+    if (!out) return fail(PB200_E_INVALID_ARG, "pb200_plan_create: null output");
+    *out = nullptr;
+    pb200_plan *pl = new pb200_plan();
+    int rc = plan_build(ctx, tiles, n_tiles, params, pl, nullptr, false);
+    if (rc == 0) {
+        cudaError_t e = cudaStreamSynchronize(nullptr);
+        if (e != cudaSuccess) rc = fail_cuda(e, "plan upload");
+    }
+    if (rc) {
+        plan_release(pl, nullptr);
+        delete pl;
+        return rc;
+    }
+    *out = pl;
+    return 0;
+}
+extern "C" int pb200_plan_run(pb200_plan *plan, void *stream) {
+    if (!plan) return fail(PB200_E_INVALID_ARG, "pb200_plan_run: null plan");
+    return plan_launch(plan, (cudaStream_t)stream);
+}
+extern "C" int pb200_plan_destroy(pb200_plan *plan) {
+    if (!plan) return 0;
+    cudaSetDevice(plan->ctx->device);
+    plan_release(plan, nullptr);
+    delete plan;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// host-buffer entry point: H2D / kernel / D2H overlapped over row strips
+// ---------------------------------------------------------------------------
+extern "C" int pb200_host_alloc(size_t bytes, void **out) {
+    if (!out) return fail(PB200_E_INVALID_ARG, "pb200_host_alloc: null output");
+    CK(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return 0;
+}
+extern "C" int pb200_host_free(void *p) {
+    if (p) CK(cudaFreeHost(p));
+    return 0;
+}
+
+static int pipe_reserve(HostPipe &p, size_t px, size_t dem_elems) {
+    if (!p.s_in) {
+        CK(cudaStreamCreateWithFlags(&p.s_in, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&p.s_k, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&p.s_out, cudaStreamNonBlocking));
+        CK(cudaMalloc((void **)&p.counters, PB200_N_COUNTERS * sizeof(unsigned long long)));
+    }
+    if (px > p.cap_px) {
+        for (auto &b : p.band) { cudaFree(b); b = nullptr; }
+        cudaFree(p.fmask); cudaFree(p.land); cudaFree(p.ocean); cudaFree(p.diag);
+        for (auto &b : p.u8out) { cudaFree(b); b = nullptr; }
+        for (auto &b : p.band) CK(cudaMalloc((void **)&b, px * 2));
+        CK(cudaMalloc((void **)&p.fmask, px));
+        CK(cudaMalloc((void **)&p.land, px));
+        CK(cudaMalloc((void **)&p.ocean, px));
+        CK(cudaMalloc((void **)&p.diag, px * 2));
+        for (auto &b : p.u8out) CK(cudaMalloc((void **)&b, px));
+        p.cap_px = px;
+    }
+    if (dem_elems > p.cap_dem) {
+        cudaFree(p.dem);
+        p.dem = nullptr;
+        CK(cudaMalloc((void **)&p.dem, dem_elems * 4));
+        p.cap_dem = dem_elems;
+    }
+    return 0;
+}
+
+extern "C" int pb200_classify_host(pb200_ctx *ctx, const pb200_tile *ht, const pb200_params *params,
+                                   int strip_rows) {
+    if (!ctx || !ht || !params) return fail(PB200_E_INVALID_ARG, "pb200_classify_host: null argument");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    const int H = ht->height, W = ht->width;
+    if (H <= 0 || W <= 0) return fail(PB200_E_INVALID_ARG, "pb200_classify_host: empty raster");
+    if (strip_rows <= 0) strip_rows = 8 * TH;
+    strip_rows = ((strip_rows + TH - 1) / TH) * TH;
+    const size_t px = (size_t)H * W;
+    const size_t dem_elems = ht->dem ? (size_t)ht->dem_rows * ht->dem_pitch : 0;
+    HostPipe &p = ctx->pipe;
+    int rc = pipe_reserve(p, px, dem_elems);
+    if (rc) return rc;
+    const int n_strips = (H + strip_rows - 1) / strip_rows;
+    while ((int)p.ev_in.size() < n_strips) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        p.ev_in.push_back(e);
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        p.ev_k.push_back(e);
+    }
+    // validate once with a whole-tile descriptor on the device mirror
+    pb200_tile dt = *ht;
+    for (int k = 0; k < 6; ++k) dt.band[k] = p.band[k];
+    dt.fmask = p.fmask;
+    dt.land = ht->land ? p.land : nullptr;
+    dt.ocean = ht->ocean ? p.ocean : nullptr;
+    dt.dem = ht->dem ? p.dem : nullptr;
+    dt.diag = ht->diag ? p.diag : nullptr;
+    uint8_t *const host_u8[8] = {ht->wtr1, ht->wtr1_remapped, ht->wtr2, ht->cloud, ht->shad, ht->wtr, ht->bwtr, ht->conf};
+    uint8_t **dev_u8_field[8] = {&dt.wtr1, &dt.wtr1_remapped, &dt.wtr2, &dt.cloud, &dt.shad, &dt.wtr, &dt.bwtr, &dt.conf};
+    for (int i = 0; i < 8; ++i) *dev_u8_field[i] = host_u8[i] ? p.u8out[i] : nullptr;
+    dt.counters = ht->counters ? (uint64_t *)p.counters : nullptr;
+    DevParams P;
+    rc = derive_params(params, &P, true);
+    if (rc) return rc;
+    if (dt.counters) CK(cudaMemsetAsync(p.counters, 0, PB200_N_COUNTERS * sizeof(unsigned long long), p.s_k));
+
+    std::vector<pb200_plan> plans(n_strips);
+    int dem_copied = 0;                 // DEM rows [.., dem_copied) are on the device
+    bool first_dem = true;
+    for (int sidx = 0; sidx < n_strips; ++sidx) {
+        const int r0 = sidx * strip_rows, r1 = std::min(H, r0 + strip_rows), nr = r1 - r0;
+        const size_t off = (size_t)r0 * W, cnt = (size_t)nr * W;
+        // ---- H2D ------------------------------------------------------------
+        for (int k = 0; k < 6; ++k)
+            CK(cudaMemcpyAsync(p.band[k] + off, ht->band[k] + off, cnt * 2, cudaMemcpyHostToDevice, p.s_in));
+        CK(cudaMemcpyAsync(p.fmask + off, ht->fmask + off, cnt, cudaMemcpyHostToDevice, p.s_in));
+        if (ht->land) CK(cudaMemcpyAsync(p.land + off, ht->land + off, cnt, cudaMemcpyHostToDevice, p.s_in));
+        if (ht->ocean) CK(cudaMemcpyAsync(p.ocean + off, ht->ocean + off, cnt, cudaMemcpyHostToDevice, p.s_in));
+        if (ht->dem) {
+            int d0 = ht->dem_off_y + r0 - 1, d1 = ht->dem_off_y + r1 + 1;     // rows the strip's stencil reads
+            if (!first_dem) d0 = std::max(d0, dem_copied);
+            d0 = std::max(d0, 0);
+            d1 = std::min(d1, ht->dem_rows);
+            if (d1 > d0)
+                CK(cudaMemcpyAsync(p.dem + (size_t)d0 * ht->dem_pitch, ht->dem + (size_t)d0 * ht->dem_pitch,
+                                   (size_t)(d1 - d0) * ht->dem_pitch * 4, cudaMemcpyHostToDevice, p.s_in));
+            dem_copied = d1;
+            first_dem = false;
+        }
+        CK(cudaEventRecord(p.ev_in[sidx], p.s_in));
+        // ---- kernel on the strip -------------------------------------------
+        pb200_tile st = dt;
+        st.height = nr;
+        for (int k = 0; k < 6; ++k) st.band[k] = dt.band[k] + off;
+        st.fmask = dt.fmask + off;
+        if (st.land) st.land = dt.land + off;
+        if (st.ocean) st.ocean = dt.ocean + off;
+        st.dem_off_y = dt.dem_off_y + r0;
+        if (st.diag) st.diag = dt.diag + off;
+        uint8_t **sf[8] = {&st.wtr1, &st.wtr1_remapped, &st.wtr2, &st.cloud, &st.shad, &st.wtr, &st.bwtr, &st.conf};
+        for (int i = 0; i < 8; ++i)
+            if (*sf[i]) *sf[i] += off;
+        CK(cudaStreamWaitEvent(p.s_k, p.ev_in[sidx], 0));
+        rc = plan_build(ctx, &st, 1, params, &plans[sidx], p.s_k, true);
+        if (rc == 0) rc = plan_launch(&plans[sidx], p.s_k);
+        plan_release(&plans[sidx], p.s_k);
+        if (rc) { cudaDeviceSynchronize(); return rc; }
+        CK(cudaEventRecord(p.ev_k[sidx], p.s_k));
+        // ---- D2H --------------------------------------------------------------
+        CK(cudaStreamWaitEvent(p.s_out, p.ev_k[sidx], 0));
+        if (ht->diag) CK(cudaMemcpyAsync(ht->diag + off, p.diag + off, cnt * 2, cudaMemcpyDeviceToHost, p.s_out));
+        for (int i = 0; i < 8; ++i)
+            if (host_u8[i])
+                CK(cudaMemcpyAsync(host_u8[i] + off, p.u8out[i] + off, cnt, cudaMemcpyDeviceToHost, p.s_out));
+    }
+    if (ht->counters)
+        CK(cudaMemcpyAsync(ht->counters, p.counters, PB200_N_COUNTERS * sizeof(unsigned long long),
+                           cudaMemcpyDeviceToHost, p.s_out));
+    CK(cudaStreamSynchronize(p.s_out));
+    CK(cudaStreamSynchronize(p.s_k));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// function-granular entry points
+// ---------------------------------------------------------------------------
+static int grid_for(pb200_ctx *ctx, long long n, int block) {
+    long long g = (n + block - 1) / block;
+    const long long cap = (long long)ctx->sm_count * 16;
+    return (int)std::max(1LL, std::min(g, cap));
+}
+#define REQUIRE(cond, ...) \
+    do { if (!(cond)) return fail(PB200_E_INVALID_ARG, __VA_ARGS__); } while (0)
+#define ENTER(ctx)                                         \
+    REQUIRE(ctx != nullptr, "%s: null context", __func__); \
+    CK(cudaSetDevice(ctx->device));                        \
+    cudaStream_t st = (cudaStream_t)stream
+#define LEAVE() CK(cudaGetLastError()); return 0
+#define EMPTY_OK(n) do { if ((n) == 0) return 0; } while (0)
+
+extern "C" int pb200_invalid_and_clip(pb200_ctx *ctx, const int16_t *const raw[6], const uint8_t *fmask,
+                                      const pb200_params *params, int64_t n, int16_t *const clipped[6],
+                                      uint8_t *invalid, void *stream) {
+    ENTER(ctx);
+    EMPTY_OK(n);
+    REQUIRE(raw && params && n >= 0, "pb200_invalid_and_clip: bad argument");
+    if (n == 0) return 0;
+    DevParams P;
+    std::memset(&P, 0, sizeof(P));
+    for (int k = 0; k < 6; ++k) P.band_fill[k] = params->band_fill[k];
+    P.fmask_fill = params->fmask_fill;
+    BandPtrs in; BandOutPtrs out;
+    for (int k = 0; k < 6; ++k) {
+        REQUIRE(raw[k], "pb200_invalid_and_clip: band %d is NULL", k);
+        in.p[k] = raw[k];
+        out.p[k] = clipped ? clipped[k] : nullptr;
+    }
+    invalid_and_clip_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(in, fmask, out, invalid, n, P);
+    LEAVE();
+}
+
+extern "C" int pb200_diagnostic_tests(pb200_ctx *ctx, const int16_t *const band[6], const pb200_thresholds *th,
+                                      int64_t n, uint16_t *diag, void *stream) {
+    ENTER(ctx);
+    EMPTY_OK(n);
+    REQUIRE(band && th && diag && n >= 0, "pb200_diagnostic_tests: bad argument");
+    if (n == 0) return 0;
+    DevParams P;
+    std::memset(&P, 0, sizeof(P));
+    int rc = derive_thresholds(*th, &P);
+    if (rc) return rc;
+    BandPtrs in;
+    for (int k = 0; k < 6; ++k) {
+        REQUIRE(band[k], "pb200_diagnostic_tests: band %d is NULL", k);
+        in.p[k] = band[k];
+    }
+    diagnostic_tests_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(in, diag, n, P);
+    LEAVE();
+}
+
+extern "C" int pb200_interpreted_layer(pb200_ctx *ctx, const uint16_t *diag, int64_t n, uint8_t *wtr1, void *stream) {
+    ENTER(ctx);
+    EMPTY_OK(n);
+    REQUIRE(diag && wtr1 && n >= 0, "pb200_interpreted_layer: bad argument");
+    if (n == 0) return 0;
+    interpreted_layer_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(diag, wtr1, n);
+    LEAVE();
+}
+
+extern "C" int pb200_binary_representation(pb200_ctx *ctx, const uint16_t *diag, int64_t n, uint16_t *out,
+                                           void *stream) {
+    ENTER(ctx);
+    EMPTY_OK(n);
+    REQUIRE(diag && out && n >= 0, "pb200_binary_representation: bad argument");
+    if (n == 0) return 0;
+    binary_representation_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(diag, out, n);
+    LEAVE();
+}
+
+static int check_mode(int mode) {
+    if (mode != PB200_ADJ_MASK && mode != PB200_ADJ_IGNORE && mode != PB200_ADJ_COVER)
+        return fail(PB200_E_BAD_MODE, "ERROR mask adjacent to cloud/cloud-shadow mode: %d", mode);
+    return 0;
+}
+
+extern "C" int pb200_preliminary_cloud(pb200_ctx *ctx, const uint8_t *fmask, int mode, int64_t n, uint8_t *cloud,
+                                       void *stream) {
+    ENTER(ctx);
+    int rc = check_mode(mode);
+    if (rc) return rc;
+    EMPTY_OK(n);
+    REQUIRE(fmask && cloud && n >= 0, "pb200_preliminary_cloud: bad argument");
+    if (n == 0) return 0;
+    preliminary_cloud_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(fmask, cloud, mode == PB200_ADJ_MASK ? 0 : 1, n);
+    LEAVE();
+}
+
+extern "C" int pb200_aerosol_remap(pb200_ctx *ctx, uint8_t *wtr1, const int16_t *nir, uint8_t *cloud,
+                                   const uint8_t *fmask, const uint8_t bits[256], int64_t n, void *stream) {
+    ENTER(ctx);
+    EMPTY_OK(n);
+    REQUIRE(wtr1 && nir && cloud && fmask && bits && n >= 0, "pb200_aerosol_remap: bad argument");
+    if (n == 0) return 0;
+    AerosolBits ab;
+    for (int i = 0; i < 64; ++i)
+        ab.w[i] = (uint32_t)(bits[4 * i] & 0x1D) | ((uint32_t)(bits[4 * i + 1] & 0x1D) << 8) |
+                  ((uint32_t)(bits[4 * i + 2] & 0x1D) << 16) | ((uint32_t)(bits[4 * i + 3] & 0x1D) << 24);
+    aerosol_remap_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(wtr1, nir, cloud, fmask, ab, n);
+    LEAVE();
+}
+
+extern "C" int pb200_landcover_shadow_masks(pb200_ctx *ctx, const uint8_t *wtr1, const int16_t *nir,
+                                            const uint8_t *land, const uint8_t *shad, double lcmask_nir, int64_t n,
+                                            uint8_t *wtr2, void *stream) {
+    ENTER(ctx);
+    EMPTY_OK(n);
+    REQUIRE(wtr1 && wtr2 && n >= 0, "pb200_landcover_shadow_masks: bad argument");
+    REQUIRE(nir || !land, "pb200_landcover_shadow_masks: nir is required with a land-cover raster");
+    if (n == 0) return 0;
+    landcover_shadow_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(wtr1, nir ? nir : (const int16_t *)wtr1, land,
+                                                                    shad, gt_threshold(lcmask_nir), wtr2, n);
+    LEAVE();
+}
+
+extern "C" int pb200_snow_to_cloud(pb200_ctx *ctx, const uint8_t *wtr2, uint8_t *cloud, const uint8_t *fmask,
+                                   int mode, int64_t n, void *stream) {
+    ENTER(ctx);
+    int rc = check_mode(mode);
+    if (rc) return rc;
+    EMPTY_OK(n);
+    if (mode == PB200_ADJ_COVER)
+        return fail(PB200_E_UNSUPPORTED, "pb200_snow_to_cloud: 'cover' dilation (D:2055-2078) not implemented yet");
+    REQUIRE(wtr2 && cloud && fmask && n >= 0, "pb200_snow_to_cloud: bad argument");
+    if (n == 0) return 0;
+    snow_to_cloud_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(wtr2, cloud, fmask, n);
+    LEAVE();
+}
+
+extern "C" int pb200_cloud_masking(pb200_ctx *ctx, const uint8_t *wtr2, const uint8_t *cloud, int64_t n,
+                                   uint8_t *wtr, void *stream) {
+    ENTER(ctx);
+    EMPTY_OK(n);
+    REQUIRE(wtr2 && cloud && wtr && n >= 0, "pb200_cloud_masking: bad argument");
+    if (n == 0) return 0;
+    cloud_masking_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(wtr2, cloud, wtr, n);
+    LEAVE();
+}
+extern "C" int pb200_binary_water(pb200_ctx *ctx, const uint8_t *wtr, int64_t n, uint8_t *bwtr, void *stream) {
+    ENTER(ctx);
+    EMPTY_OK(n);
+    REQUIRE(wtr && bwtr && n >= 0, "pb200_binary_water: bad argument");
+    if (n == 0) return 0;
+    binary_water_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(wtr, bwtr, n);
+    LEAVE();
+}
+extern "C" int pb200_confidence(pb200_ctx *ctx, const uint8_t *wtr2, const uint8_t *cloud, int64_t n, uint8_t *conf,
+                                void *stream) {
+    ENTER(ctx);
+    EMPTY_OK(n);
+    REQUIRE(wtr2 && cloud && conf && n >= 0, "pb200_confidence: bad argument");
+    if (n == 0) return 0;
+    confidence_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(wtr2, cloud, conf, n);
+    LEAVE();
+}
+extern "C" int pb200_collapse(pb200_ctx *ctx, const uint8_t *layer, int64_t n, uint8_t *out, void *stream) {
+    ENTER(ctx);
+    EMPTY_OK(n);
+    REQUIRE(layer && out && n >= 0, "pb200_collapse: bad argument");
+    if (n == 0) return 0;
+    collapse_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(layer, out, n);
+    LEAVE();
+}
+
+extern "C" int pb200_shadow(pb200_ctx *ctx, const float *dem, int rows, int cols, double sun_azimuth,
+                            double sun_elevation, const double *terms, const pb200_params *params, uint8_t *out,
+                            void *stream) {
+    ENTER(ctx);
+    REQUIRE(dem && out && params, "pb200_shadow: null argument");
+    // np.gradient needs at least 2 samples along every axis (ValueError otherwise)
+    REQUIRE(rows >= 2 && cols >= 2, "pb200_shadow: the DEM must be at least 2 x 2 (np.gradient, D:4255)");
+    DevParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.dxf = (float)params->pixel_spacing_x;
+    P.dyf = -std::fabs((float)params->pixel_spacing_y);
+    pb200_angle_thresholds(params, &P.cos_thr, &P.tan_thr);
+    pb200_tile t;
+    std::memset(&t, 0, sizeof(t));
+    t.sun_azimuth = sun_azimuth;
+    t.sun_elevation = sun_elevation;
+    t.sun_terms[0] = std::numeric_limits<double>::quiet_NaN();
+    if (terms)
+        for (int i = 0; i < 5; ++i) t.sun_terms[i] = terms[i];
+    TileDev d;
+    sun_terms(t, &d);
+    SunTerms S{d.sx, d.sy, d.sz, d.sin_az, d.cos_az};
+    dim3 block(64, 4), grid((cols + 63) / 64, (rows + 3) / 4);
+    shadow_kernel<<<grid, block, 0, st>>>(dem, rows, cols, out, S, P);
+    LEAVE();
+}
+
+extern "C" int pb200_ratio_sweep(pb200_ctx *ctx, double t, int is_less, uint64_t *mismatches) {
+    REQUIRE(ctx && mismatches, "pb200_ratio_sweep: null argument");
+    CK(cudaSetDevice(ctx->device));
+    int32_t a, b;
+    int rc = pb200_ratio_bound(t, is_less, &a, &b);
+    if (rc) return rc;
+    unsigned long long *d = nullptr;
+    CK(cudaMalloc((void **)&d, 8));
+    CK(cudaMemset(d, 0, 8));
+    ratio_sweep_kernel<<<65536, 256>>>(a, b, t, is_less, d);
+    cudaError_t e = cudaMemcpy(mismatches, d, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail_cuda(e, "pb200_ratio_sweep");
+    return 0;
+}

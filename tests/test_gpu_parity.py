@@ -1,0 +1,301 @@
+"""GPU parity: the CUDA path (through the C ABI) against the committed
+reference fixtures and against the CPU oracle on seeded inputs.
+
+Bar: bit-exact (np.array_equal) on every uint8 / uint16 layer and on the three
+coverage counters - the reference's own comparison rule for integer layers
+(compare_dswx_hls_products, dswx_hls.py:753-755)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import dswx_oracle as O
+from proteus_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+GPU_CASES = ('full_default', 'full_adversarial', 'ignore_noaerosol',
+             'l30_minimal', 'ragged_adversarial', 'shadow_only')
+FUSED_LAYERS = ('DIAG', 'WTR1', 'WTR1_REMAPPED', 'WTR2', 'CLOUD', 'SHAD', 'WTR',
+                'BWTR', 'CONF')
+
+
+def _assert_layers(got, ref, names, what):
+    for name in names:
+        if name not in ref:
+            continue
+        g, r = got[name], ref[name]
+        assert g.dtype == r.dtype, (what, name, g.dtype, r.dtype)
+        if not np.array_equal(g, r):
+            bad = np.argwhere(g != r)
+            y, x = bad[0]
+            raise AssertionError(
+                f'{what}: layer {name}: {len(bad)} of {g.size} pixels differ; first at '
+                f'({y},{x}): got {g[y, x]}, reference {r[y, x]}')
+
+
+def _classify_host(pb, ins, collapse, **kw):
+    return pb.classify_tile(
+        ins['bands'], ins['fmask'], ins['dem'], ins['land'], ins['ocean'],
+        ins['sun_azimuth'], ins['sun_elevation'],
+        mask_adjacent_to_cloud_mode=ins['mode'],
+        apply_aerosol_class_remapping=ins['aerosol'],
+        collapse_wtr_classes=collapse, dem_margin=ins['dem_margin'], **kw)
+
+
+@pytest.mark.parametrize('case', GPU_CASES)
+def test_fused_host_path_matches_reference_fixture(pb, case):
+    ins, ref = load_golden(case)
+    got = _classify_host(pb, ins, collapse=False, class_histogram=True)
+    _assert_layers(got, ref, FUSED_LAYERS, case)
+    assert np.array_equal(got['counters'][:3], ref['counters'])
+    cov = got['coverage']
+    assert [cov['SPATIAL_COVERAGE'], cov['SPATIAL_COVERAGE_EXCLUDING_MASKED_OCEAN'],
+            cov['CLOUD_COVERAGE']] == ref['percentages'].tolist()
+    hist = np.bincount(ref['WTR'].ravel(), minlength=256)
+    assert [cov['class_histogram'][c] for c in (0, 1, 2, 3, 4, 252, 253, 254, 255)] == \
+        [int(hist[c]) for c in (0, 1, 2, 3, 4, 252, 253, 254, 255)]
+    # collapsed variants as saved by save_dswx_product (dswx_hls.py:2688-2689)
+    got_c = _classify_host(pb, ins, collapse=True)
+    for name, key in (('WTR', 'WTR_COLLAPSED'), ('WTR1', 'WTR1_COLLAPSED'), ('WTR2', 'WTR2_COLLAPSED')):
+        assert np.array_equal(got_c[name], ref[key]), (case, key)
+    for name in ('BWTR', 'CONF', 'DIAG', 'CLOUD'):
+        assert np.array_equal(got_c[name], ref[name]), (case, name)
+
+
+@pytest.mark.parametrize('case', GPU_CASES)
+def test_fused_device_path_matches_reference_fixture(pb, case):
+    import torch
+    ins, ref = load_golden(case)
+    dev = 'cuda'
+    tile = dict(bands=[torch.from_numpy(b).to(dev) for b in ins['bands']],
+                fmask=torch.from_numpy(ins['fmask']).to(dev),
+                dem=torch.from_numpy(ins['dem']).to(dev) if ins['dem'] is not None else None,
+                land=torch.from_numpy(ins['land']).to(dev) if ins['land'] is not None else None,
+                ocean=torch.from_numpy(ins['ocean']).to(dev) if ins['ocean'] is not None else None,
+                sun_azimuth=ins['sun_azimuth'], sun_elevation=ins['sun_elevation'],
+                dem_margin=ins['dem_margin'])
+    params = pb.make_params(mask_adjacent_to_cloud_mode=ins['mode'],
+                            apply_aerosol_class_remapping=ins['aerosol'],
+                            collapse_wtr_classes=False)
+    layers = [n for n in FUSED_LAYERS if n != 'SHAD' or ins['dem'] is not None]
+    plan = pb.Plan([tile, tile], params, layers)       # two descriptors, same inputs
+    plan.run()
+    for i in (0, 1):
+        got = plan.results(i)
+        _assert_layers(got, ref, FUSED_LAYERS, f'{case}[{i}]')
+        assert np.array_equal(got['counters'][:3], ref['counters'])
+    # a second run ADDS to the counters (documented contract)
+    plan.run()
+    assert np.array_equal(plan.results(0)['counters'][:3], 2 * ref['counters'])
+
+
+@pytest.mark.parametrize('seed,h,w,kw', [
+    (11, 96, 128, {}),                                       # vector path, exact tile multiple
+    (12, 70, 132, dict(with_ocean=False)),                   # W % 4 == 0, ragged tile edges
+    (13, 33, 129, dict(adversarial=True)),                   # generic path (W % 4 != 0)
+    (14, 1, 5, dict(adversarial=True, with_dem=False)),      # single row
+    (15, 130, 1, dict(with_land=False)),                     # single column
+    (16, 64, 260, dict(adversarial=True, with_land=False, with_ocean=False)),
+])
+def test_fused_matches_oracle_on_seeded_tiles(pb, seed, h, w, kw):
+    t = synth.make_tile(seed, h, w, **kw)
+    for mode, aerosol in (('mask', True), ('ignore', False)):
+        ref = O.reference_chain(t['bands'], t['fmask'], t['dem'], t['land'], t['ocean'],
+                                t['sun_azimuth'], t['sun_elevation'],
+                                processing=dict(mask_adjacent_to_cloud_mode=mode,
+                                                apply_aerosol_class_remapping=aerosol))
+        got = pb.classify_tile(t['bands'], t['fmask'], t['dem'], t['land'], t['ocean'],
+                               t['sun_azimuth'], t['sun_elevation'],
+                               mask_adjacent_to_cloud_mode=mode,
+                               apply_aerosol_class_remapping=aerosol,
+                               collapse_wtr_classes=False)
+        _assert_layers(got, ref, FUSED_LAYERS, f'seed {seed} {mode}')
+        assert np.array_equal(got['counters'][:3], ref['counters'])
+
+
+def test_non_default_thresholds_and_fills(pb):
+    """Thresholds that sit exactly on representable ratios (0.25, 1/3, 0.5),
+    non-integral band thresholds and a different fill value."""
+    t = synth.make_tile(21, 128, 256, adversarial=True)
+    # plant exact ratios: green=5, swir1=3 -> mndwi = 0.25 exactly
+    t['bands'][1][0, :64] = 5
+    t['bands'][4][0, :64] = 3
+    t['bands'][3][1, :64] = 2       # nir=2, red=1 -> ndvi = 1/3
+    t['bands'][2][1, :64] = 1
+    for b in t['bands']:
+        b[5, 5] = -32768
+    kw = dict(wigt=0.25, awgt=-0.25, pswt_1_mndwi=1 / 3, pswt_1_nir=1500.5,
+              pswt_1_swir1=899.99, pswt_1_ndvi=1 / 3, pswt_2_mndwi=-0.5,
+              pswt_2_blue=1000.0, pswt_2_nir=2500, pswt_2_swir1=3000,
+              pswt_2_swir2=1000, lcmask_nir=1199.5)
+    ref = O.reference_chain(t['bands'], t['fmask'], t['dem'], t['land'], t['ocean'],
+                            t['sun_azimuth'], t['sun_elevation'],
+                            thresholds=O.HlsThresholds(**kw), band_fill=-32768, fmask_fill=7)
+    got = pb.classify_tile(t['bands'], t['fmask'], t['dem'], t['land'], t['ocean'],
+                           t['sun_azimuth'], t['sun_elevation'],
+                           hls_thresholds=pb.HlsThresholds(**kw), band_fill=-32768,
+                           fmask_fill=7, collapse_wtr_classes=False)
+    _assert_layers(got, ref, FUSED_LAYERS, 'custom thresholds')
+    assert np.array_equal(got['counters'][:3], ref['counters'])
+
+
+@pytest.mark.parametrize('t,is_less', [(0.124, 0), (-0.44, 0), (-0.5, 0), (0.7, 1),
+                                       (0.0, 0), (0.25, 1), (1 / 3, 0), (-1.0, 1)])
+def test_ratio_test_exhaustive_int16_pairs(pb, t, is_less):
+    """All 2^32 (n, d) int16 pairs: the integer form of float64(n)/float64(d)
+    {>,<} t equals IEEE float64 division (incl. d == 0 -> inf / nan)."""
+    import ctypes as C
+    ctx = pb.get_context()
+    bad = C.c_uint64(123)
+    from proteus_b200 import _lib
+    _lib.check(ctx._lib.pb200_ratio_sweep(ctx.handle, float(t), int(is_less), C.byref(bad)))
+    assert bad.value == 0
+
+
+def test_device_division_matches_numpy_division():
+    """The sweep above trusts __ddiv_rn == numpy true_divide; spot-check that
+    link on the host side of the same inputs through the function-level kernel."""
+    import proteus_b200.dswx_hls as G
+    rng = np.random.default_rng(5)
+    bands = [rng.integers(-32768, 32768, (64, 1024), dtype=np.int16) for _ in range(6)]
+    bands[1][0, :32] = 0            # green = 0 and swir1 = 0 -> 0/0
+    bands[4][0, :32] = 0
+    bands[1][1, :32] = 7            # x/0
+    bands[4][1, :32] = -7
+    with np.errstate(all='ignore'):
+        ref = O.compute_diagnostic_tests(*bands, O.default_thresholds())
+    got = G._compute_diagnostic_tests(*bands, G.HlsThresholds())
+    assert got.dtype == np.uint16
+    assert np.array_equal(got, ref)
+
+
+def test_function_level_dropins_match_oracle(pb):
+    import proteus_b200.dswx_hls as G
+    rng = np.random.default_rng(9)
+    shape = (61, 257)
+    u8 = lambda: rng.integers(0, 256, shape, dtype=np.uint8)
+    fmask, land = u8(), u8()
+    wtr_vals = np.array([0, 1, 2, 3, 4, 254, 255, 9, 100, 252, 253], dtype=np.uint8)
+    wtr1 = wtr_vals[rng.integers(0, len(wtr_vals), shape)]
+    cloud_vals = np.array(list(range(16)) + [255, 254, 77], dtype=np.uint8)
+    cloud = cloud_vals[rng.integers(0, len(cloud_vals), shape)]
+    nir = rng.integers(-32768, 32768, shape, dtype=np.int16)
+    nir[::2] = rng.integers(900, 1300, nir[::2].shape, dtype=np.int16)
+    shad = rng.integers(0, 2, shape).astype(bool)
+    th = O.default_thresholds()
+    gth = G.HlsThresholds()
+
+    diag = rng.integers(0, 70, shape).astype(np.uint16)
+    assert np.array_equal(G.generate_interpreted_layer(diag), O.generate_interpreted_layer(diag))
+    big = rng.integers(-5, 200000, shape)
+    assert np.array_equal(G.generate_interpreted_layer(big), O.generate_interpreted_layer(big))
+    assert np.array_equal(G._get_binary_representation(diag), O.get_binary_representation(diag))
+    for mode in ('mask', 'ignore', 'cover'):
+        assert np.array_equal(G._compute_preliminary_cloud_layer(fmask, mode),
+                              O.compute_preliminary_cloud_layer(fmask, mode))
+    with pytest.raises(Exception, match='ERROR mask adjacent to cloud/cloud-shadow mode'):
+        G._compute_preliminary_cloud_layer(fmask, 'bogus')
+
+    lists = ([224, 160, 96], [224, 160, 96, 1], [224, 192, 160, 128, 96], [0, 255, 96])
+    w_ref, c_ref = wtr1.copy(), cloud.copy()
+    assert O.apply_aerosol_class_remapping(w_ref, nir, c_ref, fmask, *lists) is None
+    w_got, c_got = wtr1.copy(), cloud.copy()
+    assert G._apply_aerosol_class_remapping(w_got, nir, c_got, fmask, *lists) is None
+    assert np.array_equal(w_got, w_ref) and np.array_equal(c_got, c_ref)
+
+    for l, s in ((land, shad), (None, shad), (land, None), (None, None)):
+        assert np.array_equal(G._apply_landcover_and_shadow_masks(wtr1, nir, l, s, gth),
+                              O.apply_landcover_and_shadow_masks(wtr1, nir, l, s, th))
+    for mode in ('mask', 'ignore'):
+        c_ref = O.add_snow_to_cloud_layer(wtr1, cloud.copy(), fmask, mode)
+        c_in = cloud.copy()
+        c_got = G._add_snow_to_cloud_layer(wtr1, c_in, fmask, mode)
+        assert c_got is c_in and np.array_equal(c_got, c_ref)
+    with pytest.raises(NotImplementedError):
+        G._add_snow_to_cloud_layer(wtr1, cloud.copy(), fmask, 'cover')
+    assert np.array_equal(G._apply_cloud_masking(wtr1, cloud), O.apply_cloud_masking(wtr1, cloud))
+    assert np.array_equal(G._get_binary_water_layer(wtr1), O.get_binary_water_layer(wtr1))
+    assert np.array_equal(G._get_confidence_layer(wtr1, cloud), O.get_confidence_layer(wtr1, cloud))
+    allv = np.arange(256, dtype=np.uint8).reshape(16, 16)
+    assert np.array_equal(G._collapse_wtr_classes(allv), O.collapse_wtr_classes(allv))
+    # empty rasters
+    e = np.zeros((0, 7), np.uint8)
+    assert G._get_binary_water_layer(e).shape == (0, 7)
+
+
+def test_shadow_function_matches_oracle_including_borders(pb):
+    import proteus_b200.dswx_hls as G
+    for seed, shape, sigma in ((1, (90, 140), 400.0), (2, (2, 2), 50.0), (3, (3, 301), 900.0)):
+        rng = np.random.default_rng(seed)
+        dem = synth._smooth_field(rng, shape[0] + 8, shape[1] + 8, 12.0)[:shape[0], :shape[1]]
+        dem = np.ascontiguousarray(dem * np.float32(sigma), dtype=np.float32)
+        for az, el in ((150.0, 45.0), (10.0, 5.0), (359.0, 89.0)):
+            ref = O.compute_opera_shadow_layer(dem, az, el, -5, 40)
+            got = G._compute_opera_shadow_layer(dem, az, el, -5, 40)
+            assert got.dtype == np.bool_
+            assert np.array_equal(got, ref), (seed, az, el, int((got != ref).sum()))
+    # flat DEM, NaN and inf samples: NaN compares false -> "not shadow" 
+    dem = np.zeros((40, 40), np.float32)
+    dem[10, 10] = np.nan
+    dem[20, 20] = np.inf
+    dem[30, 5] = 1e30
+    with np.errstate(all='ignore'):
+        ref = O.compute_opera_shadow_layer(dem, 150.0, 45.0, -5, 40)
+    assert np.array_equal(G._compute_opera_shadow_layer(dem, 150.0, 45.0, -5, 40), ref)
+    with pytest.raises(NotImplementedError):
+        G._compute_opera_shadow_layer(dem.astype(np.float64), 150.0, 45.0, -5, 40)
+
+
+def test_error_paths(pb):
+    t = synth.make_tile(3, 32, 32)
+    with pytest.raises(Exception, match='ERROR mask adjacent to cloud/cloud-shadow mode'):
+        pb.classify_tile(t['bands'], t['fmask'], mask_adjacent_to_cloud_mode='nope')
+    from proteus_b200._lib import Pb200Error
+    with pytest.raises(Pb200Error, match='cover'):
+        pb.classify_tile(t['bands'], t['fmask'], mask_adjacent_to_cloud_mode='cover')
+    with pytest.raises(NotImplementedError):
+        pb.classify_tile([b.astype(np.float32) for b in t['bands']], t['fmask'])
+    with pytest.raises(ValueError):
+        pb.classify_tile(t['bands'], t['fmask'], t['dem'][:-1], dem_margin=50)
+    with pytest.raises(OverflowError):
+        pb.classify_tile(t['bands'], t['fmask'], hls_thresholds=pb.HlsThresholds(pswt_1_nir=40000))
+
+
+def test_full_size_tile_properties(pb):
+    """BASELINE config 2 size (3660 x 3660, full product) without running the
+    8 s/tile numpy chain: size-independent properties + exact parity on a
+    row band that the oracle can afford."""
+    t = synth.make_tile(0)
+    got = pb.classify_tile(t['bands'], t['fmask'], t['dem'], t['land'], t['ocean'],
+                           t['sun_azimuth'], t['sun_elevation'], collapse_wtr_classes=False,
+                           class_histogram=True)
+    h, w = t['fmask'].shape
+    # (1) exact parity on rows [1700, 1956) - the DEM window carries its own margin
+    r0, r1, m = 1700, 1956, t['dem_margin']
+    sub = dict(bands=[b[r0:r1] for b in t['bands']], fmask=t['fmask'][r0:r1],
+               dem=t['dem'][r0:r1 + 2 * m], land=t['land'][r0:r1], ocean=t['ocean'][r0:r1])
+    ref = O.reference_chain(sub['bands'], sub['fmask'], sub['dem'], sub['land'], sub['ocean'],
+                            t['sun_azimuth'], t['sun_elevation'])
+    for name in FUSED_LAYERS:
+        assert np.array_equal(got[name][r0:r1], ref[name]), name
+    # (2) idempotence / functional relations between whole layers
+    assert np.array_equal(O.get_binary_water_layer(got['WTR']), got['BWTR'])
+    assert np.array_equal(O.apply_cloud_masking(got['WTR2'], got['CLOUD']), got['WTR'])
+    assert np.array_equal(O.get_confidence_layer(got['WTR2'], got['CLOUD']), got['CONF'])
+    inv = got['DIAG'] == 65535
+    assert np.array_equal(inv, got['WTR'] == 255)
+    assert np.array_equal(got['CLOUD'] == 255, inv)
+    # (3) counters are a checksum of the layers
+    cov = got['coverage']
+    assert cov['n_not_ocean'] == int(t['ocean'].sum())
+    assert cov['n_valid'] == int((~inv & (t['ocean'] != 0)).sum())
+    hist = np.bincount(got['WTR'].ravel(), minlength=256)
+    assert sum(cov['class_histogram'].values()) == h * w
+    assert all(cov['class_histogram'][c] == hist[c] for c in cov['class_histogram'])
+    # (4) strip size must not change anything (host pipeline)
+    got2 = pb.classify_tile(t['bands'], t['fmask'], t['dem'], t['land'], t['ocean'],
+                            t['sun_azimuth'], t['sun_elevation'], collapse_wtr_classes=False,
+                            strip_rows=96, outputs=('WTR', 'CONF', 'DIAG', 'SHAD'))
+    for name in ('WTR', 'CONF', 'DIAG', 'SHAD'):
+        assert np.array_equal(got2[name], got[name]), name
+    assert np.array_equal(got2['counters'][:3], got['counters'][:3])

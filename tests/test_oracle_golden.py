@@ -1,0 +1,122 @@
+"""The CPU oracle against the reference's own vectors (no GPU).
+
+Pins oracle/dswx_oracle.py to (1) the reference's known-answer table
+(tests/test_dswx_hls_units.py:7-28 of the reference, exported to
+tests/golden/reference_tables.json) and (2) the outputs of the LIVE reference
+on seeded tiles (tests/golden/*.npz, made by oracle/make_golden.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, GOLDEN_DIR, load_golden
+from oracle import dswx_oracle as O
+
+LAYERS = ('DIAG', 'WTR1', 'WTR1_REMAPPED', 'WTR2', 'CLOUD', 'WTR', 'BWTR',
+          'CONF', 'WTR_COLLAPSED', 'WTR1_COLLAPSED', 'WTR2_COLLAPSED')
+
+
+def _tables():
+    with open(os.path.join(GOLDEN_DIR, 'reference_tables.json')) as f:
+        return json.load(f)
+
+
+def test_interpreted_layer_known_answers():
+    """Same construction as the reference's unit test: every key of
+    interpreted_dswx_band_dict plus an out-of-table value (111111)."""
+    table = {int(k): v for k, v in _tables()['interpreted_dswx_band_dict'].items()}
+    assert len(table) == 33
+    width = len(table) + 1
+    inp = np.full((1, width), 111111)
+    exp = np.full((1, width), 255)
+    for i, (k, v) in enumerate(table.items()):
+        inp[0, i] = k
+        exp[0, i] = v
+    out = O.generate_interpreted_layer(inp)
+    assert out.dtype == np.uint8
+    assert np.array_equal(out, exp)
+
+
+def test_collapse_table_and_defaults_match_reference():
+    t = _tables()
+    for k, v in t['collapse_wtr_classes_dict'].items():
+        assert O.COLLAPSE_LUT[int(k)] == v
+    others = [i for i in range(256) if str(i) not in t['collapse_wtr_classes_dict']]
+    assert np.all(O.COLLAPSE_LUT[others] == 255)
+    th = O.default_thresholds()
+    for k, v in t['hls_thresholds'].items():
+        assert getattr(th, k) == v
+    pr = O.default_processing()
+    for k, v in t['processing'].items():
+        assert pr[k] == v
+    assert O.AEROSOL_REMAPPING_MAX_NIR == t['constants']['AEROSOL_REMAPPING_MAX_NIR'] == 1000.0
+    assert O.DEM_MARGIN_IN_PIXELS == t['constants']['DEM_MARGIN_IN_PIXELS']
+
+
+@pytest.mark.parametrize('case', GOLDEN_CASES)
+def test_chain_matches_reference_fixture(case):
+    ins, ref = load_golden(case)
+    got = O.reference_chain(
+        ins['bands'], ins['fmask'], ins['dem'], ins['land'], ins['ocean'],
+        ins['sun_azimuth'], ins['sun_elevation'],
+        processing=dict(mask_adjacent_to_cloud_mode=ins['mode'],
+                        apply_aerosol_class_remapping=ins['aerosol']),
+        dem_margin=ins['dem_margin'])
+    for name in LAYERS + (('SHAD',) if ins['dem'] is not None else ()):
+        assert got[name].dtype == ref[name].dtype, name
+        assert np.array_equal(got[name], ref[name]), name
+    assert np.array_equal(got['counters'], ref['counters'])
+    assert np.array_equal(got['percentages'], ref['percentages'])
+
+
+@pytest.mark.parametrize('case', ('full_default', 'full_adversarial', 'shadow_only'))
+def test_functions_match_reference_fixture(case):
+    """Function-granular: feed each oracle function the reference's
+    intermediate layers."""
+    ins, ref = load_golden(case)
+    th = O.default_thresholds()
+    inv, clipped = O.invalid_mask_and_clip(ins['bands'], ins['fmask'])
+    assert np.array_equal(inv, ref['INVALID'])
+    diag = O.compute_diagnostic_tests(*clipped, th)
+    diag[inv] = 32
+    assert np.array_equal(diag, ref['DIAG_DECIMAL'])
+    assert np.array_equal(O.get_binary_representation(ref['DIAG_DECIMAL']), ref['DIAG'])
+    assert np.array_equal(O.compute_preliminary_cloud_layer(ins['fmask'], ins['mode']),
+                          ref['PRELIM_CLOUD'])
+    if ins['dem'] is not None:
+        shad_m = O.compute_opera_shadow_layer(ins['dem'], ins['sun_azimuth'],
+                                              ins['sun_elevation'], -5, 40)
+        assert shad_m.dtype == np.bool_
+        assert np.array_equal(shad_m.astype(np.uint8), ref['SHAD_WITH_MARGIN'])
+    shad = ref['SHAD'].astype(bool) if 'SHAD' in ref else None
+    w2 = O.apply_landcover_and_shadow_masks(ref['WTR1_REMAPPED'], clipped[3],
+                                            ins['land'], shad, th)
+    assert np.array_equal(w2, ref['WTR2'])
+    cloud = O.add_snow_to_cloud_layer(ref['WTR2'], ref['PRELIM_CLOUD_AFTER_AEROSOL'].copy(),
+                                      ins['fmask'], ins['mode'])
+    assert np.array_equal(cloud, ref['CLOUD'])
+    assert np.array_equal(O.apply_cloud_masking(ref['WTR2'], ref['CLOUD']), ref['WTR'])
+    assert np.array_equal(O.get_binary_water_layer(ref['WTR']), ref['BWTR'])
+    assert np.array_equal(O.get_confidence_layer(ref['WTR2'], ref['CLOUD']), ref['CONF'])
+
+
+def test_central_differences_equal_numpy_gradient():
+    rng = np.random.default_rng(3)
+    for dt in (np.float32, np.float64):
+        f = rng.normal(size=(37, 53)).astype(dt) * 100
+        g0, g1 = np.gradient(f)
+        assert np.array_equal(O._central_differences(f, 0), g0)
+        assert np.array_equal(O._central_differences(f, 1), g1)
+        assert O._central_differences(f, 0).dtype == dt
+
+
+def test_bad_adjacent_mode_raises_like_reference():
+    with pytest.raises(Exception, match='ERROR mask adjacent to cloud/cloud-shadow mode'):
+        O.compute_preliminary_cloud_layer(np.zeros((2, 2), np.uint8), 'bogus')
+
+
+def test_coverage_percentages_edge_cases():
+    assert O.coverage_percentages(0, 0, 0, 100) == (0, 0, 0)
+    assert O.coverage_percentages(99, 98, 100, 100) == (99, 99, 98)
+    assert O.coverage_percentages(1, 1, 3, 3) == (33, 33, 100)
