@@ -16,8 +16,13 @@ constexpr int TH = 32;             // rows per CTA tile        (8 warps x 4 rows
 constexpr int NTHREADS = 256;
 constexpr int NWARPS = NTHREADS / 32;
 constexpr int ROWS_PER_WARP = TH / NWARPS;
-constexpr int DEM_PADX = 4;        // left halo padded to 4 so a lane's centre quad is 16-B aligned
-constexpr int SMW = TW + 2 * DEM_PADX;   // 136 floats = 544 B (multiple of 16 B: TMA box rule)
+// The TMA box must START on a 16-byte boundary of the DEM row (measured on B200:
+// UTMALDG traps with "illegal instruction" when the inner coordinate is not a
+// multiple of 4 floats, scripts/tma_probe.cu).  The tile's first DEM column is
+// dem_off_x + x0 with x0 % 128 == 0 and dem_off_x = 50 in production, so the box
+// starts DEM_PADX + (dem_off_x & 3) columns to the left of the tile: 4..7 columns.
+constexpr int DEM_PADX = 4;
+constexpr int SMW = TW + 2 * DEM_PADX;   // 136 floats = 544 B >= 7 + 128 + 1; multiple of 16 B (TMA box rule)
 constexpr int SMH = TH + 2;
 constexpr int N_CNT = 12;
 
@@ -59,6 +64,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
 }
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1,
                                             unsigned long long *bar) {
+    // The tensor maps live in GLOBAL memory (one per tile of the batch, written
+    // by the host with cudaMemcpy): the tensormap proxy must acquire them before
+    // first use in every CTA (CUDA programming guide, "tensor map in global
+    // memory"); without the fence UTMALDG traps with an illegal instruction.
+    asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(map) : "memory");
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
             "r"(smem_u32(dst)),
@@ -91,7 +101,8 @@ dswx_fused_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__restri
     const bool has_ocean = T.ocean != nullptr;
 
     // ---- stage the DEM tile (+halo) ---------------------------------------
-    const int dem_x0 = T.dem_off_x + x0 - DEM_PADX;
+    const int padx = DEM_PADX + (T.dem_off_x & 3);
+    const int dem_x0 = T.dem_off_x + x0 - padx;          // multiple of 4 -> 16-B aligned box start
     const int dem_y0 = T.dem_off_y + y0 - 1;
     const bool use_tma = has_dem && (T.flags & TF_TMA);
     if (use_tma && tid == 0) {
@@ -191,15 +202,15 @@ dswx_fused_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__restri
                 mbar_wait(&s.mbar, 0);
                 dem_ready = true;
             }
-            const int sc = lane * 4 + DEM_PADX;          // smem column of pixel 0
-            const float4 up = *reinterpret_cast<const float4 *>(&s.dem[ly][sc]);
-            const float4 mid = *reinterpret_cast<const float4 *>(&s.dem[ly + 1][sc]);
-            const float4 dn = *reinterpret_cast<const float4 *>(&s.dem[ly + 2][sc]);
-            const float left = s.dem[ly + 1][sc - 1];
-            const float right = s.dem[ly + 1][sc + 4];
-            const float m[6] = {left, mid.x, mid.y, mid.z, mid.w, right};
-            const float u[4] = {up.x, up.y, up.z, up.w};
-            const float d[4] = {dn.x, dn.y, dn.z, dn.w};
+            const int sc = lane * 4 + padx;              // smem column of pixel 0
+            float m[6], u[4], d[4];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) m[j] = s.dem[ly + 1][sc - 1 + j];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                u[j] = s.dem[ly][sc + j];
+                d[j] = s.dem[ly + 2][sc + j];
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 // np.gradient interior: (f[i+1] - f[i-1]) / 2.0 in float32 (D:4255)
