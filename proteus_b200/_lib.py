@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libproteus_b200.so')
+LIB_PATH = os.environ.get('PB200_LIB_PATH') or os.path.join(HERE, 'libproteus_b200.so')
 
 ABI_VERSION = 1
 NO_FILL = -2 ** 31

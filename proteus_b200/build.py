@@ -18,6 +18,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libproteus_b200.so')
 SOURCES = [os.path.join(CSRC, 'pb200_api.cu')]
 HEADERS = [os.path.join(CSRC, 'pb200_kernels.cuh'),
+           os.path.join(CSRC, 'pb200_fused.cuh'),
            os.path.join(CSRC, 'pb200_device.cuh'),
            os.path.join(HERE, '..', 'include', 'proteus_b200.h')]
 

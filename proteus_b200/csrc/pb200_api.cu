@@ -20,6 +20,7 @@
 
 #include "../../include/proteus_b200.h"
 #include "pb200_kernels.cuh"
+#include "pb200_fused.cuh"
 
 using namespace pb200;
 
@@ -270,6 +271,102 @@ static int derive_params(const pb200_params *p, DevParams *D, bool fused) {
 }
 
 // ---------------------------------------------------------------------------
+// tables and packed constants of the fast kernel (pb200_fused.cuh)
+// ---------------------------------------------------------------------------
+static uint32_t land_category(uint32_t land) {          // D:1133-1207
+    if (land == 200u) return LC_WATER;
+    if (land == 201u || land < 100u) return LC_EVERGREEN_OR_LOW;
+    if (land < 200u) return LC_HIGH;
+    return LC_NONE;
+}
+static uint32_t kill_class(uint32_t kb, bool shadowed, bool bright, uint32_t cat) {   // D:1331-1376
+    const bool water = kb >= 1u && kb <= 4u, psw = kb == 3u || kb == 4u;
+    const bool kill = (shadowed && water && cat != LC_WATER) || (cat == LC_EVERGREEN_OR_LOW && bright && psw) ||
+                      (cat == LC_HIGH && water);
+    return kill ? 0u : kb;
+}
+
+static void build_fused_tables(const pb200_params *p, const DevParams &D, FusedTables *T) {
+    std::memset(T, 0, sizeof(*T));
+    for (uint32_t idx = 0; idx < 128; ++idx) {
+        const uint32_t d = idx & 31u;
+        const bool valid = (idx >> 5) & 1u, not_ocean = (idx >> 6) & 1u;
+        const uint32_t rep = valid ? (D.diag_lut[d] & 0xffffu) : 65535u;                 // D:5227, D:5231
+        const uint32_t k1 = !valid ? 7u : (!not_ocean ? 6u : (D.diag_lut[d] >> 16));     // D:5229, 5245, 5249
+        T->diag_lut[idx] = rep | ((k1 << 8) << 16);
+    }
+    for (uint32_t v = 0; v < 256; ++v) T->land_lut[v] = (uint8_t)land_category(v);
+    const bool aerosol_on = p->apply_aerosol_class_remapping != 0;
+    for (uint32_t idx = 0; idx < 4096; ++idx) {
+        const uint32_t fm = idx & 255u, k1 = (idx >> 8) & 7u, nle = idx >> 11;
+        const uint32_t fe = D.fmask_lut[fm];
+        const uint32_t cprelim = fe & 7u, snow = (fe >> 3) & 1u, aero = (fe >> 4) & 0x1Fu;
+        const bool remap = aerosol_on && nle && k1 <= 4u && ((aero >> k1) & 1u);        // D:1237-1239
+        const uint32_t kb = remap ? 1u : k1;
+        const uint32_t c = cprelim | (remap ? 8u : 0u) | (snow << 1);                    // D:1246, D:2081
+        T->fk_lut[idx] = (uint8_t)(kb | (c << 3));
+    }
+    for (uint32_t idx = 0; idx < 128; ++idx)
+        T->kill_lut[idx] = (uint8_t)kill_class(idx & 7u, (idx >> 3) & 1u, (idx >> 4) & 1u, (idx >> 5) & 3u);
+    for (uint32_t idx = 0; idx < 2048; ++idx) {
+        const uint32_t kb = idx & 7u, c = (idx >> 3) & 15u, cat = (idx >> 7) & 3u;
+        const bool shadowed = (idx >> 9) & 1u, bright = (idx >> 10) & 1u;
+        const uint32_t k2 = kill_class(kb, shadowed, bright, cat);
+        const uint32_t k2_lit = kill_class(kb, false, bright, cat), k2_dark = kill_class(kb, true, bright, cat);
+        const uint32_t out = D.out_lut[k2 * 16 + c] & 0x00ffffffu;                       // WTR | BWTR | CONF
+        // flags: valid / valid-and-preliminary-cloud (D:5104-5111), shadow sensitivity, histogram bin
+        const bool valid = kb <= 4u;
+        const bool cv = valid && (c & 5u) != 0u;
+        const uint32_t w2 = k2 < 5u ? k2 : (k2 == 5u ? 255u : 248u + k2);
+        const uint32_t wtr = cloud_masking(w2, c);                                       // uncollapsed WTR class
+        const uint32_t bin = wtr < 5u ? wtr : wtr - 247u;                                // 252..255 -> 5..8
+        uint32_t flags = (valid ? 1u : 0u) | (cv ? 2u : 0u) | (k2_lit != k2_dark ? 4u : 0u) | (bin << 4);
+        T->big_lut[idx] = out | (flags << 24);
+    }
+}
+
+static uint32_t pack_neg(int v) { const uint32_t h = (uint32_t)(-v) & 0xffffu; return h | (h << 16); }
+static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+static void build_fast_params(const pb200_params *p, const DevParams &D, FastParams *F) {
+    std::memset(F, 0, sizeof(*F));
+    for (int k = 0; k < 6; ++k) {
+        const int f = p->band_fill[k];
+        if (f == PB200_NO_FILL || f < -32768 || f > 32767) {
+            F->fill_xor[k] = 0u; F->fill_or[k] = 0xffffffffu;          // never equal
+        } else {
+            const uint32_t h = (uint32_t)f & 0xffffu;
+            F->fill_xor[k] = h | (h << 16); F->fill_or[k] = 0u;
+        }
+    }
+    // clipped reflectances lie in [1, 32767]: "x < t" only needs t in [1, 32768]
+    F->m_p1swir1 = pack_neg(clampi(D.p1_swir1, 1, 32768));
+    F->m_p1nir = pack_neg(clampi(D.p1_nir, 1, 32768));
+    F->m_p2blue = pack_neg(clampi(D.p2_blue, 1, 32768));
+    F->m_p2swir1 = pack_neg(clampi(D.p2_swir1, 1, 32768));
+    F->m_p2swir2 = pack_neg(clampi(D.p2_swir2, 1, 32768));
+    F->m_p2nir = pack_neg(clampi(D.p2_nir, 1, 32768));
+    F->m_nle = pack_neg(1001);                                          // nir <= 1000.0  (D:46, D:1239)
+    F->m_lc = pack_neg(clampi(D.lc_nir, 0, 32767) + 1);                 // nir > lcmask_nir
+    // |4*awesh| < 2^20: clamp so that init - 4*awesh cannot overflow
+    F->awesh_init = clampi(D.awesh4_thr, -(1 << 24), 1 << 24);
+    for (int i = 0; i < 4; ++i) { F->ra[i] = D.r_a[i]; F->rb[i] = D.r_b[i]; }
+    if (p->fmask_fill >= 0 && p->fmask_fill <= 255) {
+        F->fmask_xor4 = (uint32_t)p->fmask_fill * 0x01010101u; F->fmask_or = 0u;
+    } else {
+        F->fmask_xor4 = 0u; F->fmask_or = 0x00010001u;                  // never equal
+    }
+    F->kx = 0.5f / D.dxf;
+    F->ky = 0.5f / D.dyf;
+    const bool ok = std::isfinite(D.cos_thr) && std::fabs(D.cos_thr) <= 1.0 && std::isfinite(D.tan_thr) &&
+                    std::fabs(D.tan_thr) < 1e6 && std::isfinite(F->kx) && std::isfinite(F->ky);
+    F->fast_shadow_ok = ok ? 1u : 0u;
+    F->tan32 = ok ? (float)D.tan_thr : 0.0f;
+    F->abs_tan32 = std::fabs(F->tan32);
+    F->cc32 = ok ? (float)(D.cos_thr * std::fabs(D.cos_thr)) : 0.0f;
+}
+
+// ---------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -284,6 +381,7 @@ struct HostPipe {               // device mirror of one host tile (pb200_classif
     uint16_t *diag = nullptr;
     uint8_t *u8out[8] = {};
     unsigned long long *counters = nullptr;
+    FusedTables *tables = nullptr;      // uploaded once per pb200_classify_host call
     cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_k;
 };
@@ -291,18 +389,29 @@ struct HostPipe {               // device mirror of one host tile (pb200_classif
 struct pb200_ctx {
     int device = 0;
     int sm_count = 0;
+    bool fast_ready = false;
+    int fast_ctas_per_sm = 1;
     EncodeTiledFn encode = nullptr;
     HostPipe pipe;
     std::mutex mu;
 };
 
+// tile groups of a plan: which kernel runs them
+enum { G_FAST = 0, G_VEC = 1, G_GENERIC = 2, N_GROUPS = 3 };
+
 struct pb200_plan {
     pb200_ctx *ctx = nullptr;
     DevParams P;
-    TileDev *d_tiles[2] = {nullptr, nullptr};        // [0] vectorised tiles, [1] generic tiles
-    CUtensorMap *d_maps[2] = {nullptr, nullptr};
-    int n[2] = {0, 0};
-    int max_ctas[2] = {0, 0};
+    FastParams F;
+    TileDev *d_tiles[N_GROUPS] = {};                 // [G_FAST] packed-SIMD persistent kernel,
+    CUtensorMap *d_maps[N_GROUPS] = {};              // [G_VEC] / [G_GENERIC] dswx_fused_kernel<true/false>
+    int n[N_GROUPS] = {};
+    int max_ctas[N_GROUPS] = {};
+    FusedTables *d_tables = nullptr;                 // G_FAST only
+    bool owns_tables = false;
+    ItemDesc *d_items = nullptr;
+    int n_items = 0;
+    bool fast_optional = false;                      // some fast tile wants WTR-1 / WTR-2 / CLOUD / SHAD
     bool stream_ordered = false;                     // allocated with cudaMallocAsync
 };
 
@@ -348,6 +457,7 @@ extern "C" int pb200_ctx_destroy(pb200_ctx *ctx) {
     HostPipe &p = ctx->pipe;
     pipe_free(p);
     cudaFree(p.counters);
+    cudaFree(p.tables);
     if (p.s_in) cudaStreamDestroy(p.s_in);
     if (p.s_k) cudaStreamDestroy(p.s_k);
     if (p.s_out) cudaStreamDestroy(p.s_out);
@@ -431,71 +541,143 @@ static int make_tile_dev(pb200_ctx *ctx, const pb200_tile &t, int index, TileDev
 }
 
 static int plan_build(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles, const pb200_params *params,
-                      pb200_plan *pl, cudaStream_t stream, bool stream_ordered) {
+                      pb200_plan *pl, cudaStream_t stream, bool stream_ordered,
+                      FusedTables *shared_tables = nullptr) {
     if (!ctx || !tiles || n_tiles <= 0 || !params)
         return fail(PB200_E_INVALID_ARG, "classify: null argument or n_tiles <= 0");
     if (n_tiles > 65535) return fail(PB200_E_INVALID_ARG, "classify: at most 65535 tiles per launch");
     int rc = derive_params(params, &pl->P, true);
     if (rc) return rc;
+    build_fast_params(params, pl->P, &pl->F);
     pl->ctx = ctx;
     pl->stream_ordered = stream_ordered;
-    std::vector<TileDev> td[2];
-    std::vector<CUtensorMap> tm[2];
+    std::vector<TileDev> td[N_GROUPS];
+    std::vector<CUtensorMap> tm[N_GROUPS];
+    std::vector<ItemDesc> items;
     for (int i = 0; i < n_tiles; ++i) {
         TileDev d;
         alignas(64) CUtensorMap m;
         std::memset(&m, 0, sizeof(m));
         rc = make_tile_dev(ctx, tiles[i], i, &d, &m);
         if (rc) return rc;
-        const int g = (d.flags & TF_VEC) ? 0 : 1;
+        const pb200_tile &t = tiles[i];
+        bool fast = (d.flags & TF_VEC) && (d.dem == nullptr || (d.flags & TF_TMA)) &&
+                    (uint64_t)d.height * (uint64_t)d.width < 0xfff00000ull && d.width <= 65000 * FT_W &&
+                    d.height <= 65000 * FT_H;
+        // 16-byte band loads / DIAG stores, 8-byte loads / stores of the byte rasters
+        for (int k = 0; k < 6; ++k) fast = fast && aligned(t.band[k], 16);
+        fast = fast && aligned(t.fmask, 8) && aligned(t.land, 8) && aligned(t.ocean, 8) && aligned(t.diag, 16) &&
+               aligned(t.wtr1, 8) && aligned(t.wtr1_remapped, 8) && aligned(t.wtr2, 8) && aligned(t.cloud, 8) &&
+               aligned(t.shad, 8) && aligned(t.wtr, 8) && aligned(t.bwtr, 8) && aligned(t.conf, 8);
+        // the first DEM box of a row of items must not start left of the DEM array
+        if (d.dem) fast = fast && d.dem_off_x >= 4 + DEM_PADX + (d.dem_off_x & 3);
+        const int g = fast ? G_FAST : ((d.flags & TF_VEC) ? G_VEC : G_GENERIC);
+        if (fast) {
+            // the fast kernel stages the DEM with its own box shape
+            if (d.dem) {
+                const cuuint64_t gdim[2] = {(cuuint64_t)d.dem_pitch, (cuuint64_t)d.dem_rows};
+                const cuuint64_t gstr[1] = {(cuuint64_t)d.dem_pitch * sizeof(float)};
+                const cuuint32_t box[2] = {(cuuint32_t)FT_SMW, (cuuint32_t)FT_SMH};
+                const cuuint32_t estr[2] = {1, 1};
+                const CUresult r = ctx->encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)d.dem, gdim, gstr, box,
+                                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) return fail(PB200_E_INVALID_ARG, "tile %d: cuTensorMapEncodeTiled failed (%d)", i, (int)r);
+            }
+            // odd rows are processed shifted left by 4 pixels: cover width + 4
+            const int ntx = (d.width + 4 + FT_W - 1) / FT_W, nty = (d.height + FT_H - 1) / FT_H;
+            const uint32_t slot = (uint32_t)td[G_FAST].size();
+            for (int ty = 0; ty < nty; ++ty)
+                for (int tx = 0; tx < ntx; ++tx) items.push_back(ItemDesc{slot, (uint16_t)tx, (uint16_t)ty});
+            if (d.wtr1 || d.wtr1r || d.wtr2 || d.cloud || d.shad) pl->fast_optional = true;
+        }
         td[g].push_back(d);
         tm[g].push_back(m);
         pl->max_ctas[g] = std::max(pl->max_ctas[g], d.n_ctas);
     }
     CK(cudaSetDevice(ctx->device));
-    for (int g = 0; g < 2; ++g) {
+    auto dev_alloc = [&](void **ptr, size_t bytes) -> cudaError_t {
+        return stream_ordered ? cudaMallocAsync(ptr, bytes, stream) : cudaMalloc(ptr, bytes);
+    };
+    for (int g = 0; g < N_GROUPS; ++g) {
         pl->n[g] = (int)td[g].size();
         if (!pl->n[g]) continue;
         const size_t bt = td[g].size() * sizeof(TileDev), bm = tm[g].size() * sizeof(CUtensorMap);
-        if (stream_ordered) {
-            CK(cudaMallocAsync((void **)&pl->d_tiles[g], bt, stream));
-            CK(cudaMallocAsync((void **)&pl->d_maps[g], bm, stream));
-        } else {
-            CK(cudaMalloc((void **)&pl->d_tiles[g], bt));
-            CK(cudaMalloc((void **)&pl->d_maps[g], bm));
-        }
+        CK(dev_alloc((void **)&pl->d_tiles[g], bt));
+        CK(dev_alloc((void **)&pl->d_maps[g], bm));
         // pageable source: the copy is staged before the call returns
         CK(cudaMemcpyAsync(pl->d_tiles[g], td[g].data(), bt, cudaMemcpyHostToDevice, stream));
         CK(cudaMemcpyAsync(pl->d_maps[g], tm[g].data(), bm, cudaMemcpyHostToDevice, stream));
     }
+    if (pl->n[G_FAST]) {
+        pl->n_items = (int)items.size();
+        CK(dev_alloc((void **)&pl->d_items, items.size() * sizeof(ItemDesc)));
+        CK(cudaMemcpyAsync(pl->d_items, items.data(), items.size() * sizeof(ItemDesc), cudaMemcpyHostToDevice, stream));
+        if (shared_tables) {
+            pl->d_tables = shared_tables;
+        } else {
+            FusedTables T;
+            build_fused_tables(params, pl->P, &T);
+            CK(dev_alloc((void **)&pl->d_tables, sizeof(FusedTables)));
+            pl->owns_tables = true;
+            CK(cudaMemcpyAsync(pl->d_tables, &T, sizeof(T), cudaMemcpyHostToDevice, stream));
+        }
+    }
+    return 0;
+}
+
+static int fast_kernel_setup(pb200_ctx *ctx) {
+    if (ctx->fast_ready) return 0;
+    CK(cudaFuncSetAttribute(dswx_fused_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)sizeof(FastSmem)));
+    CK(cudaFuncSetAttribute(dswx_fused_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)sizeof(FastSmem)));
+    int nb = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dswx_fused_fast_kernel<false>, FT_THREADS, sizeof(FastSmem)));
+    ctx->fast_ctas_per_sm = nb > 0 ? nb : 1;
+    ctx->fast_ready = true;
     return 0;
 }
 
 static int plan_launch(pb200_plan *pl, cudaStream_t stream) {
-    if (pl->n[0]) {
-        dim3 grid(pl->max_ctas[0], pl->n[0]);
-        dswx_fused_kernel<true><<<grid, NTHREADS, 0, stream>>>(pl->d_tiles[0], pl->d_maps[0], pl->P);
+    if (pl->n[G_FAST]) {
+        int rc = fast_kernel_setup(pl->ctx);
+        if (rc) return rc;
+        const int grid = std::min(pl->n_items, pl->ctx->sm_count * pl->ctx->fast_ctas_per_sm);
+        if (pl->fast_optional)
+            dswx_fused_fast_kernel<true><<<grid, FT_THREADS, sizeof(FastSmem), stream>>>(
+                pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, pl->d_items, pl->n_items, pl->P, pl->F);
+        else
+            dswx_fused_fast_kernel<false><<<grid, FT_THREADS, sizeof(FastSmem), stream>>>(
+                pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, pl->d_items, pl->n_items, pl->P, pl->F);
     }
-    if (pl->n[1]) {
-        dim3 grid(pl->max_ctas[1], pl->n[1]);
-        dswx_fused_kernel<false><<<grid, NTHREADS, 0, stream>>>(pl->d_tiles[1], pl->d_maps[1], pl->P);
+    if (pl->n[G_VEC]) {
+        dim3 grid(pl->max_ctas[G_VEC], pl->n[G_VEC]);
+        dswx_fused_kernel<true><<<grid, NTHREADS, 0, stream>>>(pl->d_tiles[G_VEC], pl->d_maps[G_VEC], pl->P);
+    }
+    if (pl->n[G_GENERIC]) {
+        dim3 grid(pl->max_ctas[G_GENERIC], pl->n[G_GENERIC]);
+        dswx_fused_kernel<false><<<grid, NTHREADS, 0, stream>>>(pl->d_tiles[G_GENERIC], pl->d_maps[G_GENERIC], pl->P);
     }
     CK(cudaGetLastError());
     return 0;
 }
 
 static void plan_release(pb200_plan *pl, cudaStream_t stream) {
-    for (int g = 0; g < 2; ++g) {
-        if (pl->stream_ordered) {
-            if (pl->d_tiles[g]) cudaFreeAsync(pl->d_tiles[g], stream);
-            if (pl->d_maps[g]) cudaFreeAsync(pl->d_maps[g], stream);
-        } else {
-            cudaFree(pl->d_tiles[g]);
-            cudaFree(pl->d_maps[g]);
-        }
+    auto dev_free = [&](void *ptr) {
+        if (!ptr) return;
+        if (pl->stream_ordered) cudaFreeAsync(ptr, stream); else cudaFree(ptr);
+    };
+    for (int g = 0; g < N_GROUPS; ++g) {
+        dev_free(pl->d_tiles[g]);
+        dev_free(pl->d_maps[g]);
         pl->d_tiles[g] = nullptr;
         pl->d_maps[g] = nullptr;
     }
+    dev_free(pl->d_items);
+    pl->d_items = nullptr;
+    if (pl->owns_tables) dev_free(pl->d_tables);
+    pl->d_tables = nullptr;
 }
 
 extern "C" int pb200_classify(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles, const pb200_params *params,
@@ -557,6 +739,7 @@ static int pipe_reserve(HostPipe &p, size_t px, size_t dem_elems) {
         CK(cudaStreamCreateWithFlags(&p.s_k, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&p.s_out, cudaStreamNonBlocking));
         CK(cudaMalloc((void **)&p.counters, PB200_N_COUNTERS * sizeof(unsigned long long)));
+        CK(cudaMalloc((void **)&p.tables, sizeof(FusedTables)));
     }
     if (px > p.cap_px) {
         for (auto &b : p.band) { cudaFree(b); b = nullptr; }
@@ -617,6 +800,11 @@ extern "C" int pb200_classify_host(pb200_ctx *ctx, const pb200_tile *ht, const p
     rc = derive_params(params, &P, true);
     if (rc) return rc;
     if (dt.counters) CK(cudaMemsetAsync(p.counters, 0, PB200_N_COUNTERS * sizeof(unsigned long long), p.s_k));
+    {
+        FusedTables T;
+        build_fused_tables(params, P, &T);
+        CK(cudaMemcpyAsync(p.tables, &T, sizeof(T), cudaMemcpyHostToDevice, p.s_k));
+    }
 
     std::vector<pb200_plan> plans(n_strips);
     int dem_copied = 0;                 // DEM rows [.., dem_copied) are on the device
@@ -655,7 +843,7 @@ extern "C" int pb200_classify_host(pb200_ctx *ctx, const pb200_tile *ht, const p
         for (int i = 0; i < 8; ++i)
             if (*sf[i]) *sf[i] += off;
         CK(cudaStreamWaitEvent(p.s_k, p.ev_in[sidx], 0));
-        rc = plan_build(ctx, &st, 1, params, &plans[sidx], p.s_k, true);
+        rc = plan_build(ctx, &st, 1, params, &plans[sidx], p.s_k, true, p.tables);
         if (rc == 0) rc = plan_launch(&plans[sidx], p.s_k);
         plan_release(&plans[sidx], p.s_k);
         if (rc) { cudaDeviceSynchronize(); return rc; }
