@@ -51,6 +51,11 @@ def parse_args():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', choices=('ours', 'reference'), default='ours')
     ap.add_argument('--tiles', type=int, default=16, help='tiles per GPU per step')
+    ap.add_argument('--workload', choices=('tiles', 'timeseries', 'mosaic'), default='tiles',
+                    help="tiles: configs[1]/[2] batch sharded by tile (default); timeseries: configs[3], the "
+                         "acquisitions of --tiles share DEM/LAND/ocean; mosaic: configs[4], one --mosaic-size^2 "
+                         "raster row-stripped over the ranks with a NCCL DEM halo exchange")
+    ap.add_argument('--mosaic-size', type=int, default=21960)
     ap.add_argument('--size', type=int, default=TILE, help='tile edge in pixels (default 3660)')
     ap.add_argument('--e2e-steps', type=int, default=0, help='host-path steps (default: min(steps, 20))')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -69,7 +74,7 @@ _REASONS = {0x4: 'sw_power_cap', 0x8: 'hw_slowdown', 0x20: 'sw_thermal_slowdown'
 
 
 class ClockSampler:
-    def __init__(self, device_index, period_s=0.004):
+    def __init__(self, device_index, period_s=0.02):
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
         self._active = threading.Event()
@@ -225,6 +230,82 @@ def run_reference_arm(args):
 
 
 # ---------------------------------------------------------------------------
+# GPU arm, mosaic workload (BASELINE configs[4])
+# ---------------------------------------------------------------------------
+def run_mosaic(args, rank, world, local_rank, sampler):
+    import torch
+    import torch.distributed as dist
+    import proteus_b200 as pb
+    from proteus_b200 import mosaic, synth
+    size, m = args.mosaic_size, 50
+    r0, r1 = mosaic.strip_bounds(size, world)[rank]
+    n = r1 - r0
+    dev = f'cuda:{local_rank}'
+    t = synth.make_device_batch(1, n, size, device=dev, seed=2000 + rank, n_distinct=1, full_product=False)[0]
+    g = torch.Generator(device=dev)
+    g.manual_seed(3000 + rank)
+    d0, d1 = mosaic.dem_rows_for_strip(r0, r1, size, m)
+    coarse = torch.randn((1, 1, (d1 - d0) // 25 + 2, (size + 2 * m) // 25 + 2), device=dev, generator=g)
+    dem_local = (torch.nn.functional.interpolate(coarse, size=(d1 - d0, size + 2 * m), mode='bilinear',
+                                                 align_corners=True)[0, 0] * 400.0 + 800.0).contiguous()
+    land = torch.full((n, size), 255, dtype=torch.uint8, device=dev)
+    land[:, ::7] = 21
+    land[::5] = 200
+    ocean = torch.ones((n, size), dtype=torch.uint8, device=dev)
+    ocean[:, : size // 10] = 0
+    strip = mosaic.MosaicStrip(t['bands'], t['fmask'], dem_local, land, ocean, r0, r1, size,
+                               sun_azimuth=150.0, sun_elevation=45.0, params=pb.make_params(),
+                               outputs=pb.GRADED_LAYERS, rank=rank, world=world)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(max(args.warmup, 3)):
+        strip.run()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    ev0.record()
+    for _ in range(args.steps):
+        strip.run()
+    ev1.record()
+    barrier()
+    sampler.pause()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms.item()) / args.steps
+    total_px = size * size
+    value = total_px / 1e6 / (ms_per_step / 1e3)
+    clocks = sampler.summary()
+    if rank == 0:
+        peak = FALLBACK_HBM_GBS
+        try:
+            with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+                peak = float(json.load(f)['hbm_gbs'])
+        except Exception:
+            pass
+        achieved = n * size * ALGO_BYTES_PER_PX / (ms_per_step / 1e3) / 1e9
+        print(json.dumps({
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True,
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'int16', 'data': 'synthetic',
+            'tiles_per_s': value * 1e6 / PIXELS_PER_TILE,
+            'config': {'workload': f'configs[4]: one synthetic {size}x{size} mosaic (full product) row-stripped over '
+                                   f'{world} GPU(s), one DEM halo row per neighbour exchanged with NCCL send/recv '
+                                   'and overlapped with the interior rows',
+                       'rows_per_rank': n, 'halo_bytes_per_neighbour': (size + 2 * m) * 4,
+                       'layers_out': list(pb.GRADED_LAYERS), 'bytes_per_pixel': ALGO_BYTES_PER_PX,
+                       'l2_policy': 'strip inputs >> 126 MB L2; no flush needed'},
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'traffic': None, 'note': 'rank 0 strip incl. halo wait, per step'},
+            'e2e': None, 'cpu_baseline': None, 'gpu_launches': args.steps * 2, 'clocks': clocks}), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
 def run_ours(args):
@@ -248,10 +329,16 @@ def run_ours(args):
     size, n_tiles = args.size, args.tiles
     px_per_tile = size * size
     sampler = ClockSampler(local_rank)
+    if args.workload == 'mosaic':
+        rc = run_mosaic(args, rank, world, local_rank, sampler)
+        if world > 1:
+            dist.destroy_process_group()
+        return rc
 
     # ---- device-resident batch (weak scaling: n_tiles per rank) -------------
     tiles = synth.make_device_batch(n_tiles, size, size, device=f'cuda:{local_rank}',
-                                    seed=1000 + rank, n_distinct=min(4, n_tiles))
+                                    seed=1000 + rank, n_distinct=min(4, n_tiles),
+                                    shared_ancillary=(args.workload == 'timeseries'))
     params = pb.make_params(collapse_wtr_classes=True)
     plan = pb.Plan(tiles, params, pb.GRADED_LAYERS)
     stream = torch.cuda.current_stream()
@@ -362,7 +449,8 @@ def run_ours(args):
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int16', 'data': 'synthetic',
             'tiles_per_s': value * 1e6 / px_per_tile,
             'config': {
-                'workload': f'configs[1]: synthetic HLS S30 tile {size}x{size} full product '
+                'workload': ('configs[3] time series (shared DEM/LAND/ocean): ' if args.workload == 'timeseries' else '') +
+                            f'configs[1]: synthetic HLS S30 tile {size}x{size} full product '
                             f'(6 int16 bands + Fmask + DEM + LAND + ocean -> WTR/BWTR/CONF/DIAG + counters), '
                             f'{n_tiles} distinct device-resident tiles per GPU per step, sharded by tile',
                 'tile': [size, size], 'tiles_per_gpu_per_step': n_tiles,
@@ -373,7 +461,7 @@ def run_ours(args):
                          'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                          'algorithmic_bytes_per_launch': algo_bytes, 'kernel_ms': kernel_ms,
                          'frac_of_nominal_8TBs': achieved / 8000.0,
-                         'kernel': 'pb200::dswx_fused_kernel<true>'},
+                         'kernel': 'pb200::dswx_fused_fast_kernel<false>'},
             'e2e': e2e, 'cpu_baseline': cpu_baseline, 'parity': parity,
             'gpu_launches': args.steps, 'clocks': clocks,
         }

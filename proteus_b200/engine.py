@@ -196,7 +196,7 @@ class Plan:
     given in ``outputs_into``."""
 
     def __init__(self, tiles, params=None, outputs=GRADED_LAYERS, *,
-                 counters=True, ctx=None, outputs_into=None):
+                 counters=True, ctx=None, outputs_into=None, counters_into=None):
         import torch
         self.ctx = ctx or get_context()
         self.params = params if params is not None else make_params()
@@ -208,8 +208,16 @@ class Plan:
         dev = torch.device('cuda', self.ctx.device)
         n = len(tiles)
         self.outputs = []
-        self.counters = (torch.zeros((n, _lib.N_COUNTERS), dtype=torch.int64, device=dev)
-                         if counters else None)
+        if counters_into is not None:
+            # caller-owned slots, shape (n, 12) int64; rows may alias (several
+            # pieces of one raster adding into the same counters)
+            if counters_into.dtype != torch.int64 or tuple(counters_into.shape) != (n, _lib.N_COUNTERS):
+                raise ValueError('counters_into: expected an int64 tensor of shape (n_tiles, 12)')
+            self.counters = counters_into
+            counters = True
+        else:
+            self.counters = (torch.zeros((n, _lib.N_COUNTERS), dtype=torch.int64, device=dev)
+                             if counters else None)
         self._tile_array = (_lib.Tile * n)()
         for i, t in enumerate(tiles):
             bands, fmask = t['bands'], t['fmask']

@@ -1,0 +1,178 @@
+"""Multi-GPU partitioning of the classification path.
+
+Two schemes:
+
+* **by tile** - MGRS tiles / acquisitions are independent: tile ``i`` goes to
+  rank ``i % world`` and nothing is exchanged (``shard_tiles``).
+* **row strips of one oversized raster** - every function of the path is
+  point-wise except the terrain-shadow stencil (``np.gradient`` inside
+  ``_compute_opera_shadow_layer``, dswx_hls.py:4255) whose radius is one DEM
+  row.  Each rank owns a contiguous strip of rows and needs ONE DEM row from
+  each neighbour: ``exchange_dem_halo`` posts the two sends / receives as one
+  ``torch.distributed`` P2P batch (NCCL send/recv over NVLink on GPUs; gloo in
+  the CPU tests).  ``MosaicStrip`` classifies the interior rows while the
+  exchange is in flight and the two boundary rows afterwards.
+
+The reference never splits a raster; parity is defined against the reference
+run on the whole raster.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .params import DEM_MARGIN_IN_PIXELS
+
+
+def shard_tiles(n_tiles, rank, world):
+    """Indices of the tiles rank ``rank`` processes (round robin)."""
+    return list(range(int(rank), int(n_tiles), int(world)))
+
+
+def strip_bounds(height, world, align=32):
+    """Row ranges [r0, r1) of ``world`` contiguous strips.  Strip starts are
+    multiples of ``align`` rows (keeps every plane's strip pointer 16-byte
+    aligned for any width that is a multiple of 4)."""
+    height, world = int(height), int(world)
+    blocks = -(-height // align)
+    per, extra = divmod(blocks, world)
+    bounds, r = [], 0
+    for k in range(world):
+        nb = per + (1 if k < extra else 0)
+        r1 = min(height, r + nb * align)
+        bounds.append((r, r1))
+        r = r1
+    return bounds
+
+
+def dem_rows_for_strip(r0, r1, height, margin=DEM_MARGIN_IN_PIXELS):
+    """DEM rows (in the margin-included DEM array) a rank holds locally: its
+    own pixel rows, plus the whole top margin on the first strip and the whole
+    bottom margin on the last - i.e. a partition of the DEM rows, no overlap."""
+    d0 = 0 if r0 == 0 else margin + r0
+    d1 = height + 2 * margin if r1 == height else margin + r1
+    return d0, d1
+
+
+def exchange_dem_halo(dem_ext, n_rows, rank, world, group=None):
+    """Fill ``dem_ext[0]`` and ``dem_ext[n_rows + 1]`` with the neighbouring
+    ranks' boundary DEM rows.
+
+    ``dem_ext`` is a (n_rows + 2, pitch) float32 tensor whose rows
+    ``1 .. n_rows`` already hold this rank's DEM rows (pixel rows of the
+    strip).  Rank 0 keeps its own ``dem_ext[0]`` (taken from the DEM margin by
+    the caller) and the last rank its own ``dem_ext[n_rows + 1]``.
+    Returns the list of outstanding P2P requests (empty when world == 1)."""
+    import torch.distributed as dist
+    if world == 1:
+        return []
+    ops = []
+    if rank > 0:
+        ops.append(dist.P2POp(dist.isend, dem_ext[1], rank - 1, group))
+        ops.append(dist.P2POp(dist.irecv, dem_ext[0], rank - 1, group))
+    if rank < world - 1:
+        ops.append(dist.P2POp(dist.isend, dem_ext[n_rows], rank + 1, group))
+        ops.append(dist.P2POp(dist.irecv, dem_ext[n_rows + 1], rank + 1, group))
+    return dist.batch_isend_irecv(ops) if ops else []
+
+
+class MosaicStrip:
+    """One rank's row strip of an oversized raster, device resident.
+
+    Parameters
+    ----------
+    bands, fmask, land, ocean : torch CUDA tensors of the strip, [n_rows, W]
+    dem_local : float32 CUDA tensor [d1 - d0, W + 2*margin] with the DEM rows
+        of ``dem_rows_for_strip`` (margin columns included)
+    r0, r1, height : strip rows and full raster height
+    """
+
+    def __init__(self, bands, fmask, dem_local, land, ocean, r0, r1, height, *,
+                 sun_azimuth, sun_elevation, params=None, outputs=None,
+                 margin=DEM_MARGIN_IN_PIXELS, rank=0, world=1, group=None, ctx=None):
+        import torch
+        from .engine import GRADED_LAYERS, Plan, get_context
+        from .params import make_params
+        self.rank, self.world, self.group = int(rank), int(world), group
+        self.r0, self.r1, self.height = int(r0), int(r1), int(height)
+        n = self.r1 - self.r0
+        self.n_rows = n
+        w = int(fmask.shape[1])
+        pitch = int(dem_local.shape[1])
+        assert pitch == w + 2 * margin, 'dem_local must carry the column margins'
+        d0, d1 = dem_rows_for_strip(self.r0, self.r1, self.height, margin)
+        assert int(dem_local.shape[0]) == d1 - d0, (tuple(dem_local.shape), d0, d1)
+        # extended DEM: row 0 and row n+1 are the halo rows
+        self.dem_ext = torch.empty((n + 2, pitch), dtype=torch.float32, device=fmask.device)
+        first = margin + self.r0 - d0              # local index of the strip's first pixel row
+        self.dem_ext[1:n + 1].copy_(dem_local[first:first + n])
+        if self.r0 == 0:
+            self.dem_ext[0].copy_(dem_local[first - 1])            # from the DEM margin
+        if self.r1 == self.height:
+            self.dem_ext[n + 1].copy_(dem_local[first + n])
+        self.params = params if params is not None else make_params()
+        self.layers = tuple(outputs or GRADED_LAYERS)
+        ctx = ctx or get_context()
+        dev = fmask.device
+        self.outputs = {name: torch.empty((n, w), device=dev,
+                                          dtype=torch.int16 if name == 'DIAG' else torch.uint8)
+                        for name in self.layers}
+        self.counters = torch.zeros((1, 12), dtype=torch.int64, device=dev)
+
+        def sub(rows):
+            a, b = rows
+            t = dict(bands=[x[a:b] for x in bands], fmask=fmask[a:b],
+                     land=land[a:b] if land is not None else None,
+                     ocean=ocean[a:b] if ocean is not None else None,
+                     dem=self.dem_ext, dem_off=(1 + a, margin),
+                     sun_azimuth=sun_azimuth, sun_elevation=sun_elevation)
+            outs = {k: v[a:b] for k, v in self.outputs.items()}
+            return t, outs
+
+        pieces = []
+        if n > 2:
+            pieces.append(('interior', (1, n - 1)))
+        edge_rows = [(0, 1)] + ([(n - 1, n)] if n > 1 else [])
+        self._interior = None
+        if n > 2:
+            t, o = sub((1, n - 1))
+            self._interior = Plan([t], self.params, self.layers, ctx=ctx, outputs_into=[o],
+                                  counters_into=self.counters)
+        tiles, outs = zip(*[sub(r) for r in edge_rows])
+        self._edges = Plan(list(tiles), self.params, self.layers, ctx=ctx, outputs_into=list(outs),
+                           counters_into=self.counters.expand(len(tiles), 12))
+        self._side = torch.cuda.Stream(device=dev) if fmask.is_cuda else None
+
+    def run(self, halo=None):
+        """Halo exchange overlapped with the interior rows, then the two
+        boundary rows.  Asynchronous on the current stream.
+
+        ``halo`` = (row_above, row_below) tensors (either may be None) replaces
+        the exchange - used to emulate several ranks inside one process."""
+        import torch
+        cur = torch.cuda.current_stream()
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            if halo is not None:
+                if halo[0] is not None:
+                    self.dem_ext[0].copy_(halo[0])
+                if halo[1] is not None:
+                    self.dem_ext[self.n_rows + 1].copy_(halo[1])
+            else:
+                reqs = exchange_dem_halo(self.dem_ext, self.n_rows, self.rank, self.world, self.group)
+                for r in reqs:
+                    r.wait()
+        if self._interior is not None:
+            self._interior.run(cur)
+        cur.wait_stream(self._side)
+        self._edges.run(cur)
+
+    def zero_counters(self):
+        self.counters.zero_()
+
+    def results(self):
+        import torch
+        torch.cuda.synchronize()
+        res = {k: (v.cpu().numpy().view(np.uint16) if k == 'DIAG' else v.cpu().numpy())
+               for k, v in self.outputs.items()}
+        res['counters'] = self.counters[0].cpu().numpy().astype(np.uint64)
+        return res
