@@ -362,7 +362,7 @@ static void build_fast_params(const pb200_params *p, const DevParams &D, FastPar
                     std::fabs(D.tan_thr) < 1e6 && std::isfinite(F->kx) && std::isfinite(F->ky);
     F->fast_shadow_ok = ok ? 1u : 0u;
     F->tan32 = ok ? (float)D.tan_thr : 0.0f;
-    F->abs_tan32 = std::fabs(F->tan32);
+    F->e0 = 1e-6f * std::fabs(F->tan32) + 1e-30f;
     F->cc32 = ok ? (float)(D.cos_thr * std::fabs(D.cos_thr)) : 0.0f;
 }
 
@@ -564,13 +564,9 @@ static int plan_build(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles, cons
         bool fast = (d.flags & TF_VEC) && (d.dem == nullptr || (d.flags & TF_TMA)) &&
                     (uint64_t)d.height * (uint64_t)d.width < 0xfff00000ull && d.width <= 65000 * FT_W &&
                     d.height <= 65000 * FT_H;
-        // 16-byte band loads / DIAG stores, 8-byte loads / stores of the byte rasters
-        for (int k = 0; k < 6; ++k) fast = fast && aligned(t.band[k], 16);
-        fast = fast && aligned(t.fmask, 8) && aligned(t.land, 8) && aligned(t.ocean, 8) && aligned(t.diag, 16) &&
-               aligned(t.wtr1, 8) && aligned(t.wtr1_remapped, 8) && aligned(t.wtr2, 8) && aligned(t.cloud, 8) &&
-               aligned(t.shad, 8) && aligned(t.wtr, 8) && aligned(t.bwtr, 8) && aligned(t.conf, 8);
+        (void)t;
         // the first DEM box of a row of items must not start left of the DEM array
-        if (d.dem) fast = fast && d.dem_off_x >= 4 + DEM_PADX + (d.dem_off_x & 3);
+        if (d.dem) fast = fast && d.dem_off_x >= DEM_PADX + (d.dem_off_x & 3);
         const int g = fast ? G_FAST : ((d.flags & TF_VEC) ? G_VEC : G_GENERIC);
         if (fast) {
             // the fast kernel stages the DEM with its own box shape
@@ -584,8 +580,7 @@ static int plan_build(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles, cons
                                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
                 if (r != CUDA_SUCCESS) return fail(PB200_E_INVALID_ARG, "tile %d: cuTensorMapEncodeTiled failed (%d)", i, (int)r);
             }
-            // odd rows are processed shifted left by 4 pixels: cover width + 4
-            const int ntx = (d.width + 4 + FT_W - 1) / FT_W, nty = (d.height + FT_H - 1) / FT_H;
+            const int ntx = (d.width + FT_W - 1) / FT_W, nty = (d.height + FT_H - 1) / FT_H;
             const uint32_t slot = (uint32_t)td[G_FAST].size();
             for (int ty = 0; ty < nty; ++ty)
                 for (int tx = 0; tx < ntx; ++tx) items.push_back(ItemDesc{slot, (uint16_t)tx, (uint16_t)ty});

@@ -6,10 +6,12 @@
 // TMA), re-organised for instruction issue - the resource that bounds this
 // pass on B200 once the memory side streams (profiles/):
 //
-//  * a lane owns 8 consecutive pixels of a row: one 16-byte load per band,
-//    8-byte loads of Fmask / LAND / ocean, 8- and 16-byte stores.  Row pitch
-//    3660 * 2 B is only 8-byte aligned, so odd rows are processed shifted by
-//    4 pixels: every access of every row is then naturally aligned;
+//  * a lane owns 4 consecutive pixels of a row (one 8-byte load per band - row
+//    pitch 3660 * 2 B is only 8-byte aligned - and 4-byte loads / stores of the
+//    byte rasters); a CTA is 16 warps at <= 64 registers so that 32 warps per SM
+//    hide the table-look-up, shared-memory and global-load latencies (an 8-pixel
+//    lane with 16-byte accesses needed 123 registers -> 16 warps per SM and
+//    measured 60 % issue utilisation, profiles/);
 //  * int16 bands stay packed two pixels per register: fill test, clip, the
 //    wrapping sums and the integer threshold tests run on the 16x2 SIMD
 //    integer pipe (VIMNMX[3].x16x2, VIADD.16x2, VIADDMNMX.S16x2); 4*awesh is
@@ -32,15 +34,15 @@
 
 namespace pb200 {
 
-constexpr int FT_W = 256;          // item width: 32 lanes x 8 pixels
-constexpr int FT_H = 32;           // item height: 8 warps x 4 rows
-constexpr int FT_THREADS = 256;
-constexpr int FT_ROWS_PER_WARP = FT_H / (FT_THREADS / 32);
+constexpr int FT_W = 256;          // item width: two 128-pixel halves, one warp (32 lanes x 4 px) each
+constexpr int FT_H = 32;           // item height: 8 warp pairs x 4 rows
+constexpr int FT_THREADS = 512;
+constexpr int FT_ROWS_PER_WARP = FT_H / (FT_THREADS / 64);
 // DEM staging: one TMA box per 128-pixel half (a box is at most 256 elements
-// wide).  Box start = dem_off_x + x0 + 128*half - 4 - padx with padx = 4 +
+// wide).  Box start = dem_off_x + x0 + 128*half - padx with padx = 4 +
 // (dem_off_x & 3): a multiple of 4 floats (UTMALDG needs a 16-byte aligned box
-// start), and wide enough for the 4-pixel row shift plus the one-column halo.
-constexpr int FT_SMW = 140;        // 4 (row shift) + 7 (max padx) + 128 + 1 -> 140 floats = 560 B
+// start on B200, scripts/tma_probe.cu), one-column halo on each side.
+constexpr int FT_SMW = 136;        // 7 (max padx) + 128 + 1 = 136 floats = 544 B
 constexpr int FT_SMH = FT_H + 2;
 
 // land classes as the kill table sees them
@@ -69,7 +71,7 @@ struct FastParams {
     int32_t  awesh_init;                // floor(4*awgt): sign(init - 4*awesh) <=> awesh > awgt
     int32_t  ra[4], rb[4];
     float    kx, ky;                    // 0.5 / dxf, 0.5 / dyf
-    float    tan32, abs_tan32, cc32;    // float32(tan_thr), |.|, c*|c| with c = cos_thr
+    float    tan32, e0, cc32;           // float32(tan_thr), 1e-6*|tan_thr| + 1e-30, c*|c| with c = cos_thr
     uint32_t fast_shadow_ok;            // thresholds are finite and |cos_thr| <= 1
 };
 
@@ -101,64 +103,33 @@ __device__ __forceinline__ void stg_stream_v4(void *p, uint32_t a, uint32_t b, u
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d));
 }
 
-// 8 pixels of a plane: both quads, or the valid one.  Invalid quads get neutral values.
-__device__ __forceinline__ void load_u16x8(const int16_t *p, bool va, bool vb, uint32_t w[4]) {
-    w[0] = w[1] = w[2] = w[3] = 0x00010001u;
-    if (va && vb) {
-        const int4 v = ldg_stream_v4(p);
-        w[0] = (uint32_t)v.x; w[1] = (uint32_t)v.y; w[2] = (uint32_t)v.z; w[3] = (uint32_t)v.w;
-    } else if (va) {
-        const int2 v = ldg_stream_v2(p);
-        w[0] = (uint32_t)v.x; w[1] = (uint32_t)v.y;
-    } else {
-        const int2 v = ldg_stream_v2(p + 4);
-        w[2] = (uint32_t)v.x; w[3] = (uint32_t)v.y;
-    }
-}
-__device__ __forceinline__ void load_u8x8(const uint8_t *p, bool va, bool vb, uint32_t neutral, uint32_t w[2]) {
-    w[0] = w[1] = neutral;
-    if (va && vb) {
-        const int2 v = ldg_stream_v2(p);
-        w[0] = (uint32_t)v.x; w[1] = (uint32_t)v.y;
-    } else if (va) {
-        w[0] = ldg_stream_u32(p);
-    } else {
-        w[1] = ldg_stream_u32(p + 4);
-    }
-}
-__device__ __forceinline__ void store_u8x8(uint8_t *p, bool va, bool vb, uint32_t a, uint32_t b) {
-    if (va && vb) stg_stream_v2(p, a, b);
-    else if (va) stg_stream_u32(p, a);
-    else stg_stream_u32(p + 4, b);
-}
-
-// float32 shortcut of the shadow test (branch-free).  returns 1 = not shadow,
-// 0 = shadow, 2 = too close to a decision boundary (or non-finite input): the
-// caller then runs the exact float64 sequence.  Error budget in DESIGN.md.
+// float32 shortcut of the shadow test (branch-free).  Returns 0x200 (the big_lut
+// index bit) when the pixel is CERTAINLY in terrain shadow, 0 when it is
+// certainly not, and sets *undecided when a value is too close to a decision
+// boundary (or not finite): the caller then runs the exact float64 sequence.
+// Error budget in DESIGN.md section 3.
 __device__ __forceinline__ uint32_t shadow_fast(float l, float r, float u, float d, const FastParams &F,
-                                                float sa, float ca, float sx, float sy, float sz) {
+                                                float sa, float ca, float sx, float sy, float sz, bool *undecided) {
     const float nxa = (l - r) * F.kx;                     // ~ -g_col / dx
     const float nya = (u - d) * F.ky;                     // ~ -g_row / dy
     const float t1 = nxa * sa, t2 = nya * ca;
     const float diff = (t1 + t2) - F.tan32;               // ~ s - tan_thr
-    const float e = fmaf(fabsf(t1) + fabsf(t2) + F.abs_tan32, 1e-6f, 1e-30f);
+    const float e = fmaf(fabsf(t1) + fabsf(t2), 1e-6f, F.e0);
     const float dot = fmaf(nxa, sx, fmaf(nya, sy, sz));
     const float v = fmaf(nxa, nxa, fmaf(nya, nya, 1.0f));
     const float L = dot * fabsf(dot);                     // t -> t|t| is monotone: x >= c for any sign of c
-    const float D = L - F.cc32 * v;
+    const float D = fmaf(-F.cc32, v, L);
     const float eg = 4e-6f * v;
-    const bool not_back = diff > e;                       // certainly not a back slope -> not shadow
-    const bool back = diff < -e;                          // certainly a back slope
-    const bool low = (D > eg) && (L < 0.99999f * v);      // certainly low incidence (and x <= 1)
-    const bool high = D < -eg;                            // certainly not low incidence
-    uint32_t res = 2u;
-    if (back && high) res = 0u;
-    if (not_back || (back && low)) res = 1u;
-    return res;
+    // shadow      <=> back slope AND NOT low incidence:  diff < -e  and  D < -eg
+    // not shadow  <=> not a back slope, or low incidence with x <= 1:  diff > e  or  (D > eg and L < 0.99999 v)
+    const bool is_shadow = fmaxf(diff + e, D + eg) < 0.0f;
+    const bool not_shadow = fmaxf(diff - e, fminf(D - eg, fmaf(0.99999f, v, -L))) > 0.0f;
+    // NaN / inf anywhere makes |diff| + v non-finite -> undecided
+    *undecided = *undecided || !(is_shadow || not_shadow) || !(fabsf(diff) + v < 3e38f);
+    return is_shadow ? 0x200u : 0u;
 }
 
-// ---------------------------------------------------------------------------
-// Rare paths kept out of line so that the hot loop stays inside the instruction cache.
+// Rare paths kept out of line so that the hot loop stays small.
 __device__ __noinline__ uint32_t diag_pair_slow(uint32_t B, uint32_t G, uint32_t R, uint32_t N, uint32_t S1,
                                                 uint32_t S2, const DevParams &P) {
     // some int16 sum of this pair wrapped: per-pixel evaluation with sign normalisation (D:1872-1914)
@@ -172,20 +143,20 @@ __device__ __noinline__ uint32_t shadow_exact(float l, float r, float u, float d
     S.sx = T.sx; S.sy = T.sy; S.sz = T.sz; S.sin_az = T.sin_az; S.cos_az = T.cos_az;
     const float g_col = __fmul_rn(__fsub_rn(r, l), 0.5f);                     // D:4255
     const float g_row = __fmul_rn(__fsub_rn(d, u), 0.5f);
-    return shadow_from_gradient(g_col, g_row, P.dxf, P.dyf, S, P.cos_thr, P.tan_thr);
+    return shadow_from_gradient(g_col, g_row, P.dxf, P.dyf, S, P.cos_thr, P.tan_thr) ? 0u : 0x200u;
 }
 
-#ifndef PB200_FAST_MIN_CTAS
-#define PB200_FAST_MIN_CTAS 2      // 128 registers, no spills: measured faster than 3 CTAs with spills (profiles/)
-#endif
+// ---------------------------------------------------------------------------
 template <bool OPTIONAL_LAYERS>
-__global__ void __launch_bounds__(FT_THREADS, PB200_FAST_MIN_CTAS)
+__global__ void __launch_bounds__(FT_THREADS, 2)
 dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__restrict__ tmaps,
                        const FusedTables *__restrict__ tables, const ItemDesc *__restrict__ items, int n_items,
                        const __grid_constant__ DevParams P, const __grid_constant__ FastParams F) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FastSmem &s = *reinterpret_cast<FastSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int half = warp & 1;                            // which 128-pixel half of the item
+    const int rgrp = warp >> 1;                           // which group of 4 rows
 
     // ---- tables: once per CTA -------------------------------------------------
     {
@@ -225,291 +196,234 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
             // async-proxy writes by the barrier above plus this fence
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(&s.mbar, 2u * DEM_BOX_BYTES);
-            const int gx = s.tile.dem_off_x + x0 - 4 - padx, gy = s.tile.dem_off_y + y0 - 1;
+            const int gx = s.tile.dem_off_x + x0 - padx, gy = s.tile.dem_off_y + y0 - 1;
             tma_load_2d(&s.dem[0].v[0][0], &tmaps[item.tile], gx, gy, &s.mbar);
             tma_load_2d(&s.dem[1].v[0][0], &tmaps[item.tile], gx + 128, gy, &s.mbar);
         }
         const float sa = (float)s.tile.sin_az, ca = (float)s.tile.cos_az;
         const float sx = (float)s.tile.sx, sy = (float)s.tile.sy, sz = (float)s.tile.sz;
         const bool want_shad = OPTIONAL_LAYERS && s.tile.shad != nullptr;
+        // the four graded layers present: one test instead of four in the row loop
+        const bool all_graded = s.tile.diag && s.tile.wtr && s.tile.bwtr && s.tile.conf;
 
         uint32_t acc_valid = 0, acc_cv = 0, acc_nno = 0;
         unsigned long long acc_hist = 0ull;
         bool dem_ready = !has_dem;
 
+        const int x = x0 + 128 * half + 4 * lane;         // this lane's 4 pixels
+        if (x < W) {
 #pragma unroll 1
-        for (int rr = 0; rr < FT_ROWS_PER_WARP; ++rr) {
-            const int ly = warp * FT_ROWS_PER_WARP + rr;
-            const int y = y0 + ly;
-            if (y >= H) break;                            // warp-uniform
-            const uint32_t rowoff = (uint32_t)y * (uint32_t)W;      // < 2^32 checked on the host
-            const int shift = (int)(rowoff & 4u);         // odd rows of a 3660-wide raster start 8 B off a 16-B boundary
-            const int x = x0 - shift + 8 * lane;          // first of this lane's 8 pixels (may be -4)
-            const bool va = x >= 0 && x < W;
-            const bool vb = x + 4 < W;
-            if (!va && !vb) continue;
-            const uint32_t pix = rowoff + (uint32_t)x;    // multiple of 8
+            for (int rr = 0; rr < FT_ROWS_PER_WARP; ++rr) {
+                const int ly = rgrp * FT_ROWS_PER_WARP + rr;
+                const int y = y0 + ly;
+                if (y >= H) break;                        // warp-uniform
+                const uint32_t pix = (uint32_t)y * (uint32_t)W + (uint32_t)x;     // < 2^32 checked on the host
 
-            // ---- loads ---------------------------------------------------------------
-            // A lane with one quad outside the row (x = -4 on a shifted row, or the row's
-            // last quad) still loads all 8 pixels: the other 4 belong to the neighbouring
-            // row of the same plane, are in bounds, and their results are never stored or
-            // counted.  Only the raster's last row takes the guarded loads.
-            uint32_t w[6][4], fm8[2], ld8[2], oc8[2];
-            ld8[0] = ld8[1] = 0xffffffffu;
-            oc8[0] = oc8[1] = 0x01010101u;
-            if (y != H - 1) {
+                // ---- loads: 8 bytes per band, 4 bytes per byte raster ------------------
+                uint32_t w[6][2];
 #pragma unroll
                 for (int k = 0; k < 6; ++k) {
-                    const int4 v = ldg_stream_v4(s.tile.band[k] + pix);
-                    w[k][0] = (uint32_t)v.x; w[k][1] = (uint32_t)v.y; w[k][2] = (uint32_t)v.z; w[k][3] = (uint32_t)v.w;
+                    const int2 v = ldg_stream_v2(s.tile.band[k] + pix);
+                    w[k][0] = (uint32_t)v.x; w[k][1] = (uint32_t)v.y;
                 }
-                const int2 f = ldg_stream_v2(s.tile.fmask + pix);
-                fm8[0] = (uint32_t)f.x; fm8[1] = (uint32_t)f.y;
-                if (has_land) {
-                    const int2 v = ldg_stream_v2(s.tile.land + pix);
-                    ld8[0] = (uint32_t)v.x; ld8[1] = (uint32_t)v.y;
-                }
-                if (has_ocean) {
-                    const int2 v = ldg_stream_v2(s.tile.ocean + pix);
-                    oc8[0] = (uint32_t)v.x; oc8[1] = (uint32_t)v.y;
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < 6; ++k) load_u16x8(s.tile.band[k] + pix, va, vb, w[k]);
-                load_u8x8(s.tile.fmask + pix, va, vb, 0u, fm8);
-                if (has_land) load_u8x8(s.tile.land + pix, va, vb, 0xffffffffu, ld8);
-                if (has_ocean) load_u8x8(s.tile.ocean + pix, va, vb, 0x01010101u, oc8);
-            }
+                const uint32_t fm4 = ldg_stream_u32(s.tile.fmask + pix);
+                uint32_t ld4 = 0xffffffffu, oc4 = 0x01010101u;          // no LAND class / not ocean
+                if (has_land) ld4 = ldg_stream_u32(s.tile.land + pix);
+                if (has_ocean) oc4 = ldg_stream_u32(s.tile.ocean + pix);
 
-            uint32_t idx[8], o[8], dgw[4], k1p[4];
+                uint32_t idx[4], o[4], dgw[2], k1p[2];
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                // ================= packed stage: pixels 2p, 2p+1 =====================
-                const uint32_t selb = (p & 1) ? 0x4342u : 0x4140u;          // bytes -> 16-bit halves
-                const uint32_t fmw = fm8[p >> 1];
-                const uint32_t fmh = __byte_perm(fmw, 0u, selb);             // Fmask values as halves
-                uint32_t xm;
-                {
-                    uint32_t xf[6];
+                for (int p = 0; p < 2; ++p) {
+                    // ================= packed stage: pixels 2p, 2p+1 =================
+                    const uint32_t selb = p ? 0x4342u : 0x4140u;              // bytes -> 16-bit halves
+                    const uint32_t fmh = __byte_perm(fm4, 0u, selb);          // Fmask values as halves
+                    uint32_t xm;
+                    {
+                        uint32_t xf[6];
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) xf[k] = (w[k][p] ^ F.fill_xor[k]) | F.fill_or[k];   // D:2204-2207
-                    const uint32_t xfm = __byte_perm(fmw ^ F.fmask_xor4, 0u, selb) | F.fmask_or;
-                    xm = __vimin3_u16x2(__vimin3_u16x2(xf[0], xf[1], xf[2]), xf[3], xf[4]);
-                    xm = __vimin3_u16x2(xm, xf[5], xfm);                     // half == 0 <=> pixel invalid
-                }
-                const uint32_t nz = __vminu2(xm, 0x00010001u);               // 1 = valid
-                uint32_t comb = nz + 0x00020002u;                            // | not_ocean << 1
-                if (has_ocean) {
-                    const uint32_t ob = __vminu2(__byte_perm(oc8[p >> 1], 0u, selb), 0x00010001u);
-                    comb = ob * 2u + nz;                                     // D:5245: ocean == 0 is masked
-                }
-                const uint32_t B = __vmaxs2(w[0][p], 0x00010001u), G = __vmaxs2(w[1][p], 0x00010001u);   // D:2299
-                const uint32_t R = __vmaxs2(w[2][p], 0x00010001u), N = __vmaxs2(w[3][p], 0x00010001u);
-                const uint32_t S1 = __vmaxs2(w[4][p], 0x00010001u), S2 = __vmaxs2(w[5][p], 0x00010001u);
-                const uint32_t gs = __vadd2(G, S1), gd = __vsub2(G, S1);                                 // D:1872
-                const uint32_t gr = __vadd2(G, R), ns = __vadd2(N, S1);                                  // D:1875-1878
-                const uint32_t nrs = __vadd2(N, R), nrd = __vsub2(N, R);                                 // D:1884
-                const bool slow = ((gs | gr | ns | nrs) & 0x80008000u) != 0u;      // some int16 sum wrapped
-                const uint32_t T4 = __viaddmax_s16x2(N, F.m_p1nir, __vadd2(S1, F.m_p1swir1));           // < 0 <=> all below
-                const uint32_t T5 = __viaddmax_s16x2(N, F.m_p2nir, __viaddmax_s16x2(S2, F.m_p2swir2,
-                                    __viaddmax_s16x2(S1, F.m_p2swir1, __vadd2(B, F.m_p2blue))));
-                const uint32_t tn = __vadd2(N, F.m_nle);                     // sign <=> nir <= 1000      (D:1239)
-                const uint32_t tb = __vadd2(N, F.m_lc);                      // sign <=> !(nir > lcmask)  (D:1354)
-                // fmask value | (nir <= 1000) << 11, and bright << 10, per half
-                const uint32_t fa = fmh | ((tn >> 4) & 0x08000800u);
-                const uint32_t brp = (~tb >> 5) & 0x04000400u;
+                        for (int k = 0; k < 6; ++k) xf[k] = (w[k][p] ^ F.fill_xor[k]) | F.fill_or[k];   // D:2204-2207
+                        const uint32_t xfm = __byte_perm(fm4 ^ F.fmask_xor4, 0u, selb) | F.fmask_or;
+                        xm = __vimin3_u16x2(__vimin3_u16x2(xf[0], xf[1], xf[2]), xf[3], xf[4]);
+                        xm = __vimin3_u16x2(xm, xf[5], xfm);                  // half == 0 <=> pixel invalid
+                    }
+                    const uint32_t nz = __vminu2(xm, 0x00010001u);            // 1 = valid
+                    const uint32_t ob = __vminu2(__byte_perm(oc4, 0u, selb), 0x00010001u);   // D:5245: 0 is masked
+                    const uint32_t comb = ob * 2u + nz;
+                    const uint32_t B = __vmaxs2(w[0][p], 0x00010001u), G = __vmaxs2(w[1][p], 0x00010001u);   // D:2299
+                    const uint32_t R = __vmaxs2(w[2][p], 0x00010001u), N = __vmaxs2(w[3][p], 0x00010001u);
+                    const uint32_t S1 = __vmaxs2(w[4][p], 0x00010001u), S2 = __vmaxs2(w[5][p], 0x00010001u);
+                    const uint32_t gs = __vadd2(G, S1), gd = __vsub2(G, S1);                                 // D:1872
+                    const uint32_t gr = __vadd2(G, R), ns = __vadd2(N, S1);                                  // D:1875-1878
+                    const uint32_t nrs = __vadd2(N, R), nrd = __vsub2(N, R);                                 // D:1884
+                    const bool slow = ((gs | gr | ns | nrs) & 0x80008000u) != 0u;      // some int16 sum wrapped
+                    const uint32_t T4 = __viaddmax_s16x2(N, F.m_p1nir, __vadd2(S1, F.m_p1swir1));           // < 0 <=> all below
+                    const uint32_t T5 = __viaddmax_s16x2(N, F.m_p2nir, __viaddmax_s16x2(S2, F.m_p2swir2,
+                                        __viaddmax_s16x2(S1, F.m_p2swir1, __vadd2(B, F.m_p2blue))));
+                    const uint32_t tn = __vadd2(N, F.m_nle);                  // sign <=> nir <= 1000      (D:1239)
+                    const uint32_t tb = __vadd2(N, F.m_lc);                   // sign <=> !(nir > lcmask)  (D:1354)
+                    // fmask value | (nir <= 1000) << 11, and bright << 10, per half
+                    const uint32_t fa = fmh | ((tn >> 4) & 0x08000800u);
+                    const uint32_t brp = (~tb >> 5) & 0x04000400u;
 
-                uint32_t dcode[2];
-                if (!slow) {
-                    bool p2h, p2l;
-                    (void)__vibmax_s16x2(ns, gr, &p2h, &p2l);                // pred = mbsrn >= mbsrv -> test 2 is its negation
+                    uint32_t dcode[2];
+                    if (!slow) {
+                        bool p2h, p2l;
+                        (void)__vibmax_s16x2(ns, gr, &p2h, &p2l);             // pred = mbsrn >= mbsrv: test 2 is its negation
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const bool hi = hh;
+                            const int n1 = hi ? sext_hi(gd) : sext_lo(gd);
+                            const int q1 = hi ? (int)(gs >> 16) : (int)(gs & 0xffffu);
+                            const int n2 = hi ? sext_hi(nrd) : sext_lo(nrd);
+                            const int q2 = hi ? (int)(nrs >> 16) : (int)(nrs & 0xffffu);
+                            // sign set <=> test true:  a*q - p*b - 1 < 0 <=> p*b >= a*q
+                            const int x0w = F.ra[RB_WIGT] * q1 - n1 * F.rb[RB_WIGT] - 1;
+                            const int x1w = F.ra[RB_P1_MNDWI] * q1 - n1 * F.rb[RB_P1_MNDWI] - 1;
+                            const int x2w = F.ra[RB_P2_MNDWI] * q1 - n1 * F.rb[RB_P2_MNDWI] - 1;
+                            const int x3w = n2 * F.rb[RB_P1_NDVI] - F.ra[RB_P1_NDVI] * q2 - 1;   // p*b <= a*q
+                            // 4*awesh: init - 4B - 10G + 6*mbsrn + S2 < 0 <=> awesh > awgt
+                            const int cb = hi ? 8 : 0;
+                            int aw = F.awesh_init;
+                            aw = __dp2a_lo((int)B, (int)(0xFCu << cb), aw);
+                            aw = __dp2a_lo((int)G, (int)(0xF6u << cb), aw);
+                            aw = __dp2a_lo((int)ns, (int)(0x06u << cb), aw);
+                            aw = __dp2a_lo((int)S2, (int)(0x01u << cb), aw);
+                            const uint32_t sh16 = hi ? 0u : 16u;
+                            const uint32_t t2w = (hi ? p2h : p2l) ? 0u : 0x80000000u;
+                            const uint32_t t4w = (uint32_t)x1w & (uint32_t)x3w & (T4 << sh16);
+                            const uint32_t t5w = (uint32_t)x2w & (T5 << sh16);
+                            uint32_t d = t5w >> 31;
+                            d = __funnelshift_l(t4w, d, 1);
+                            d = __funnelshift_l((uint32_t)aw, d, 1);
+                            d = __funnelshift_l(t2w, d, 1);
+                            d = __funnelshift_l((uint32_t)x0w, d, 1);
+                            dcode[hh] = d;
+                        }
+                    } else {
+                        const uint32_t dd = diag_pair_slow(B, G, R, N, S1, S2, P);
+                        dcode[0] = dd & 31u;
+                        dcode[1] = dd >> 8;
+                    }
+
+                    // ================= per pixel: tables ================================
+                    uint32_t dl[2];
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
                         const bool hi = hh;
-                        const int n1 = hi ? sext_hi(gd) : sext_lo(gd);
-                        const int q1 = hi ? (int)(gs >> 16) : (int)(gs & 0xffffu);
-                        const int n2 = hi ? sext_hi(nrd) : sext_lo(nrd);
-                        const int q2 = hi ? (int)(nrs >> 16) : (int)(nrs & 0xffffu);
-                        // sign set <=> test true:  a*q - p*b - 1 < 0 <=> p*b >= a*q
-                        const int x0w = F.ra[RB_WIGT] * q1 - n1 * F.rb[RB_WIGT] - 1;
-                        const int x1w = F.ra[RB_P1_MNDWI] * q1 - n1 * F.rb[RB_P1_MNDWI] - 1;
-                        const int x2w = F.ra[RB_P2_MNDWI] * q1 - n1 * F.rb[RB_P2_MNDWI] - 1;
-                        const int x3w = n2 * F.rb[RB_P1_NDVI] - F.ra[RB_P1_NDVI] * q2 - 1;   // p*b <= a*q
-                        // 4*awesh: init - 4B - 10G + 6*mbsrn + S2 < 0 <=> awesh > awgt
-                        const int cb = hi ? 8 : 0;
-                        int aw = F.awesh_init;
-                        aw = __dp2a_lo((int)B, (int)(0xFCu << cb), aw);
-                        aw = __dp2a_lo((int)G, (int)(0xF6u << cb), aw);
-                        aw = __dp2a_lo((int)ns, (int)(0x06u << cb), aw);
-                        aw = __dp2a_lo((int)S2, (int)(0x01u << cb), aw);
-                        const uint32_t sh16 = hi ? 0u : 16u;
-                        const uint32_t t2w = (hi ? p2h : p2l) ? 0u : 0x80000000u;
-                        const uint32_t t4w = (uint32_t)x1w & (uint32_t)x3w & (T4 << sh16);
-                        const uint32_t t5w = (uint32_t)x2w & (T5 << sh16);
-                        uint32_t d = t5w >> 31;
-                        d = __funnelshift_l(t4w, d, 1);
-                        d = __funnelshift_l((uint32_t)aw, d, 1);
-                        d = __funnelshift_l(t2w, d, 1);
-                        d = __funnelshift_l((uint32_t)x0w, d, 1);
-                        dcode[hh] = d;
+                        const int j = 2 * p + hh;
+                        const uint32_t cm = hi ? ((comb >> 11) & 0x60u) : ((comb << 5) & 0x60u);
+                        dl[hh] = s.diag_lut[dcode[hh] | cm];                  // D:5227-5231, 5245, 5249
+                        const uint32_t k1s = dl[hh] >> 16;                    // k1 << 8
+                        const uint32_t fi = hi ? ((fa >> 16) | k1s) : ((fa & 0xffffu) | k1s);
+                        const uint32_t ev = s.fk_lut[fi];                     // D:1237-1246, 1984-1991, 2081
+                        const uint32_t cat = s.land_lut[(ld4 >> (8 * j)) & 255u];
+                        const uint32_t bri = hi ? (brp >> 16) : (brp & 0xffffu);
+                        idx[j] = ev | bri | (cat << 7);
+                        o[j] = s.big_lut[idx[j]];                             // D:1349-1376 (no shadow yet), 2084-2131, 1727, 1793-1835
                     }
-                } else {
-                    const uint32_t dd = diag_pair_slow(B, G, R, N, S1, S2, P);
-                    dcode[0] = dd & 31u;
-                    dcode[1] = dd >> 8;
+                    dgw[p] = __byte_perm(dl[0], dl[1], 0x5410);               // two DIAG values
+                    if (OPTIONAL_LAYERS) k1p[p] = __byte_perm(dl[0], dl[1], 0x4743);   // k1 of the two pixels in bytes 0 and 2
                 }
 
-                // ================= per pixel: tables ====================================
-                uint32_t dl[2];
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    const bool hi = hh;
-                    const int j = 2 * p + hh;
-                    const uint32_t cm = hi ? ((comb >> 11) & 0x60u) : ((comb << 5) & 0x60u);
-                    dl[hh] = s.diag_lut[dcode[hh] | cm];                      // D:5227-5231, 5245, 5249
-                    const uint32_t k1s = dl[hh] >> 16;                        // k1 << 8
-                    const uint32_t fi = hi ? ((fa >> 16) | k1s) : ((fa & 0xffffu) | k1s);
-                    const uint32_t ev = s.fk_lut[fi];                         // D:1237-1246, 1984-1991, 2081
-                    const uint32_t lb = (ld8[p >> 1] >> (8 * (j & 3))) & 255u;
-                    const uint32_t cat = has_land ? (uint32_t)s.land_lut[lb] : (uint32_t)LC_NONE;
-                    const uint32_t bri = hi ? (brp >> 16) : (brp & 0xffffu);
-                    idx[j] = ev | bri | (cat << 7);
-                    o[j] = s.big_lut[idx[j]];                                 // D:1349-1376 (no shadow yet), 2084-2131, 1727, 1793-1835
-                }
-                dgw[p] = __byte_perm(dl[0], dl[1], 0x5410);                   // two DIAG values
-                if (OPTIONAL_LAYERS) k1p[p] = __byte_perm(dl[0], dl[1], 0x4743);   // k1 of the two pixels in bytes 0 and 2
-            }
-
-            // ---- terrain shadow: only where it can change the result --------------------
-            const uint32_t sens = o[0] | o[1] | o[2] | o[3] | o[4] | o[5] | o[6] | o[7];
-            uint32_t shmask = 0u;                                             // bit j: pixel j is in shadow
-            if (has_dem && (want_shad || (sens & FL_SHADOW_SENSITIVE))) {
-                if (!dem_ready) {
-                    mbar_wait(&s.mbar, dem_phase);
-                    dem_ready = true;
-                }
-                const int half = lane >> 4;
-                const int sc = 8 * (lane & 15) - shift + 4 + padx;            // smem column of this lane's first pixel
-                const float *rm = &s.dem[half].v[ly + 1][sc];
-                const float *ru = &s.dem[half].v[ly][sc];
-                const float *rd = &s.dem[half].v[ly + 2][sc];
-                float m[10], u[8], d[8];
-                if ((padx & 3) == 2) {
-                    // production alignment (DEM margin 50): sc = 2 mod 4 -> 8-byte / 16-byte vectors
-                    const float2 m0 = *reinterpret_cast<const float2 *>(rm - 2);
-                    const float2 m1 = *reinterpret_cast<const float2 *>(rm);
-                    const float4 m2 = *reinterpret_cast<const float4 *>(rm + 2);
-                    const float4 m3 = *reinterpret_cast<const float4 *>(rm + 6);
-                    m[0] = m0.y; m[1] = m1.x; m[2] = m1.y;
-                    m[3] = m2.x; m[4] = m2.y; m[5] = m2.z; m[6] = m2.w;
-                    m[7] = m3.x; m[8] = m3.y; m[9] = m3.z;
-                    const float2 u0 = *reinterpret_cast<const float2 *>(ru);
-                    const float4 u1 = *reinterpret_cast<const float4 *>(ru + 2);
-                    const float2 u2 = *reinterpret_cast<const float2 *>(ru + 6);
-                    u[0] = u0.x; u[1] = u0.y; u[2] = u1.x; u[3] = u1.y; u[4] = u1.z; u[5] = u1.w; u[6] = u2.x; u[7] = u2.y;
-                    const float2 d0 = *reinterpret_cast<const float2 *>(rd);
-                    const float4 d1 = *reinterpret_cast<const float4 *>(rd + 2);
-                    const float2 d2 = *reinterpret_cast<const float2 *>(rd + 6);
-                    d[0] = d0.x; d[1] = d0.y; d[2] = d1.x; d[3] = d1.y; d[4] = d1.z; d[5] = d1.w; d[6] = d2.x; d[7] = d2.y;
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 10; ++j) m[j] = rm[j - 1];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) { u[j] = ru[j]; d[j] = rd[j]; }
-                }
-                uint32_t undecided = F.fast_shadow_ok ? 0u : 0xffu;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint32_t r = shadow_fast(m[j], m[j + 2], u[j], d[j], F, sa, ca, sx, sy, sz);
-                    shmask |= (r == 0u ? 1u : 0u) << j;
-                    undecided |= (r == 2u ? 1u : 0u) << j;
-                }
-                if (undecided) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if ((undecided >> j) & 1u) {
-                            const uint32_t r = shadow_exact(m[j], m[j + 2], u[j], d[j], P, s.tile);
-                            shmask = (shmask & ~(1u << j)) | ((r == 0u ? 1u : 0u) << j);
-                        }
+                // ---- terrain shadow: only where it can change the result ----------------
+                uint32_t shw[4] = {0u, 0u, 0u, 0u};                           // 0x200 = in shadow
+                if (has_dem && (want_shad || ((o[0] | o[1] | o[2] | o[3]) & FL_SHADOW_SENSITIVE))) {
+                    if (!dem_ready) {
+                        mbar_wait(&s.mbar, dem_phase);
+                        dem_ready = true;
                     }
+                    const int sc = 4 * lane + padx;                           // smem column of this lane's first pixel
+                    const float *rm = &s.dem[half].v[ly + 1][sc];
+                    const float *ru = &s.dem[half].v[ly][sc];
+                    const float *rd = &s.dem[half].v[ly + 2][sc];
+                    float m[6], u[4], d[4];
+                    if ((padx & 1) == 0) {
+                        // even DEM margins (production: 50): 8-byte vectors
+                        const float2 m0 = *reinterpret_cast<const float2 *>(rm - 2);
+                        const float2 m1 = *reinterpret_cast<const float2 *>(rm);
+                        const float2 m2 = *reinterpret_cast<const float2 *>(rm + 2);
+                        const float2 m3 = *reinterpret_cast<const float2 *>(rm + 4);
+                        m[0] = m0.y; m[1] = m1.x; m[2] = m1.y; m[3] = m2.x; m[4] = m2.y; m[5] = m3.x;
+                        const float2 u0 = *reinterpret_cast<const float2 *>(ru);
+                        const float2 u1 = *reinterpret_cast<const float2 *>(ru + 2);
+                        u[0] = u0.x; u[1] = u0.y; u[2] = u1.x; u[3] = u1.y;
+                        const float2 d0 = *reinterpret_cast<const float2 *>(rd);
+                        const float2 d1 = *reinterpret_cast<const float2 *>(rd + 2);
+                        d[0] = d0.x; d[1] = d0.y; d[2] = d1.x; d[3] = d1.y;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) m[j] = rm[j - 1];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { u[j] = ru[j]; d[j] = rd[j]; }
+                    }
+                    bool undecided = (F.fast_shadow_ok == 0u);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        shw[j] = shadow_fast(m[j], m[j + 2], u[j], d[j], F, sa, ca, sx, sy, sz, &undecided);
+                    if (undecided) {
+                        // rare: redo the 4 pixels with the float64 reference sequence
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) shw[j] = shadow_exact(m[j], m[j + 2], u[j], d[j], P, s.tile);
+                    }
+                    // look the pixels up again with the shadow bit (D:1331-1344)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) o[j] = s.big_lut[idx[j] | shw[j]];
                 }
-                // look the pixels up again with the shadow bit (D:1331-1344)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = s.big_lut[idx[j] | (((shmask >> j) & 1u) << 9)];
-            }
 
-            // ---- pack and store --------------------------------------------------------
-            uint32_t wtr2w[2], bwtr2w[2], conf2w[2], flag2w[2];
-#pragma unroll
-            for (int qd = 0; qd < 2; ++qd) {
-                const uint32_t *oq = &o[4 * qd];
-                const uint32_t t01a = __byte_perm(oq[0], oq[1], 0x5140);
-                const uint32_t t23a = __byte_perm(oq[2], oq[3], 0x5140);
-                const uint32_t t01b = __byte_perm(oq[0], oq[1], 0x7362);
-                const uint32_t t23b = __byte_perm(oq[2], oq[3], 0x7362);
-                wtr2w[qd] = __byte_perm(t01a, t23a, 0x5410);
-                bwtr2w[qd] = __byte_perm(t01a, t23a, 0x7632);
-                conf2w[qd] = __byte_perm(t01b, t23b, 0x5410);
-                flag2w[qd] = __byte_perm(t01b, t23b, 0x7632);
-            }
-            if (s.tile.diag) {
-                uint16_t *dp = s.tile.diag + pix;
-                if (va && vb) stg_stream_v4(dp, dgw[0], dgw[1], dgw[2], dgw[3]);
-                else if (va) stg_stream_v2(dp, dgw[0], dgw[1]);
-                else stg_stream_v2(dp + 4, dgw[2], dgw[3]);
-            }
-            if (s.tile.wtr) store_u8x8(s.tile.wtr + pix, va, vb, wtr2w[0], wtr2w[1]);
-            if (s.tile.bwtr) store_u8x8(s.tile.bwtr + pix, va, vb, bwtr2w[0], bwtr2w[1]);
-            if (s.tile.conf) store_u8x8(s.tile.conf + pix, va, vb, conf2w[0], conf2w[1]);
+                // ---- pack and store -------------------------------------------------------
+                const uint32_t t01a = __byte_perm(o[0], o[1], 0x5140);
+                const uint32_t t23a = __byte_perm(o[2], o[3], 0x5140);
+                const uint32_t t01b = __byte_perm(o[0], o[1], 0x7362);
+                const uint32_t t23b = __byte_perm(o[2], o[3], 0x7362);
+                const uint32_t wtr4 = __byte_perm(t01a, t23a, 0x5410);
+                const uint32_t bwtr4 = __byte_perm(t01a, t23a, 0x7632);
+                const uint32_t conf4 = __byte_perm(t01b, t23b, 0x5410);
+                const uint32_t flag4 = __byte_perm(t01b, t23b, 0x7632);
+                if (all_graded) {
+                    stg_stream_v2(s.tile.diag + pix, dgw[0], dgw[1]);
+                    stg_stream_u32(s.tile.wtr + pix, wtr4);
+                    stg_stream_u32(s.tile.bwtr + pix, bwtr4);
+                    stg_stream_u32(s.tile.conf + pix, conf4);
+                } else {
+                    if (s.tile.diag) stg_stream_v2(s.tile.diag + pix, dgw[0], dgw[1]);
+                    if (s.tile.wtr) stg_stream_u32(s.tile.wtr + pix, wtr4);
+                    if (s.tile.bwtr) stg_stream_u32(s.tile.bwtr + pix, bwtr4);
+                    if (s.tile.conf) stg_stream_u32(s.tile.conf + pix, conf4);
+                }
 
-            if (OPTIONAL_LAYERS) {
-                const uint32_t cls_lo = P.cls_lut[0] | (P.cls_lut[1] << 8) | (P.cls_lut[2] << 16) | (P.cls_lut[3] << 24);
-                const uint32_t cls_hi = P.cls_lut[4] | (P.cls_lut[5] << 8) | (P.cls_lut[6] << 16) | (P.cls_lut[7] << 24);
-                uint32_t w1[2], w1r[2], w2[2], cl[2], shd[2];
-#pragma unroll
-                for (int qd = 0; qd < 2; ++qd) {
+                if (OPTIONAL_LAYERS) {
+                    const uint32_t cls_lo = P.cls_lut[0] | (P.cls_lut[1] << 8) | (P.cls_lut[2] << 16) | (P.cls_lut[3] << 24);
+                    const uint32_t cls_hi = P.cls_lut[4] | (P.cls_lut[5] << 8) | (P.cls_lut[6] << 16) | (P.cls_lut[7] << 24);
                     uint32_t sel1r = 0, sel2 = 0, c4 = 0, s4 = 0;
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int j = 4 * qd + jj;
+                    for (int j = 0; j < 4; ++j) {
                         const uint32_t kb = idx[j] & 7u, c = (idx[j] >> 3) & 15u;
-                        const uint32_t shb = (shmask >> j) & 1u;
+                        const uint32_t shb = shw[j] >> 9;
                         // kill_lut index: kb | shadowed<<3 | bright<<4 | cat<<5  (bright = idx bit 10, cat = idx bits 7-8)
                         const uint32_t k2 = s.kill_lut[kb | (shb << 3) | ((idx[j] >> 6) & 0x10u) | ((idx[j] >> 2) & 0x60u)];
-                        sel1r |= kb << (4 * jj);
-                        sel2 |= k2 << (4 * jj);
-                        c4 |= (k2 == 7u ? 255u : c) << (8 * jj);                                   // D:2084
-                        s4 |= (shb ^ 1u) << (8 * jj);
+                        sel1r |= kb << (4 * j);
+                        sel2 |= k2 << (4 * j);
+                        c4 |= (k2 == 7u ? 255u : c) << (8 * j);                                    // D:2084
+                        s4 |= (shb ^ 1u) << (8 * j);
                     }
                     // k1p[p]: byte 0 = k1 of pixel 2p, byte 2 = k1 of pixel 2p+1
-                    const uint32_t ka = k1p[2 * qd], kc = k1p[2 * qd + 1];
-                    const uint32_t sel1 = (ka & 7u) | ((ka >> 12) & 0x70u) | ((kc & 7u) << 8) | ((kc >> 4) & 0x7000u);
-                    w1[qd] = __byte_perm(cls_lo, cls_hi, sel1);
-                    w1r[qd] = __byte_perm(cls_lo, cls_hi, sel1r);
-                    w2[qd] = __byte_perm(cls_lo, cls_hi, sel2);
-                    cl[qd] = c4;
-                    shd[qd] = s4;
+                    const uint32_t sel1 = (k1p[0] & 7u) | ((k1p[0] >> 12) & 0x70u) | ((k1p[1] & 7u) << 8) |
+                                          ((k1p[1] >> 4) & 0x7000u);
+                    if (s.tile.cloud) stg_stream_u32(s.tile.cloud + pix, c4);
+                    if (s.tile.wtr1) stg_stream_u32(s.tile.wtr1 + pix, __byte_perm(cls_lo, cls_hi, sel1));
+                    if (s.tile.wtr1r) stg_stream_u32(s.tile.wtr1r + pix, __byte_perm(cls_lo, cls_hi, sel1r));
+                    if (s.tile.wtr2) stg_stream_u32(s.tile.wtr2 + pix, __byte_perm(cls_lo, cls_hi, sel2));
+                    if (s.tile.shad) stg_stream_u32(s.tile.shad + pix, s4);
                 }
-                if (s.tile.cloud) store_u8x8(s.tile.cloud + pix, va, vb, cl[0], cl[1]);
-                if (s.tile.wtr1) store_u8x8(s.tile.wtr1 + pix, va, vb, w1[0], w1[1]);
-                if (s.tile.wtr1r) store_u8x8(s.tile.wtr1r + pix, va, vb, w1r[0], w1r[1]);
-                if (s.tile.wtr2) store_u8x8(s.tile.wtr2 + pix, va, vb, w2[0], w2[1]);
-                if (s.tile.shad) store_u8x8(s.tile.shad + pix, va, vb, shd[0], shd[1]);
-            }
 
-            // ---- counters (D:5104-5111) from the flag bytes ---------------------------------
-            if (has_counters) {
-#pragma unroll
-                for (int qd = 0; qd < 2; ++qd) {
-                    if (qd == 0 ? !va : !vb) continue;
-                    acc_valid += __popc(flag2w[qd] & 0x01010101u);
-                    acc_cv += __popc(flag2w[qd] & 0x02020202u);
-                    acc_nno = has_ocean ? __dp4a(oc8[qd], 0x01010101u, acc_nno) : acc_nno + 4u;   // D:5105 / D:5107
+                // ---- counters (D:5104-5111) from the flag bytes -----------------------------
+                if (has_counters) {
+                    acc_valid += __popc(flag4 & 0x01010101u);
+                    acc_cv += __popc(flag4 & 0x02020202u);
+                    acc_nno = __dp4a(oc4, 0x01010101u, acc_nno);               // D:5105; no shoreline: 1 per pixel (D:5107)
                     if (histogram) {
 #pragma unroll
-                        for (int jj = 0; jj < 4; ++jj)
-                            acc_hist += 1ull << (6u * ((flag2w[qd] >> (8 * jj + 4)) & 15u));
+                        for (int j = 0; j < 4; ++j) acc_hist += 1ull << (6u * ((flag4 >> (8 * j + 4)) & 15u));
                     }
                 }
             }
