@@ -34,10 +34,15 @@
 
 namespace pb200 {
 
-constexpr int FT_W = 256;          // item width: two 128-pixel halves, one warp (32 lanes x 4 px) each
-constexpr int FT_H = 32;           // item height: 8 warp pairs x 4 rows
-constexpr int FT_THREADS = 512;
-constexpr int FT_ROWS_PER_WARP = FT_H / (FT_THREADS / 64);
+#ifndef PB200_FT_HALVES
+#define PB200_FT_HALVES 1          // 128-pixel halves per item: 1 -> 256-thread CTAs (4 per SM), 2 -> 512-thread CTAs
+#endif
+constexpr int FT_HALVES = PB200_FT_HALVES;
+constexpr int FT_W = 128 * FT_HALVES;   // item width: one warp (32 lanes x 4 px) per 128-pixel half
+constexpr int FT_H = 32;                // item height: 8 row groups x 4 rows
+constexpr int FT_THREADS = 256 * FT_HALVES;
+constexpr int FT_ROWS_PER_WARP = 4;
+constexpr int FT_MIN_CTAS = 1024 / FT_THREADS;   // 64 registers per thread
 // DEM staging: one TMA box per 128-pixel half (a box is at most 256 elements
 // wide).  Box start = dem_off_x + x0 + 128*half - padx with padx = 4 +
 // (dem_off_x & 3): a multiple of 4 floats (UTMALDG needs a 16-byte aligned box
@@ -79,7 +84,7 @@ struct __align__(128) DemHalf { float v[FT_SMH][FT_SMW]; };   // TMA destination
 constexpr uint32_t DEM_BOX_BYTES = FT_SMH * FT_SMW * sizeof(float);
 
 struct __align__(128) FastSmem {
-    DemHalf dem[2];                     // left / right 128-px half of the item
+    DemHalf dem[FT_HALVES];             // one box per 128-px half of the item
     uint32_t big_lut[2048];
     uint32_t diag_lut[128];
     uint8_t  fk_lut[4096];
@@ -148,15 +153,15 @@ __device__ __noinline__ uint32_t shadow_exact(float l, float r, float u, float d
 
 // ---------------------------------------------------------------------------
 template <bool OPTIONAL_LAYERS>
-__global__ void __launch_bounds__(FT_THREADS, 2)
+__global__ void __launch_bounds__(FT_THREADS, FT_MIN_CTAS)
 dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__restrict__ tmaps,
                        const FusedTables *__restrict__ tables, const ItemDesc *__restrict__ items, int n_items,
                        const __grid_constant__ DevParams P, const __grid_constant__ FastParams F) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FastSmem &s = *reinterpret_cast<FastSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int half = warp & 1;                            // which 128-pixel half of the item
-    const int rgrp = warp >> 1;                           // which group of 4 rows
+    const int half = warp % FT_HALVES;                    // which 128-pixel half of the item
+    const int rgrp = warp / FT_HALVES;                    // which group of 4 rows
 
     // ---- tables: once per CTA -------------------------------------------------
     {
@@ -195,10 +200,11 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
             // the generic-proxy reads of the previous item are ordered before these
             // async-proxy writes by the barrier above plus this fence
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(&s.mbar, 2u * DEM_BOX_BYTES);
+            mbar_expect_tx(&s.mbar, (uint32_t)FT_HALVES * DEM_BOX_BYTES);
             const int gx = s.tile.dem_off_x + x0 - padx, gy = s.tile.dem_off_y + y0 - 1;
-            tma_load_2d(&s.dem[0].v[0][0], &tmaps[item.tile], gx, gy, &s.mbar);
-            tma_load_2d(&s.dem[1].v[0][0], &tmaps[item.tile], gx + 128, gy, &s.mbar);
+#pragma unroll
+            for (int hf = 0; hf < FT_HALVES; ++hf)
+                tma_load_2d(&s.dem[hf].v[0][0], &tmaps[item.tile], gx + 128 * hf, gy, &s.mbar);
         }
         const float sa = (float)s.tile.sin_az, ca = (float)s.tile.cos_az;
         const float sx = (float)s.tile.sx, sy = (float)s.tile.sy, sz = (float)s.tile.sz;
