@@ -334,6 +334,7 @@ static void build_fast_params(const pb200_params *p, const DevParams &D, FastPar
         const int f = p->band_fill[k];
         if (f == PB200_NO_FILL || f < -32768 || f > 32767) {
             F->fill_xor[k] = 0u; F->fill_or[k] = 0xffffffffu;          // never equal
+            F->any_nofill = 1u;
         } else {
             const uint32_t h = (uint32_t)f & 0xffffu;
             F->fill_xor[k] = h | (h << 16); F->fill_or[k] = 0u;

@@ -78,6 +78,7 @@ struct FastParams {
     float    kx, ky;                    // 0.5 / dxf, 0.5 / dyf
     float    tan32, e0, cc32;           // float32(tan_thr), 1e-6*|tan_thr| + 1e-30, c*|c| with c = cos_thr
     uint32_t fast_shadow_ok;            // thresholds are finite and |cos_thr| <= 1
+    uint32_t any_nofill;                // some band has no fill value (fill_or != 0)
 };
 
 struct __align__(128) DemHalf { float v[FT_SMH][FT_SMW]; };   // TMA destination: 128-B aligned
@@ -247,7 +248,11 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                     {
                         uint32_t xf[6];
 #pragma unroll
-                        for (int k = 0; k < 6; ++k) xf[k] = (w[k][p] ^ F.fill_xor[k]) | F.fill_or[k];   // D:2204-2207
+                        for (int k = 0; k < 6; ++k) xf[k] = w[k][p] ^ F.fill_xor[k];                   // D:2204-2207
+                        if (F.any_nofill) {                                   // rare: a raster without fill value
+#pragma unroll
+                            for (int k = 0; k < 6; ++k) xf[k] |= F.fill_or[k];
+                        }
                         const uint32_t xfm = __byte_perm(fm4 ^ F.fmask_xor4, 0u, selb) | F.fmask_or;
                         xm = __vimin3_u16x2(__vimin3_u16x2(xf[0], xf[1], xf[2]), xf[3], xf[4]);
                         xm = __vimin3_u16x2(xm, xf[5], xfm);                  // half == 0 <=> pixel invalid
@@ -298,7 +303,8 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                             const uint32_t t2w = (hi ? p2h : p2l) ? 0u : 0x80000000u;
                             const uint32_t t4w = (uint32_t)x1w & (uint32_t)x3w & (T4 << sh16);
                             const uint32_t t5w = (uint32_t)x2w & (T5 << sh16);
-                            uint32_t d = t5w >> 31;
+                            const uint32_t cpx = hi ? (comb >> 16) : (comb & 3u);   // valid | not_ocean << 1
+                            uint32_t d = __funnelshift_l(t5w, cpx, 1);
                             d = __funnelshift_l(t4w, d, 1);
                             d = __funnelshift_l((uint32_t)aw, d, 1);
                             d = __funnelshift_l(t2w, d, 1);
@@ -307,8 +313,8 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                         }
                     } else {
                         const uint32_t dd = diag_pair_slow(B, G, R, N, S1, S2, P);
-                        dcode[0] = dd & 31u;
-                        dcode[1] = dd >> 8;
+                        dcode[0] = (dd & 31u) | ((comb & 3u) << 5);
+                        dcode[1] = (dd >> 8) | ((comb >> 16) << 5);
                     }
 
                     // ================= per pixel: tables ================================
@@ -317,8 +323,7 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                     for (int hh = 0; hh < 2; ++hh) {
                         const bool hi = hh;
                         const int j = 2 * p + hh;
-                        const uint32_t cm = hi ? ((comb >> 11) & 0x60u) : ((comb << 5) & 0x60u);
-                        dl[hh] = s.diag_lut[dcode[hh] | cm];                  // D:5227-5231, 5245, 5249
+                        dl[hh] = s.diag_lut[dcode[hh]];                       // D:5227-5231, 5245, 5249
                         const uint32_t k1s = dl[hh] >> 16;                    // k1 << 8
                         const uint32_t fi = hi ? ((fa >> 16) | k1s) : ((fa & 0xffffu) | k1s);
                         const uint32_t ev = s.fk_lut[fi];                     // D:1237-1246, 1984-1991, 2081
