@@ -74,7 +74,7 @@ _REASONS = {0x4: 'sw_power_cap', 0x8: 'hw_slowdown', 0x20: 'sw_thermal_slowdown'
 
 
 class ClockSampler:
-    def __init__(self, device_index, period_s=0.02):
+    def __init__(self, device_index, period_s=float(os.environ.get('PB200_BENCH_NVML_PERIOD', '0.02'))):
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
         self._active = threading.Event()

@@ -374,6 +374,17 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+struct Arena {                  // grow-only device scratch, reused by every pb200_classify_host call
+    unsigned char *base = nullptr;
+    size_t cap = 0, used = 0;
+    void *take(size_t bytes) {
+        const size_t a = (used + 255) & ~(size_t)255;
+        if (a + bytes > cap) return nullptr;
+        used = a + bytes;
+        return base + a;
+    }
+};
+
 struct HostPipe {               // device mirror of one host tile (pb200_classify_host)
     size_t cap_px = 0, cap_dem = 0;
     int16_t *band[6] = {};
@@ -383,6 +394,7 @@ struct HostPipe {               // device mirror of one host tile (pb200_classif
     uint8_t *u8out[8] = {};
     unsigned long long *counters = nullptr;
     FusedTables *tables = nullptr;      // uploaded once per pb200_classify_host call
+    Arena arena;                        // strip descriptors, tensor maps, item list
     cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_k;
 };
@@ -414,6 +426,9 @@ struct pb200_plan {
     int n_items = 0;
     bool fast_optional = false;                      // some fast tile wants WTR-1 / WTR-2 / CLOUD / SHAD
     bool stream_ordered = false;                     // allocated with cudaMallocAsync
+    bool from_arena = false;                         // allocated from a caller-owned arena: nothing to free
+    // per input tile: where it went (for launching one tile of the plan on its own)
+    std::vector<int> tile_group, tile_slot, tile_ctas, item_start, item_end;
 };
 
 extern "C" int pb200_ctx_create(int device, pb200_ctx **out) {
@@ -440,6 +455,15 @@ extern "C" int pb200_ctx_create(int device, pb200_ctx **out) {
         return fail(PB200_E_NO_DRIVER_API, "cuTensorMapEncodeTiled not available from the driver");
     }
     c->encode = (EncodeTiledFn)fn;
+    {
+        // pb200_classify allocates its descriptors stream-ordered: keep the pool's memory between calls
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     *out = c;
     return 0;
 }
@@ -459,6 +483,7 @@ extern "C" int pb200_ctx_destroy(pb200_ctx *ctx) {
     pipe_free(p);
     cudaFree(p.counters);
     cudaFree(p.tables);
+    cudaFree(p.arena.base);
     if (p.s_in) cudaStreamDestroy(p.s_in);
     if (p.s_k) cudaStreamDestroy(p.s_k);
     if (p.s_out) cudaStreamDestroy(p.s_out);
@@ -543,7 +568,7 @@ static int make_tile_dev(pb200_ctx *ctx, const pb200_tile &t, int index, TileDev
 
 static int plan_build(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles, const pb200_params *params,
                       pb200_plan *pl, cudaStream_t stream, bool stream_ordered,
-                      FusedTables *shared_tables = nullptr) {
+                      FusedTables *shared_tables = nullptr, Arena *arena = nullptr) {
     if (!ctx || !tiles || n_tiles <= 0 || !params)
         return fail(PB200_E_INVALID_ARG, "classify: null argument or n_tiles <= 0");
     if (n_tiles > 65535) return fail(PB200_E_INVALID_ARG, "classify: at most 65535 tiles per launch");
@@ -569,6 +594,10 @@ static int plan_build(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles, cons
         // the first DEM box of a row of items must not start left of the DEM array
         if (d.dem) fast = fast && d.dem_off_x >= DEM_PADX + (d.dem_off_x & 3);
         const int g = fast ? G_FAST : ((d.flags & TF_VEC) ? G_VEC : G_GENERIC);
+        pl->tile_group.push_back(g);
+        pl->tile_slot.push_back((int)td[g].size());
+        pl->tile_ctas.push_back(d.n_ctas);
+        pl->item_start.push_back((int)items.size());
         if (fast) {
             // the fast kernel stages the DEM with its own box shape
             if (d.dem) {
@@ -587,12 +616,18 @@ static int plan_build(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles, cons
                 for (int tx = 0; tx < ntx; ++tx) items.push_back(ItemDesc{slot, (uint16_t)tx, (uint16_t)ty});
             if (d.wtr1 || d.wtr1r || d.wtr2 || d.cloud || d.shad) pl->fast_optional = true;
         }
+        pl->item_end.push_back((int)items.size());
         td[g].push_back(d);
         tm[g].push_back(m);
         pl->max_ctas[g] = std::max(pl->max_ctas[g], d.n_ctas);
     }
     CK(cudaSetDevice(ctx->device));
+    pl->from_arena = arena != nullptr;
     auto dev_alloc = [&](void **ptr, size_t bytes) -> cudaError_t {
+        if (arena) {
+            *ptr = arena->take(bytes);
+            return *ptr ? cudaSuccess : cudaErrorMemoryAllocation;
+        }
         return stream_ordered ? cudaMallocAsync(ptr, bytes, stream) : cudaMalloc(ptr, bytes);
     };
     for (int g = 0; g < N_GROUPS; ++g) {
@@ -659,9 +694,35 @@ static int plan_launch(pb200_plan *pl, cudaStream_t stream) {
     return 0;
 }
 
+// launch only input tile `i` of the plan (host pipeline: one strip at a time)
+static int plan_launch_tile(pb200_plan *pl, int i, cudaStream_t stream) {
+    const int g = pl->tile_group[i], slot = pl->tile_slot[i];
+    if (g == G_FAST) {
+        int rc = fast_kernel_setup(pl->ctx);
+        if (rc) return rc;
+        const int n = pl->item_end[i] - pl->item_start[i];
+        const int grid = std::min(n, pl->ctx->sm_count * pl->ctx->fast_ctas_per_sm);
+        const ItemDesc *it = pl->d_items + pl->item_start[i];
+        if (pl->fast_optional)
+            dswx_fused_fast_kernel<true><<<grid, FT_THREADS, sizeof(FastSmem), stream>>>(
+                pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, it, n, pl->P, pl->F);
+        else
+            dswx_fused_fast_kernel<false><<<grid, FT_THREADS, sizeof(FastSmem), stream>>>(
+                pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, it, n, pl->P, pl->F);
+    } else if (g == G_VEC) {
+        dswx_fused_kernel<true><<<dim3(pl->tile_ctas[i], 1), NTHREADS, 0, stream>>>(pl->d_tiles[g] + slot,
+                                                                                    pl->d_maps[g] + slot, pl->P);
+    } else {
+        dswx_fused_kernel<false><<<dim3(pl->tile_ctas[i], 1), NTHREADS, 0, stream>>>(pl->d_tiles[g] + slot,
+                                                                                     pl->d_maps[g] + slot, pl->P);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
 static void plan_release(pb200_plan *pl, cudaStream_t stream) {
     auto dev_free = [&](void *ptr) {
-        if (!ptr) return;
+        if (!ptr || pl->from_arena) return;
         if (pl->stream_ordered) cudaFreeAsync(ptr, stream); else cudaFree(ptr);
     };
     for (int g = 0; g < N_GROUPS; ++g) {
@@ -765,7 +826,7 @@ extern "C" int pb200_classify_host(pb200_ctx *ctx, const pb200_tile *ht, const p
     CK(cudaSetDevice(ctx->device));
     const int H = ht->height, W = ht->width;
     if (H <= 0 || W <= 0) return fail(PB200_E_INVALID_ARG, "pb200_classify_host: empty raster");
-    if (strip_rows <= 0) strip_rows = 8 * TH;
+    if (strip_rows <= 0) strip_rows = 32 * TH;      // 1024 rows: 4 strips per HLS tile (measured best, scripts/e2e_probe.py)
     strip_rows = ((strip_rows + TH - 1) / TH) * TH;
     const size_t px = (size_t)H * W;
     const size_t dem_elems = ht->dem ? (size_t)ht->dem_rows * ht->dem_pitch : 0;
@@ -802,7 +863,44 @@ extern "C" int pb200_classify_host(pb200_ctx *ctx, const pb200_tile *ht, const p
         CK(cudaMemcpyAsync(p.tables, &T, sizeof(T), cudaMemcpyHostToDevice, p.s_k));
     }
 
-    std::vector<pb200_plan> plans(n_strips);
+    // descriptors of ALL strips in one plan, uploaded before the pipeline starts: inside the
+    // loop the host only enqueues asynchronous work and never waits for the GPU
+    std::vector<pb200_tile> strips(n_strips);
+    for (int sidx = 0; sidx < n_strips; ++sidx) {
+        const int r0 = sidx * strip_rows, r1 = std::min(H, r0 + strip_rows);
+        const size_t off = (size_t)r0 * W;
+        pb200_tile &st = strips[sidx];
+        st = dt;
+        st.height = r1 - r0;
+        for (int k = 0; k < 6; ++k) st.band[k] = dt.band[k] + off;
+        st.fmask = dt.fmask + off;
+        if (st.land) st.land = dt.land + off;
+        if (st.ocean) st.ocean = dt.ocean + off;
+        st.dem_off_y = dt.dem_off_y + r0;
+        if (st.diag) st.diag = dt.diag + off;
+        uint8_t **sf[8] = {&st.wtr1, &st.wtr1_remapped, &st.wtr2, &st.cloud, &st.shad, &st.wtr, &st.bwtr, &st.conf};
+        for (int i = 0; i < 8; ++i)
+            if (*sf[i]) *sf[i] += off;
+    }
+    // worst case per strip: descriptor + tensor map + one item per 128 x 32 pixels
+    {
+        const size_t items_max = (size_t)((W + FT_W - 1) / FT_W) * (size_t)((H + FT_H - 1) / FT_H + n_strips);
+        const size_t need = (size_t)n_strips * (sizeof(TileDev) + sizeof(CUtensorMap) + 1024) +
+                            items_max * sizeof(ItemDesc) + 8192;
+        if (need > p.arena.cap) {
+            CK(cudaStreamSynchronize(p.s_k));
+            cudaFree(p.arena.base);
+            p.arena.base = nullptr;
+            p.arena.cap = 0;
+            CK(cudaMalloc((void **)&p.arena.base, need * 2));
+            p.arena.cap = need * 2;
+        }
+        p.arena.used = 0;
+    }
+    pb200_plan plan;
+    rc = plan_build(ctx, strips.data(), n_strips, params, &plan, p.s_k, true, p.tables, &p.arena);
+    if (rc) { plan_release(&plan, p.s_k); return rc; }
+
     int dem_copied = 0;                 // DEM rows [.., dem_copied) are on the device
     bool first_dem = true;
     for (int sidx = 0; sidx < n_strips; ++sidx) {
@@ -827,22 +925,9 @@ extern "C" int pb200_classify_host(pb200_ctx *ctx, const pb200_tile *ht, const p
         }
         CK(cudaEventRecord(p.ev_in[sidx], p.s_in));
         // ---- kernel on the strip -------------------------------------------
-        pb200_tile st = dt;
-        st.height = nr;
-        for (int k = 0; k < 6; ++k) st.band[k] = dt.band[k] + off;
-        st.fmask = dt.fmask + off;
-        if (st.land) st.land = dt.land + off;
-        if (st.ocean) st.ocean = dt.ocean + off;
-        st.dem_off_y = dt.dem_off_y + r0;
-        if (st.diag) st.diag = dt.diag + off;
-        uint8_t **sf[8] = {&st.wtr1, &st.wtr1_remapped, &st.wtr2, &st.cloud, &st.shad, &st.wtr, &st.bwtr, &st.conf};
-        for (int i = 0; i < 8; ++i)
-            if (*sf[i]) *sf[i] += off;
         CK(cudaStreamWaitEvent(p.s_k, p.ev_in[sidx], 0));
-        rc = plan_build(ctx, &st, 1, params, &plans[sidx], p.s_k, true, p.tables);
-        if (rc == 0) rc = plan_launch(&plans[sidx], p.s_k);
-        plan_release(&plans[sidx], p.s_k);
-        if (rc) { cudaDeviceSynchronize(); return rc; }
+        rc = plan_launch_tile(&plan, sidx, p.s_k);
+        if (rc) { cudaDeviceSynchronize(); plan_release(&plan, p.s_k); return rc; }
         CK(cudaEventRecord(p.ev_k[sidx], p.s_k));
         // ---- D2H --------------------------------------------------------------
         CK(cudaStreamWaitEvent(p.s_out, p.ev_k[sidx], 0));
@@ -851,6 +936,7 @@ extern "C" int pb200_classify_host(pb200_ctx *ctx, const pb200_tile *ht, const p
             if (host_u8[i])
                 CK(cudaMemcpyAsync(host_u8[i] + off, p.u8out[i] + off, cnt, cudaMemcpyDeviceToHost, p.s_out));
     }
+    plan_release(&plan, p.s_k);
     if (ht->counters)
         CK(cudaMemcpyAsync(ht->counters, p.counters, PB200_N_COUNTERS * sizeof(unsigned long long),
                            cudaMemcpyDeviceToHost, p.s_out));
