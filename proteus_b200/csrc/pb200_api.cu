@@ -115,6 +115,45 @@ extern "C" int pb200_ratio_bound(double t, int is_less, int32_t *a_out, int32_t 
     return 0;
 }
 
+// Strict companion of pb200_ratio_bound for the fast kernel:
+//   is_less = 0:  RN(n/d) > t  <=>  p/q > a/b   with a/b = LARGEST fraction <= midpoint M
+//   is_less = 1:  RN(n/d) < t  <=>  p/q < a/b   with a/b = SMALLEST fraction >= midpoint M-
+// (p/q is never equal to a midpoint, so "<= M" / ">= M" only matter when M is itself such a
+// fraction, which cannot happen; the test then needs no "- 1" term.)  b == 0: always / never as in
+// pb200_ratio_bound, with a = -1 (">" always), +1 (">" never), +1 ("<" always), -1 ("<" never).
+static int ratio_bound_strict(double t, int is_less, int32_t *a_out, int32_t *b_out) {
+    const int never_a = is_less ? -1 : 1, always_a = is_less ? 1 : -1;
+    if (std::isnan(t)) { *a_out = never_a; *b_out = 0; return 0; }
+    if (t >= 1048576.0) { *a_out = is_less ? always_a : never_a; *b_out = 0; return 0; }
+    if (t <= -1048576.0) { *a_out = is_less ? never_a : always_a; *b_out = 0; return 0; }
+    const double nb = is_less ? std::nextafter(t, -INFINITY) : std::nextafter(t, INFINITY);
+    long long m1, m2;
+    int e1, e2;
+    decompose(t, &m1, &e1);
+    decompose(nb, &m2, &e2);
+    if (m1 == 0) e1 = e2;
+    if (m2 == 0) e2 = e1;
+    long long best_a = 0, best_b = 0;
+    for (long long q = 1; q <= 32768; ++q) {
+        long long a;
+        if (!is_less) {
+            a = floor_mid_times(m1, e1, m2, e2, q);                // largest integer a with a/q <= M
+            if (a < -32768) continue;
+            if (a > 32768) a = 32768;
+            if (best_b == 0 || a * best_b > best_a * q) { best_a = a; best_b = q; }
+        } else {
+            a = -floor_mid_times(-m1, e1, -m2, e2, q);             // smallest integer a with a/q >= M-
+            if (a > 32768) continue;
+            if (a < -32768) a = -32768;
+            if (best_b == 0 || a * best_b < best_a * q) { best_a = a; best_b = q; }
+        }
+    }
+    if (best_b == 0) { *a_out = always_a; *b_out = 0; return 0; }   // no fraction on that side: every p/q passes
+    *a_out = (int32_t)best_a;
+    *b_out = (int32_t)best_b;
+    return 0;
+}
+
 // ---------------------------------------------------------------------------
 // angle thresholds in the cosine / tangent domain (libm flavour)
 // ---------------------------------------------------------------------------
@@ -352,6 +391,17 @@ static void build_fast_params(const pb200_params *p, const DevParams &D, FastPar
     // |4*awesh| < 2^20: clamp so that init - 4*awesh cannot overflow
     F->awesh_init = clampi(D.awesh4_thr, -(1 << 24), 1 << 24);
     for (int i = 0; i < 4; ++i) { F->ra[i] = D.r_a[i]; F->rb[i] = D.r_b[i]; }
+    {
+        const double thr[4] = {p->th.wigt, p->th.pswt_1_mndwi, p->th.pswt_2_mndwi, p->th.pswt_1_ndvi};
+        for (int i = 0; i < 4; ++i) {
+            const int less = (i == RB_P1_NDVI);
+            int32_t a, b;
+            ratio_bound_strict(thr[i], less, &a, &b);
+            // ">": sign(a*q - p*b);  "<": sign(p*b - a*q).  With b == 0 the value is +-a*q (q >= 1).
+            F->sa[i] = less ? -a : a;
+            F->nsb[i] = less ? b : -b;
+        }
+    }
     if (p->fmask_fill >= 0 && p->fmask_fill <= 255) {
         F->fmask_xor4 = (uint32_t)p->fmask_fill * 0x01010101u; F->fmask_or = 0u;
     } else {
@@ -657,14 +707,23 @@ static int plan_build(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles, cons
     return 0;
 }
 
+// one 128-px half per item: FastSmem is a static __shared__ object (absolute addresses); otherwise dynamic
+#ifdef PB200_FAST_DYNAMIC_SMEM
+constexpr size_t FAST_DYN_SMEM = sizeof(FastSmem);
+#else
+constexpr size_t FAST_DYN_SMEM = (FT_HALVES == 1) ? 0 : sizeof(FastSmem);
+#endif
+
 static int fast_kernel_setup(pb200_ctx *ctx) {
     if (ctx->fast_ready) return 0;
-    CK(cudaFuncSetAttribute(dswx_fused_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)sizeof(FastSmem)));
-    CK(cudaFuncSetAttribute(dswx_fused_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)sizeof(FastSmem)));
+    if (FAST_DYN_SMEM) {
+        CK(cudaFuncSetAttribute(dswx_fused_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)FAST_DYN_SMEM));
+        CK(cudaFuncSetAttribute(dswx_fused_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)FAST_DYN_SMEM));
+    }
     int nb = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dswx_fused_fast_kernel<false>, FT_THREADS, sizeof(FastSmem)));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dswx_fused_fast_kernel<false>, FT_THREADS, FAST_DYN_SMEM));
     ctx->fast_ctas_per_sm = nb > 0 ? nb : 1;
     ctx->fast_ready = true;
     return 0;
@@ -676,10 +735,10 @@ static int plan_launch(pb200_plan *pl, cudaStream_t stream) {
         if (rc) return rc;
         const int grid = std::min(pl->n_items, pl->ctx->sm_count * pl->ctx->fast_ctas_per_sm);
         if (pl->fast_optional)
-            dswx_fused_fast_kernel<true><<<grid, FT_THREADS, sizeof(FastSmem), stream>>>(
+            dswx_fused_fast_kernel<true><<<grid, FT_THREADS, FAST_DYN_SMEM, stream>>>(
                 pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, pl->d_items, pl->n_items, pl->P, pl->F);
         else
-            dswx_fused_fast_kernel<false><<<grid, FT_THREADS, sizeof(FastSmem), stream>>>(
+            dswx_fused_fast_kernel<false><<<grid, FT_THREADS, FAST_DYN_SMEM, stream>>>(
                 pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, pl->d_items, pl->n_items, pl->P, pl->F);
     }
     if (pl->n[G_VEC]) {
@@ -704,10 +763,10 @@ static int plan_launch_tile(pb200_plan *pl, int i, cudaStream_t stream) {
         const int grid = std::min(n, pl->ctx->sm_count * pl->ctx->fast_ctas_per_sm);
         const ItemDesc *it = pl->d_items + pl->item_start[i];
         if (pl->fast_optional)
-            dswx_fused_fast_kernel<true><<<grid, FT_THREADS, sizeof(FastSmem), stream>>>(
+            dswx_fused_fast_kernel<true><<<grid, FT_THREADS, FAST_DYN_SMEM, stream>>>(
                 pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, it, n, pl->P, pl->F);
         else
-            dswx_fused_fast_kernel<false><<<grid, FT_THREADS, sizeof(FastSmem), stream>>>(
+            dswx_fused_fast_kernel<false><<<grid, FT_THREADS, FAST_DYN_SMEM, stream>>>(
                 pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, it, n, pl->P, pl->F);
     } else if (g == G_VEC) {
         dswx_fused_kernel<true><<<dim3(pl->tile_ctas[i], 1), NTHREADS, 0, stream>>>(pl->d_tiles[g] + slot,

@@ -74,7 +74,11 @@ struct FastParams {
     uint32_t m_p2blue, m_p2swir1, m_p2swir2, m_p2nir;
     uint32_t m_nle, m_lc;               // packed -(1000 + 1), -(lcmask + 1)
     int32_t  awesh_init;                // floor(4*awgt): sign(init - 4*awesh) <=> awesh > awgt
-    int32_t  ra[4], rb[4];
+    int32_t  ra[4], rb[4];              // ">=" forms (generic kernel, slow path)
+    // strict forms for the fast path (no "- 1": one IMAD less per test):
+    //   RN(n/d) > t  <=>  p/q >  sa/sb  <=>  sa*q - p*sb < 0   (sa/sb = largest fraction <= midpoint)
+    //   RN(n/d) < t  <=>  p/q <  sa/sb  <=>  p*sb - sa*q < 0   (sa/sb = smallest fraction >= midpoint)
+    int32_t  sa[4], nsb[4];             // nsb = -sb for the ">" tests, +sb for the "<" test; sa negated for "<"
     float    kx, ky;                    // 0.5 / dxf, 0.5 / dyf
     float    tan32, e0, cc32;           // float32(tan_thr), 1e-6*|tan_thr| + 1e-30, c*|c| with c = cos_thr
     uint32_t fast_shadow_ok;            // thresholds are finite and |cos_thr| <= 1
@@ -158,8 +162,12 @@ __global__ void __launch_bounds__(FT_THREADS, FT_MIN_CTAS)
 dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__restrict__ tmaps,
                        const FusedTables *__restrict__ tables, const ItemDesc *__restrict__ items, int n_items,
                        const __grid_constant__ DevParams P, const __grid_constant__ FastParams F) {
+#if PB200_FT_HALVES == 1 && !defined(PB200_FAST_DYNAMIC_SMEM)
+    __shared__ FastSmem s;                                // 32 KB: static, absolute shared addresses
+#else
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FastSmem &s = *reinterpret_cast<FastSmem *>(smem_raw);
+#endif
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int half = warp % FT_HALVES;                    // which 128-pixel half of the item
     const int rgrp = warp / FT_HALVES;                    // which group of 4 rows
@@ -287,18 +295,24 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                             const int q1 = hi ? (int)(gs >> 16) : (int)(gs & 0xffffu);
                             const int n2 = hi ? sext_hi(nrd) : sext_lo(nrd);
                             const int q2 = hi ? (int)(nrs >> 16) : (int)(nrs & 0xffffu);
-                            // sign set <=> test true:  a*q - p*b - 1 < 0 <=> p*b >= a*q
-                            const int x0w = F.ra[RB_WIGT] * q1 - n1 * F.rb[RB_WIGT] - 1;
-                            const int x1w = F.ra[RB_P1_MNDWI] * q1 - n1 * F.rb[RB_P1_MNDWI] - 1;
-                            const int x2w = F.ra[RB_P2_MNDWI] * q1 - n1 * F.rb[RB_P2_MNDWI] - 1;
-                            const int x3w = n2 * F.rb[RB_P1_NDVI] - F.ra[RB_P1_NDVI] * q2 - 1;   // p*b <= a*q
+                            // sign set <=> test true:  sa*q + p*(-sb) < 0 <=> p/q > sa/sb  (two IMADs)
+                            const int x0w = n1 * F.nsb[RB_WIGT] + F.sa[RB_WIGT] * q1;
+                            const int x1w = n1 * F.nsb[RB_P1_MNDWI] + F.sa[RB_P1_MNDWI] * q1;
+                            const int x2w = n1 * F.nsb[RB_P2_MNDWI] + F.sa[RB_P2_MNDWI] * q1;
+                            const int x3w = n2 * F.nsb[RB_P1_NDVI] + F.sa[RB_P1_NDVI] * q2;       // p/q < sa/sb
                             // 4*awesh: init - 4B - 10G + 6*mbsrn + S2 < 0 <=> awesh > awgt
-                            const int cb = hi ? 8 : 0;
                             int aw = F.awesh_init;
-                            aw = __dp2a_lo((int)B, (int)(0xFCu << cb), aw);
-                            aw = __dp2a_lo((int)G, (int)(0xF6u << cb), aw);
-                            aw = __dp2a_lo((int)ns, (int)(0x06u << cb), aw);
-                            aw = __dp2a_lo((int)S2, (int)(0x01u << cb), aw);
+                            if (hi) {
+                                aw = __dp2a_hi((int)B, (int)0xFC0000FCu, aw);
+                                aw = __dp2a_hi((int)G, (int)0xF60000F6u, aw);
+                                aw = __dp2a_hi((int)ns, (int)0x06000006u, aw);
+                                aw = __dp2a_hi((int)S2, (int)0x01000001u, aw);
+                            } else {
+                                aw = __dp2a_lo((int)B, (int)0xFC0000FCu, aw);
+                                aw = __dp2a_lo((int)G, (int)0xF60000F6u, aw);
+                                aw = __dp2a_lo((int)ns, (int)0x06000006u, aw);
+                                aw = __dp2a_lo((int)S2, (int)0x01000001u, aw);
+                            }
                             const uint32_t sh16 = hi ? 0u : 16u;
                             const uint32_t t2w = (hi ? p2h : p2l) ? 0u : 0x80000000u;
                             const uint32_t t4w = (uint32_t)x1w & (uint32_t)x3w & (T4 << sh16);
