@@ -343,7 +343,8 @@ static void build_fused_tables(const pb200_params *p, const DevParams &D, FusedT
         const bool remap = aerosol_on && nle && k1 <= 4u && ((aero >> k1) & 1u);        // D:1237-1239
         const uint32_t kb = remap ? 1u : k1;
         const uint32_t c = cprelim | (remap ? 8u : 0u) | (snow << 1);                    // D:1246, D:2081
-        T->fk_lut[idx] = (uint8_t)(kb | (c << 3));
+        const uint32_t water = (kb >= 1u && kb <= 4u) ? 0x80u : 0u;                       // can be masked by terrain shadow
+        T->fk_lut[idx] = (uint8_t)(kb | (c << 3) | water);
     }
     for (uint32_t idx = 0; idx < 128; ++idx)
         T->kill_lut[idx] = (uint8_t)kill_class(idx & 7u, (idx >> 3) & 1u, (idx >> 4) & 1u, (idx >> 5) & 3u);

@@ -58,7 +58,7 @@ enum : uint32_t { FL_VALID = 1u << 24, FL_CLOUD_VALID = 1u << 25, FL_SHADOW_SENS
 struct FusedTables {               // built on the host per plan, global memory
     uint32_t big_lut[2048];        // [kb | c<<3 | cat<<7 | shadowed<<9 | bright<<10] -> WTR | BWTR<<8 | CONF<<16 | flags<<24
     uint32_t diag_lut[128];        // [code | valid<<5 | not_ocean<<6] -> DIAG value | (k1<<8)<<16
-    uint8_t  fk_lut[4096];         // [fmask | k1<<8 | (nir<=1000)<<11] -> kb | c<<3
+    uint8_t  fk_lut[4096];         // [fmask | k1<<8 | (nir<=1000)<<11] -> kb | c<<3 | (kb is a water class)<<7
     uint8_t  land_lut[256];        // land value -> cat
     uint8_t  kill_lut[128];        // [kb | shadowed<<3 | bright<<4 | cat<<5] -> k2 (optional layers only)
 };
@@ -132,10 +132,11 @@ __device__ __forceinline__ uint32_t shadow_fast(float l, float r, float u, float
     const float eg = 4e-6f * v;
     // shadow      <=> back slope AND NOT low incidence:  diff < -e  and  D < -eg
     // not shadow  <=> not a back slope, or low incidence with x <= 1:  diff > e  or  (D > eg and L < 0.99999 v)
-    const bool is_shadow = fmaxf(diff + e, D + eg) < 0.0f;
-    const bool not_shadow = fmaxf(diff - e, fminf(D - eg, fmaf(0.99999f, v, -L))) > 0.0f;
-    // NaN / inf anywhere makes |diff| + v non-finite -> undecided
-    *undecided = *undecided || !(is_shadow || not_shadow) || !(fabsf(diff) + v < 3e38f);
+    // NaN / inf make every comparison false -> neither -> undecided (unless the slope test alone decides,
+    // which is exact: "not a back slope" never looks at the incidence angle)
+    const bool is_shadow = (diff < -e) && (D < -eg);
+    const bool not_shadow = (diff > e) || ((D > eg) && (L < 0.99999f * v));
+    *undecided = *undecided || !(is_shadow || not_shadow);
     return is_shadow ? 0x200u : 0u;
 }
 
@@ -246,7 +247,7 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                 if (has_land) ld4 = ldg_stream_u32(s.tile.land + pix);
                 if (has_ocean) oc4 = ldg_stream_u32(s.tile.ocean + pix);
 
-                uint32_t idx[4], o[4], dgw[2], k1p[2];
+                uint32_t idx[4], dgw[2], k1p[2], water_any = 0u;
 #pragma unroll
                 for (int p = 0; p < 2; ++p) {
                     // ================= packed stage: pixels 2p, 2p+1 =================
@@ -343,16 +344,17 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                         const uint32_t ev = s.fk_lut[fi];                     // D:1237-1246, 1984-1991, 2081
                         const uint32_t cat = s.land_lut[(ld4 >> (8 * j)) & 255u];
                         const uint32_t bri = hi ? (brp >> 16) : (brp & 0xffffu);
-                        idx[j] = ev | bri | (cat << 7);
-                        o[j] = s.big_lut[idx[j]];                             // D:1349-1376 (no shadow yet), 2084-2131, 1727, 1793-1835
+                        idx[j] = ((ev & 0x7Fu) | bri) + (cat << 7);
+                        water_any |= ev;                                      // bit 7: the pixel holds a water class
                     }
                     dgw[p] = __byte_perm(dl[0], dl[1], 0x5410);               // two DIAG values
                     if (OPTIONAL_LAYERS) k1p[p] = __byte_perm(dl[0], dl[1], 0x4743);   // k1 of the two pixels in bytes 0 and 2
                 }
 
                 // ---- terrain shadow: only where it can change the result ----------------
+                // (bit 7 of a fk_lut byte = the pixel holds a water class: only those can be masked, D:1340-1343)
                 uint32_t shw[4] = {0u, 0u, 0u, 0u};                           // 0x200 = in shadow
-                if (has_dem && (want_shad || ((o[0] | o[1] | o[2] | o[3]) & FL_SHADOW_SENSITIVE))) {
+                if (has_dem && (want_shad || (water_any & 0x80u))) {
                     if (!dem_ready) {
                         mbar_wait(&s.mbar, dem_phase);
                         dem_ready = true;
@@ -390,10 +392,11 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
 #pragma unroll
                         for (int j = 0; j < 4; ++j) shw[j] = shadow_exact(m[j], m[j + 2], u[j], d[j], P, s.tile);
                     }
-                    // look the pixels up again with the shadow bit (D:1331-1344)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) o[j] = s.big_lut[idx[j] | shw[j]];
                 }
+                // ---- final look-up (D:1331-1376, 2084-2131, 1727, 1793-1835) ------------------
+                uint32_t o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] = s.big_lut[idx[j] | shw[j]];
 
                 // ---- pack and store -------------------------------------------------------
                 const uint32_t t01a = __byte_perm(o[0], o[1], 0x5140);
