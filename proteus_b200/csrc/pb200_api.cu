@@ -665,7 +665,7 @@ static int plan_build(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles, cons
             const uint32_t slot = (uint32_t)td[G_FAST].size();
             for (int ty = 0; ty < nty; ++ty)
                 for (int tx = 0; tx < ntx; ++tx) items.push_back(ItemDesc{slot, (uint16_t)tx, (uint16_t)ty});
-            if (d.wtr1 || d.wtr1r || d.wtr2 || d.cloud || d.shad) pl->fast_optional = true;
+            if (d.wtr1 || d.wtr1r || d.wtr2 || d.cloud || d.shad || params->class_histogram) pl->fast_optional = true;
         }
         pl->item_end.push_back((int)items.size());
         td[g].push_back(d);

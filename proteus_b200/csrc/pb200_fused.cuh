@@ -37,12 +37,19 @@ namespace pb200 {
 #ifndef PB200_FT_HALVES
 #define PB200_FT_HALVES 1          // 128-pixel halves per item: 1 -> 256-thread CTAs (4 per SM), 2 -> 512-thread CTAs
 #endif
+#ifndef PB200_FT_ROWGROUPS
+#define PB200_FT_ROWGROUPS 8       // warps (row groups of 4 rows) per 128-pixel half
+#endif
+#ifndef PB200_FT_MIN_CTAS
+#define PB200_FT_MIN_CTAS (1024 / (32 * PB200_FT_ROWGROUPS * PB200_FT_HALVES))
+#endif
 constexpr int FT_HALVES = PB200_FT_HALVES;
-constexpr int FT_W = 128 * FT_HALVES;   // item width: one warp (32 lanes x 4 px) per 128-pixel half
-constexpr int FT_H = 32;                // item height: 8 row groups x 4 rows
-constexpr int FT_THREADS = 256 * FT_HALVES;
+constexpr int FT_ROWGROUPS = PB200_FT_ROWGROUPS;
 constexpr int FT_ROWS_PER_WARP = 4;
-constexpr int FT_MIN_CTAS = 1024 / FT_THREADS;   // 64 registers per thread
+constexpr int FT_W = 128 * FT_HALVES;   // item width: one warp (32 lanes x 4 px) per 128-pixel half
+constexpr int FT_H = FT_ROWS_PER_WARP * FT_ROWGROUPS;     // item height
+constexpr int FT_THREADS = 32 * FT_ROWGROUPS * FT_HALVES;
+constexpr int FT_MIN_CTAS = PB200_FT_MIN_CTAS;
 // DEM staging: one TMA box per 128-pixel half (a box is at most 256 elements
 // wide).  Box start = dem_off_x + x0 + 128*half - padx with padx = 4 +
 // (dem_off_x & 3): a multiple of 4 floats (UTMALDG needs a 16-byte aligned box
@@ -96,6 +103,7 @@ struct __align__(128) FastSmem {
     uint8_t  land_lut[256];
     uint8_t  kill_lut[128];
     TileDev  tile;                      // descriptor of the current tile
+    float    sun32[8];                  // float32(sin_az, cos_az, sx, sy, sz) of the current tile
     unsigned long long mbar;
     unsigned int cnt[N_CNT];
 };
@@ -186,7 +194,7 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
     }
     uint32_t cur_tile = 0xffffffffu;
     uint32_t dem_phase = 0;
-    const bool histogram = (P.flags & PF_HISTOGRAM) != 0u;
+    const bool histogram = OPTIONAL_LAYERS && (P.flags & PF_HISTOGRAM) != 0u;   // lean variant: 3 counters only
 
 #pragma unroll 1
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
@@ -196,6 +204,11 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
             const uint32_t *src = reinterpret_cast<const uint32_t *>(&tiles[item.tile]);
             uint32_t *dst = reinterpret_cast<uint32_t *>(&s.tile);
             if (tid < (int)(sizeof(TileDev) / 4)) dst[tid] = __ldg(src + tid);
+            if (tid == 64) {
+                const TileDev &g = tiles[item.tile];
+                s.sun32[0] = (float)g.sin_az; s.sun32[1] = (float)g.cos_az;
+                s.sun32[2] = (float)g.sx; s.sun32[3] = (float)g.sy; s.sun32[4] = (float)g.sz;
+            }
             cur_tile = item.tile;
             __syncthreads();
         }
@@ -216,8 +229,6 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
             for (int hf = 0; hf < FT_HALVES; ++hf)
                 tma_load_2d(&s.dem[hf].v[0][0], &tmaps[item.tile], gx + 128 * hf, gy, &s.mbar);
         }
-        const float sa = (float)s.tile.sin_az, ca = (float)s.tile.cos_az;
-        const float sx = (float)s.tile.sx, sy = (float)s.tile.sy, sz = (float)s.tile.sz;
         const bool want_shad = OPTIONAL_LAYERS && s.tile.shad != nullptr;
         // the four graded layers present: one test instead of four in the row loop
         const bool all_graded = s.tile.diag && s.tile.wtr && s.tile.bwtr && s.tile.conf;
@@ -384,6 +395,7 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                         for (int j = 0; j < 4; ++j) { u[j] = ru[j]; d[j] = rd[j]; }
                     }
                     bool undecided = (F.fast_shadow_ok == 0u);
+                    const float sa = s.sun32[0], ca = s.sun32[1], sx = s.sun32[2], sy = s.sun32[3], sz = s.sun32[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         shw[j] = shadow_fast(m[j], m[j + 2], u[j], d[j], F, sa, ca, sx, sy, sz, &undecided);
