@@ -194,6 +194,31 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
     }
     uint32_t cur_tile = 0xffffffffu;
     uint32_t dem_phase = 0;
+    // counters accumulate in registers across the items of a tile and are flushed once per warp
+    // when the CTA moves to another tile (and at the end): valid | cloud-and-valid << 16, not-ocean
+    uint32_t acc_vc = 0, acc_nno = 0;
+    unsigned long long acc_hist = 0ull;
+    unsigned long long *cur_counters = nullptr;
+    auto flush_counters = [&]() {
+        if (cur_counters != nullptr) {
+            const uint32_t wv = __reduce_add_sync(0xffffffffu, acc_vc & 0xffffu);
+            const uint32_t wc = __reduce_add_sync(0xffffffffu, acc_vc >> 16);
+            const uint32_t wn = __reduce_add_sync(0xffffffffu, acc_nno);
+            if (lane == 0) {
+                if (wv) atomicAdd(&cur_counters[0], (unsigned long long)wv);
+                if (wc) atomicAdd(&cur_counters[1], (unsigned long long)wc);
+                if (wn) atomicAdd(&cur_counters[2], (unsigned long long)wn);
+            }
+            if (OPTIONAL_LAYERS && (P.flags & PF_HISTOGRAM)) {
+#pragma unroll
+                for (int bin = 0; bin < 9; ++bin) {
+                    const uint32_t hv = __reduce_add_sync(0xffffffffu, (uint32_t)(acc_hist >> (7 * bin)) & 127u);
+                    if (lane == 0 && hv) atomicAdd(&cur_counters[3 + bin], (unsigned long long)hv);
+                }
+            }
+        }
+        acc_vc = 0; acc_nno = 0; acc_hist = 0ull;
+    };
     const bool histogram = OPTIONAL_LAYERS && (P.flags & PF_HISTOGRAM) != 0u;   // lean variant: 3 counters only
 
 #pragma unroll 1
@@ -201,6 +226,7 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
         const ItemDesc item = items[it];
         __syncthreads();                                  // previous item fully consumed (DEM tile, tile descriptor)
         if (item.tile != cur_tile) {
+            flush_counters();                             // of the tile this CTA is leaving
             const uint32_t *src = reinterpret_cast<const uint32_t *>(&tiles[item.tile]);
             uint32_t *dst = reinterpret_cast<uint32_t *>(&s.tile);
             if (tid < (int)(sizeof(TileDev) / 4)) dst[tid] = __ldg(src + tid);
@@ -211,6 +237,7 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
             }
             cur_tile = item.tile;
             __syncthreads();
+            cur_counters = s.tile.counters;
         }
         const int W = s.tile.width, H = s.tile.height;
         const int x0 = item.tx * FT_W, y0 = item.ty * FT_H;
@@ -233,8 +260,6 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
         // the four graded layers present: one test instead of four in the row loop
         const bool all_graded = s.tile.diag && s.tile.wtr && s.tile.bwtr && s.tile.conf;
 
-        uint32_t acc_valid = 0, acc_cv = 0, acc_nno = 0;
-        unsigned long long acc_hist = 0ull;
         bool dem_ready = !has_dem;
 
         const int x = x0 + 128 * half + 4 * lane;         // this lane's 4 pixels
@@ -458,12 +483,12 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
 
                 // ---- counters (D:5104-5111) from the flag bytes -----------------------------
                 if (has_counters) {
-                    acc_valid += __popc(flag4 & 0x01010101u);
-                    acc_cv += __popc(flag4 & 0x02020202u);
+                    // valid in the low half, cloud-and-valid in the high half (a thread sees < 2^16 pixels per tile)
+                    acc_vc += __popc(flag4 & 0x01010101u) + (__popc(flag4 & 0x02020202u) << 16);
                     acc_nno = __dp4a(oc4, 0x01010101u, acc_nno);               // D:5105; no shoreline: 1 per pixel (D:5107)
                     if (histogram) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) acc_hist += 1ull << (6u * ((flag4 >> (8 * j + 4)) & 15u));
+                        for (int j = 0; j < 4; ++j) acc_hist += 1ull << (7u * ((flag4 >> (8 * j + 4)) & 15u));
                     }
                 }
             }
@@ -473,31 +498,10 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
         if (has_dem && !dem_ready) mbar_wait(&s.mbar, dem_phase);
         if (has_dem) dem_phase ^= 1u;
 
-        // ---- counters: warp-aggregated, one atomic per CTA, item and slot -------------
-        if (has_counters) {
-            const uint32_t wv = __reduce_add_sync(0xffffffffu, acc_valid);
-            const uint32_t wc = __reduce_add_sync(0xffffffffu, acc_cv);
-            const uint32_t wn = __reduce_add_sync(0xffffffffu, acc_nno);
-            if (lane == 0) {
-                if (wv) atomicAdd(&s.cnt[0], wv);
-                if (wc) atomicAdd(&s.cnt[1], wc);
-                if (wn) atomicAdd(&s.cnt[2], wn);
-            }
-            if (histogram) {
-#pragma unroll
-                for (int bin = 0; bin < 9; ++bin) {
-                    const uint32_t hv = __reduce_add_sync(0xffffffffu, (uint32_t)(acc_hist >> (6 * bin)) & 63u);
-                    if (lane == 0 && hv) atomicAdd(&s.cnt[3 + bin], hv);
-                }
-            }
-            __syncthreads();
-            if (tid < N_CNT) {
-                const unsigned int v = s.cnt[tid];
-                s.cnt[tid] = 0u;                          // next item starts from zero (ordered by the loop-top barrier)
-                if (v) atomicAdd(&s.tile.counters[tid], (unsigned long long)v);
-            }
-        }
+        // histogram bins are 7 bits wide and an item adds at most 16 pixels per thread: flush every 4 items
+        if (histogram && ((it / (int)gridDim.x) & 3) == 3) flush_counters();
     }
+    flush_counters();
 }
 
 }  // namespace pb200
