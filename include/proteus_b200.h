@@ -90,6 +90,10 @@ typedef struct pb200_params {
     double  pixel_spacing_x, pixel_spacing_y;    /* D:4217: always 30, 30 */
     int32_t collapse_wtr_classes;  /* write WTR / WTR-1 / WTR-2 collapsed (D:2688-2689) */
     int32_t class_histogram;       /* also fill counters[3..11] */
+    /* 1: leave the Fmask snow bit out of CLOUD (and of WTR / CONF): first phase of the 'cover' mode,
+     * where the snow mask is dilated (pb200_snow_to_cloud_cover) before it is added (D:2055-2081). */
+    int32_t defer_snow;
+    int32_t reserved_;
 } pb200_params;
 
 /* One raster tile (an MGRS tile, one acquisition of a time series, or one row
@@ -190,6 +194,17 @@ int  pb200_landcover_shadow_masks(pb200_ctx *ctx, const uint8_t *wtr1,
 int  pb200_snow_to_cloud(pb200_ctx *ctx, const uint8_t *wtr2, uint8_t *cloud,
                          const uint8_t *fmask, int mode, int64_t n,
                          void *stream);
+/* D:2055-2084 _add_snow_to_cloud_layer, mode 'cover': masked dilation of the snow mask (10 x) and of
+ * the not-masked area (7 x), scipy.ndimage.binary_dilation semantics; cloud IN PLACE.
+ * scratch: 4 * rows * cols bytes of device memory. */
+int  pb200_snow_to_cloud_cover(pb200_ctx *ctx, const uint8_t *wtr2, uint8_t *cloud,
+                               const uint8_t *fmask, int rows, int cols,
+                               uint8_t *scratch, void *stream);
+/* scipy.ndimage.binary_dilation(in, iterations, mask) on 0/1 byte rasters, default structure
+ * (4-connected), border 0.  scratch: rows * cols bytes.  out may not alias in. */
+int  pb200_masked_dilation(pb200_ctx *ctx, const uint8_t *in, const uint8_t *mask, int rows,
+                           int cols, int iterations, uint8_t *out, uint8_t *scratch,
+                           void *stream);
 /* D:2089-2133 _apply_cloud_masking */
 int  pb200_cloud_masking(pb200_ctx *ctx, const uint8_t *wtr2,
                          const uint8_t *cloud, int64_t n, uint8_t *wtr,

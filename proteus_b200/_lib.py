@@ -25,7 +25,7 @@ EXPORTS = (
     'pb200_diagnostic_tests', 'pb200_interpreted_layer',
     'pb200_binary_representation', 'pb200_preliminary_cloud',
     'pb200_aerosol_remap', 'pb200_landcover_shadow_masks',
-    'pb200_snow_to_cloud', 'pb200_cloud_masking', 'pb200_binary_water',
+    'pb200_snow_to_cloud', 'pb200_snow_to_cloud_cover', 'pb200_masked_dilation', 'pb200_cloud_masking', 'pb200_binary_water',
     'pb200_confidence', 'pb200_collapse', 'pb200_shadow', 'pb200_ratio_bound',
     'pb200_ratio_sweep', 'pb200_angle_thresholds',
 )
@@ -56,6 +56,8 @@ class Params(C.Structure):
         ('pixel_spacing_y', C.c_double),
         ('collapse_wtr_classes', C.c_int32),
         ('class_histogram', C.c_int32),
+        ('defer_snow', C.c_int32),
+        ('reserved_', C.c_int32),
     ]
 
 
@@ -130,6 +132,8 @@ def load():
     lib.pb200_aerosol_remap.argtypes = [vp, vp, vp, vp, vp, C.c_uint8 * 256, i64, vp]
     lib.pb200_landcover_shadow_masks.argtypes = [vp, vp, vp, vp, vp, C.c_double, i64, vp, vp]
     lib.pb200_snow_to_cloud.argtypes = [vp, vp, vp, vp, C.c_int, i64, vp]
+    lib.pb200_snow_to_cloud_cover.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, vp, vp]
+    lib.pb200_masked_dilation.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     lib.pb200_cloud_masking.argtypes = [vp, vp, vp, i64, vp, vp]
     lib.pb200_binary_water.argtypes = [vp, vp, i64, vp, vp]
     lib.pb200_confidence.argtypes = [vp, vp, vp, i64, vp, vp]

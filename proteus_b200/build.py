@@ -1,6 +1,9 @@
 """Build libproteus_b200.so in-tree with nvcc for sm_100a.
 
-    python -m proteus_b200.build [--force] [--verbose]
+    python proteus_b200/build.py [--force] [--verbose]
+
+(run it as a script: `python -m proteus_b200.build` imports the package first, and the package
+refuses to import when the library is missing or older than the header)
 
 The shared library is the only compiled artefact of the package.  It is built
 next to this file so that it travels with the source tree (it is git-ignored,
@@ -19,6 +22,7 @@ LIB = os.path.join(HERE, 'libproteus_b200.so')
 SOURCES = [os.path.join(CSRC, 'pb200_api.cu')]
 HEADERS = [os.path.join(CSRC, 'pb200_kernels.cuh'),
            os.path.join(CSRC, 'pb200_fused.cuh'),
+           os.path.join(CSRC, 'pb200_cover.cuh'),
            os.path.join(CSRC, 'pb200_device.cuh'),
            os.path.join(HERE, '..', 'include', 'proteus_b200.h')]
 

@@ -21,6 +21,7 @@
 #include "../../include/proteus_b200.h"
 #include "pb200_kernels.cuh"
 #include "pb200_fused.cuh"
+#include "pb200_cover.cuh"
 
 using namespace pb200;
 
@@ -283,7 +284,7 @@ static int derive_params(const pb200_params *p, DevParams *D, bool fused) {
     const int mode = p->adjacent_mode == PB200_ADJ_MASK ? 0 : 1;
     for (uint32_t v = 0; v < 256; ++v) {
         uint32_t e = preliminary_cloud(v, mode);
-        if (v & 16u) e |= 8u;
+        if ((v & 16u) && !p->defer_snow) e |= 8u;
         e |= (uint32_t)(p->aerosol_class_bits[v] & 0x1Du) << 4;
         if ((int)v == p->fmask_fill) e |= 0x8000u;
         D->fmask_lut[v] = (uint16_t)e;
@@ -1137,6 +1138,55 @@ extern "C" int pb200_snow_to_cloud(pb200_ctx *ctx, const uint8_t *wtr2, uint8_t 
     REQUIRE(wtr2 && cloud && fmask && n >= 0, "pb200_snow_to_cloud: bad argument");
     if (n == 0) return 0;
     snow_to_cloud_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(wtr2, cloud, fmask, n);
+    LEAVE();
+}
+
+// iterations of the masked dilation, ping-pong between `a` (holds the input) and `b`; returns the
+// buffer that holds the result
+static uint8_t *run_masked_dilation(uint8_t *a, uint8_t *b, const uint8_t *mask, int rows, int cols, int iterations,
+                                    cudaStream_t st) {
+    dim3 block(64, 4), grid((cols + 63) / 64, (rows + 3) / 4);
+    for (int it = 0; it < iterations; ++it) {
+        masked_dilation_step_kernel<<<grid, block, 0, st>>>(a, mask, b, rows, cols);
+        std::swap(a, b);
+    }
+    return a;
+}
+
+extern "C" int pb200_masked_dilation(pb200_ctx *ctx, const uint8_t *in, const uint8_t *mask, int rows, int cols,
+                                     int iterations, uint8_t *out, uint8_t *scratch, void *stream) {
+    ENTER(ctx);
+    REQUIRE(rows >= 0 && cols >= 0 && iterations >= 1, "pb200_masked_dilation: bad size / iterations");
+    if ((long long)rows * cols == 0) return 0;
+    REQUIRE(in && mask && out && scratch && in != out, "pb200_masked_dilation: bad argument");
+    const size_t n = (size_t)rows * cols;
+    // arrange the ping-pong so that the last iteration writes `out`
+    uint8_t *first = (iterations % 2) ? out : scratch;
+    dim3 block(64, 4), grid((cols + 63) / 64, (rows + 3) / 4);
+    masked_dilation_step_kernel<<<grid, block, 0, st>>>(in, mask, first, rows, cols);
+    if (iterations > 1) {
+        uint8_t *other = (first == out) ? scratch : out;
+        uint8_t *res = run_masked_dilation(first, other, mask, rows, cols, iterations - 1, st);
+        if (res != out) CK(cudaMemcpyAsync(out, res, n, cudaMemcpyDeviceToDevice, st));
+    }
+    LEAVE();
+}
+
+extern "C" int pb200_snow_to_cloud_cover(pb200_ctx *ctx, const uint8_t *wtr2, uint8_t *cloud, const uint8_t *fmask,
+                                         int rows, int cols, uint8_t *scratch, void *stream) {
+    ENTER(ctx);
+    REQUIRE(rows >= 0 && cols >= 0, "pb200_snow_to_cloud_cover: bad size");
+    const long long n = (long long)rows * cols;
+    if (n == 0) return 0;
+    REQUIRE(wtr2 && cloud && fmask && scratch, "pb200_snow_to_cloud_cover: bad argument");
+    uint8_t *A = scratch, *B = scratch + n, *M = scratch + 2 * n, *S = scratch + 3 * n;
+    const int g = grid_for(ctx, n, 256);
+    cover_init_kernel<<<g, 256, 0, st>>>(fmask, cloud, A, M, n);                      // snow, area
+    uint8_t *snow = run_masked_dilation(A, B, M, rows, cols, 10, st);                  // D:2060
+    CK(cudaMemcpyAsync(S, snow, (size_t)n, cudaMemcpyDeviceToDevice, st));
+    cover_mid_kernel<<<g, 256, 0, st>>>(S, cloud, wtr2, M, A, n);                      // area2, not_masked
+    uint8_t *nm = run_masked_dilation(A, B, M, rows, cols, 7, st);                     // D:2075
+    cover_final_kernel<<<g, 256, 0, st>>>(S, nm, wtr2, cloud, n);
     LEAVE();
 }
 

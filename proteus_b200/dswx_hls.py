@@ -11,8 +11,6 @@ unchanged; the one-pass fused path is ``proteus_b200.classify_tile``.
 Scope notes (explicit errors, no silent fallback):
   * reflectance bands must be int16 (the default, D:4640): float32 bands from
     ``--offset-and-scale-inputs`` raise NotImplementedError;
-  * ``mask_adjacent_to_cloud_mode='cover'`` (D:2055-2078, masked dilation)
-    raises NotImplementedError in ``_add_snow_to_cloud_layer``;
   * the DEM must be float32 (what the cubic warp of D:5145 produces).
 """
 from __future__ import annotations
@@ -229,17 +227,21 @@ def _apply_landcover_and_shadow_masks(interpreted_layer, nir, landcover_mask,
 # ---------------------------------------------------------------------------
 def _add_snow_to_cloud_layer(wtr_2_layer, cloud_layer, fmask,
                              mask_adjacent_to_cloud_mode):
-    if mask_adjacent_to_cloud_mode == 'cover':
-        raise NotImplementedError(
-            "mask_adjacent_to_cloud_mode='cover' (masked binary dilation, D:2055-2078) "
-            'is not implemented on the GPU path yet')
-    # the reference does not validate the mode here: anything else behaves like 'mask'/'ignore'
+    # the reference does not validate the mode here: anything but 'cover' behaves like 'mask'/'ignore'
     ctx = get_context()
     w = _to_device(wtr_2_layer, np.uint8, 'wtr_2_layer')
     c = _to_device(cloud_layer, np.uint8, 'cloud_layer')
     f = _to_device(fmask, np.uint8, 'fmask')
-    _lib.check(ctx._lib.pb200_snow_to_cloud(
-        ctx.handle, w.data_ptr(), c.data_ptr(), f.data_ptr(), 0, int(w.numel()), _stream()))
+    if mask_adjacent_to_cloud_mode == 'cover':
+        if w.dim() != 2:
+            raise ValueError("mode 'cover' dilates a 2-D raster")
+        scratch = _torch().empty(4 * max(int(w.numel()), 1), dtype=_torch().uint8, device='cuda')
+        _lib.check(ctx._lib.pb200_snow_to_cloud_cover(
+            ctx.handle, w.data_ptr(), c.data_ptr(), f.data_ptr(), int(w.shape[0]), int(w.shape[1]),
+            scratch.data_ptr(), _stream()))
+    else:
+        _lib.check(ctx._lib.pb200_snow_to_cloud(
+            ctx.handle, w.data_ptr(), c.data_ptr(), f.data_ptr(), 0, int(w.numel()), _stream()))
     cloud_layer[...] = _to_host(c, np.uint8)
     return cloud_layer
 

@@ -321,6 +321,62 @@ class Plan:
             pass
 
 
+def classify_device_cover(tile, hls_thresholds=None, outputs=ALL_LAYERS, *, collapse_wtr_classes=True,
+                          class_histogram=False, ctx=None, **processing):
+    """``mask_adjacent_to_cloud_mode='cover'`` for one device-resident tile.
+
+    The masked dilations of dswx_hls.py:2055-2078 need the whole WTR-2 / CLOUD rasters, so this mode
+    runs in three steps on the device: (1) the fused kernel with the snow bit deferred (CLOUD =
+    preliminary layer + aerosol bit, WTR-2 uncollapsed), (2) ``pb200_snow_to_cloud_cover`` (10 + 7
+    masked dilation steps), (3) the point-wise tail (cloud masking, BWTR, CONF, collapsing).
+    Returns a dict of torch tensors (+ 'counters')."""
+    import torch
+    ctx = ctx or get_context()
+    lib = ctx._lib
+    processing = dict(processing)
+    processing.pop('mask_adjacent_to_cloud_mode', None)
+    params = make_params(hls_thresholds, mask_adjacent_to_cloud_mode='ignore', defer_snow=True,
+                         collapse_wtr_classes=False, **processing)
+    has_dem = tile.get('dem') is not None
+    phase1 = ['DIAG', 'WTR1', 'WTR1_REMAPPED', 'WTR2', 'CLOUD'] + (['SHAD'] if has_dem else [])
+    plan = Plan([tile], params, phase1, ctx=ctx)
+    plan.run()
+    o = plan.outputs[0]
+    fmask = tile['fmask']
+    h, w = int(fmask.shape[0]), int(fmask.shape[1])
+    n = h * w
+    stream = C.c_void_p(torch.cuda.current_stream(ctx.device).cuda_stream)
+    scratch = torch.empty(4 * max(n, 1), dtype=torch.uint8, device=fmask.device)
+    _lib.check(lib.pb200_snow_to_cloud_cover(ctx.handle, o['WTR2'].data_ptr(), o['CLOUD'].data_ptr(),
+                                             fmask.data_ptr(), h, w, scratch.data_ptr(), stream))
+    res = dict(DIAG=o['DIAG'], CLOUD=o['CLOUD'])
+    if has_dem:
+        res['SHAD'] = o['SHAD']
+    wtr = torch.empty_like(o['WTR2'])
+    bwtr = torch.empty_like(o['WTR2'])
+    conf = torch.empty_like(o['WTR2'])
+    _lib.check(lib.pb200_cloud_masking(ctx.handle, o['WTR2'].data_ptr(), o['CLOUD'].data_ptr(), n,
+                                       wtr.data_ptr(), stream))
+    _lib.check(lib.pb200_binary_water(ctx.handle, wtr.data_ptr(), n, bwtr.data_ptr(), stream))
+    _lib.check(lib.pb200_confidence(ctx.handle, o['WTR2'].data_ptr(), o['CLOUD'].data_ptr(), n,
+                                    conf.data_ptr(), stream))
+    res.update(BWTR=bwtr, CONF=conf)
+    counters = plan.counters[0].clone()
+    if class_histogram:
+        hist = torch.bincount(wtr.reshape(-1).to(torch.int64), minlength=256)
+        for k, cls in enumerate(HISTOGRAM_CLASSES):
+            counters[3 + k] = hist[cls]
+    for name, t in (('WTR', wtr), ('WTR1', o['WTR1']), ('WTR1_REMAPPED', o['WTR1_REMAPPED']), ('WTR2', o['WTR2'])):
+        if collapse_wtr_classes:
+            c = torch.empty_like(t)
+            _lib.check(lib.pb200_collapse(ctx.handle, t.data_ptr(), n, c.data_ptr(), stream))
+            t = c
+        res[name] = t
+    res = {k: v for k, v in res.items() if k in outputs}
+    res['counters'] = counters
+    return res
+
+
 def classify_device(tiles, params=None, outputs=GRADED_LAYERS, *, stream=None, ctx=None):
     """One-shot: build a plan, run it once, return the plan (outputs on device)."""
     plan = Plan(tiles, params, outputs, ctx=ctx)
@@ -352,6 +408,11 @@ def classify_tile(bands, fmask, dem_with_margin=None, landcover_mask=None,
     Returns a dict: requested layers (numpy, pinned), 'counters' (uint64[12])
     and 'coverage' (the three percentages of D:5115-5124)."""
     ctx = ctx or get_context()
+    if params is None and processing.get('mask_adjacent_to_cloud_mode') == 'cover':
+        return _classify_tile_cover(bands, fmask, dem_with_margin, landcover_mask, ocean_mask,
+                                    sun_azimuth_angle, sun_elevation_angle, hls_thresholds,
+                                    outputs=outputs, dem_margin=dem_margin, dem_off=dem_off, ctx=ctx,
+                                    **processing)
     if params is None:
         params = make_params(hls_thresholds, **processing)
     elif processing or hls_thresholds is not None:
@@ -413,3 +474,36 @@ def classify_tile(bands, fmask, dem_with_margin=None, landcover_mask=None,
     res['counters'] = counters
     res['coverage'] = counters_to_dict(counters, h * w, ocean_mask is not None)
     return res
+
+
+def _classify_tile_cover(bands, fmask, dem_with_margin, landcover_mask, ocean_mask, sun_azimuth_angle,
+                         sun_elevation_angle, hls_thresholds, *, outputs, dem_margin, dem_off, ctx,
+                         **processing):
+    """Host-array front end of ``classify_device_cover`` (whole rasters go to the device: the dilations
+    of the 'cover' mode are not strip-local)."""
+    import torch
+    dev = torch.device('cuda', ctx.device)
+
+    def up(a, dtype):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a)
+        if a.dtype != dtype:
+            raise TypeError(f'expected {np.dtype(dtype).name}, got {a.dtype}')
+        return torch.from_numpy(a).to(dev)
+    tile = dict(bands=[up(b, np.int16) for b in bands], fmask=up(fmask, np.uint8),
+                dem=up(dem_with_margin, np.float32), land=up(landcover_mask, np.uint8),
+                ocean=up(ocean_mask, np.uint8), sun_azimuth=sun_azimuth_angle,
+                sun_elevation=sun_elevation_angle, dem_margin=dem_margin, dem_off=dem_off)
+    collapse = processing.pop('collapse_wtr_classes', True)
+    hist = processing.pop('class_histogram', False)
+    res = classify_device_cover(tile, hls_thresholds, outputs, collapse_wtr_classes=collapse,
+                                class_histogram=hist, ctx=ctx, **processing)
+    torch.cuda.synchronize(dev)
+    out = {}
+    for k, v in res.items():
+        a = v.cpu().numpy()
+        out[k] = a.view(np.uint16) if k == 'DIAG' else (a.astype(np.uint64) if k == 'counters' else a)
+    h, w = fmask.shape
+    out['coverage'] = counters_to_dict(out['counters'], h * w, ocean_mask is not None)
+    return out

@@ -158,7 +158,7 @@ def make_params(hls_thresholds=None, *, mask_adjacent_to_cloud_mode='mask',
                 apply_aerosol_class_remapping=True, aerosol_fmask_values=None,
                 min_slope_angle=-5, max_sun_local_inc_angle=40,
                 band_fill=-9999, fmask_fill=255, collapse_wtr_classes=True,
-                class_histogram=False, pixel_spacing=(30, 30)):
+                class_histogram=False, pixel_spacing=(30, 30), defer_snow=False):
     """Build a ``pb200_params`` structure."""
     th = hls_thresholds or HlsThresholds()
     p = _lib.Params()
@@ -190,6 +190,7 @@ def make_params(hls_thresholds=None, *, mask_adjacent_to_cloud_mode='mask',
     p.pixel_spacing_x, p.pixel_spacing_y = float(pixel_spacing[0]), float(pixel_spacing[1])
     p.collapse_wtr_classes = int(bool(collapse_wtr_classes))
     p.class_histogram = int(bool(class_histogram))
+    p.defer_snow = int(bool(defer_snow))
     return p
 
 

@@ -211,8 +211,14 @@ def test_function_level_dropins_match_oracle(pb):
         c_in = cloud.copy()
         c_got = G._add_snow_to_cloud_layer(wtr1, c_in, fmask, mode)
         assert c_got is c_in and np.array_equal(c_got, c_ref)
-    with pytest.raises(NotImplementedError):
-        G._add_snow_to_cloud_layer(wtr1, cloud.copy(), fmask, 'cover')
+    # 'cover': masked dilations (scipy semantics) - clouds restricted to the values the chain produces
+    cloud_c = np.array([0, 1, 4, 5, 8, 9, 12, 13], dtype=np.uint8)[rng.integers(0, 8, shape)]
+    cloud_c[rng.random(shape) < 0.6] = 0
+    fm_c = (fmask & 0x14) | (rng.random(shape) < 0.5).astype(np.uint8) * 4
+    c_ref = O.add_snow_to_cloud_layer(wtr1, cloud_c.copy(), fm_c, 'cover')
+    c_in = cloud_c.copy()
+    c_got = G._add_snow_to_cloud_layer(wtr1, c_in, fm_c, 'cover')
+    assert c_got is c_in and np.array_equal(c_got, c_ref)
     assert np.array_equal(G._apply_cloud_masking(wtr1, cloud), O.apply_cloud_masking(wtr1, cloud))
     assert np.array_equal(G._get_binary_water_layer(wtr1), O.get_binary_water_layer(wtr1))
     assert np.array_equal(G._get_confidence_layer(wtr1, cloud), O.get_confidence_layer(wtr1, cloud))
@@ -250,9 +256,6 @@ def test_error_paths(pb):
     t = synth.make_tile(3, 32, 32)
     with pytest.raises(Exception, match='ERROR mask adjacent to cloud/cloud-shadow mode'):
         pb.classify_tile(t['bands'], t['fmask'], mask_adjacent_to_cloud_mode='nope')
-    from proteus_b200._lib import Pb200Error
-    with pytest.raises(Pb200Error, match='cover'):
-        pb.classify_tile(t['bands'], t['fmask'], mask_adjacent_to_cloud_mode='cover')
     with pytest.raises(NotImplementedError):
         pb.classify_tile([b.astype(np.float32) for b in t['bands']], t['fmask'])
     with pytest.raises(ValueError):
@@ -335,3 +338,47 @@ def test_mosaic_row_strips_match_whole_raster(pb):
     for k in got:
         assert np.array_equal(got[k], ref[k]), k
     assert np.array_equal(counters, ref['counters'])
+
+
+def test_cover_mode_matches_reference_fixture(pb):
+    """mask_adjacent_to_cloud_mode='cover' (dswx_hls.py:2055-2078): the three-step device flow
+    against the live-reference fixture, uncollapsed and collapsed."""
+    ins, ref = load_golden('cover_mode')
+    assert ins['mode'] == 'cover'
+    got = _classify_host(pb, ins, collapse=False, class_histogram=True)
+    _assert_layers(got, ref, FUSED_LAYERS, 'cover_mode')
+    assert np.array_equal(got['counters'][:3], ref['counters'])
+    hist = np.bincount(ref['WTR'].ravel(), minlength=256)
+    assert [got['coverage']['class_histogram'][c] for c in (0, 1, 2, 3, 4, 252, 253, 254, 255)] == \
+        [int(hist[c]) for c in (0, 1, 2, 3, 4, 252, 253, 254, 255)]
+    got_c = _classify_host(pb, ins, collapse=True)
+    for name, key in (('WTR', 'WTR_COLLAPSED'), ('WTR1', 'WTR1_COLLAPSED'), ('WTR2', 'WTR2_COLLAPSED')):
+        assert np.array_equal(got_c[name], ref[key]), key
+    for name in ('BWTR', 'CONF', 'DIAG', 'CLOUD'):
+        assert np.array_equal(got_c[name], ref[name]), name
+    # a second, adversarial tile against the oracle
+    t = synth.make_tile(41, 150, 212, adversarial=True)
+    o = O.reference_chain(t['bands'], t['fmask'], t['dem'], t['land'], t['ocean'], t['sun_azimuth'],
+                          t['sun_elevation'], processing=dict(mask_adjacent_to_cloud_mode='cover'))
+    g = pb.classify_tile(t['bands'], t['fmask'], t['dem'], t['land'], t['ocean'], t['sun_azimuth'],
+                         t['sun_elevation'], mask_adjacent_to_cloud_mode='cover', collapse_wtr_classes=False)
+    _assert_layers(g, o, FUSED_LAYERS, 'cover adversarial')
+
+
+def test_masked_dilation_matches_scipy(pb):
+    import ctypes as C
+    import torch
+    from scipy.ndimage import binary_dilation
+    from proteus_b200 import _lib
+    ctx = pb.get_context()
+    rng = np.random.default_rng(3)
+    for shape, iters in (((37, 53), 1), ((64, 200), 10), ((1, 40), 7), ((50, 1), 3), ((129, 131), 4)):
+        a = rng.random(shape) < 0.05
+        m = rng.random(shape) < 0.7
+        ref = binary_dilation(a, iterations=iters, mask=m)
+        da, dm = torch.from_numpy(a.view(np.uint8)).cuda(), torch.from_numpy(m.view(np.uint8)).cuda()
+        out, scr = torch.empty_like(da), torch.empty_like(da)
+        _lib.check(ctx._lib.pb200_masked_dilation(
+            ctx.handle, da.data_ptr(), dm.data_ptr(), shape[0], shape[1], iters, out.data_ptr(),
+            scr.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        assert np.array_equal(out.cpu().numpy().astype(bool), ref), (shape, iters)
