@@ -171,6 +171,11 @@ int  pb200_invalid_and_clip(pb200_ctx *ctx, const int16_t *const raw[6],
 int  pb200_diagnostic_tests(pb200_ctx *ctx, const int16_t *const band[6],
                             const pb200_thresholds *th, int64_t n,
                             uint16_t *diag_decimal, void *stream);
+/* D:1840-1916 on FLOAT32 bands (the --offset-and-scale-inputs mode, D:2300-2302): every operation in
+ * float32 in numpy's order, no FMA contraction, thresholds cast to float32 */
+int  pb200_diagnostic_tests_f32(pb200_ctx *ctx, const float *const band[6],
+                                const pb200_thresholds *th, int64_t n,
+                                uint16_t *diag_decimal, void *stream);
 /* D:1687-1707 generate_interpreted_layer */
 int  pb200_interpreted_layer(pb200_ctx *ctx, const uint16_t *diag_decimal,
                              int64_t n, uint8_t *wtr1, void *stream);
@@ -226,6 +231,15 @@ int  pb200_shadow(pb200_ctx *ctx, const float *dem, int rows, int cols,
                   double sun_azimuth, double sun_elevation,
                   const double *sun_terms /* 5 doubles as in pb200_tile, or NULL */,
                   const pb200_params *params, uint8_t *out, void *stream);
+
+/* SURVEY 8f next #1 - the numpy tail of create_landcover_mask (D:1003-1115): 3x3 block counts of the
+ * 10 m ESA WorldCover raster [3*rows, 3*cols] (water {80,90,95}, urban 50, tree 10), tree count kept
+ * on CGLS forest classes only (forest_class_table[v] != 0), threshold hierarchy thresholds[4] =
+ * {evergreen, low-intensity, high-intensity, water} (D:270-271) -> LAND [rows, cols] */
+int  pb200_landcover_aggregate(pb200_ctx *ctx, const uint8_t *worldcover_up3,
+                               const uint8_t *copernicus, int rows, int cols,
+                               const uint8_t forest_class_table[256], int year_offset,
+                               const int32_t thresholds[4], uint8_t *land, void *stream);
 
 /* ---- helpers exported for tests ---------------------------------------- */
 /* The exact integer form of "float64(n)/float64(d) > t" (is_less = 0) or

@@ -370,6 +370,46 @@ def crop_2d_array_all_sides(a, margin):
 
 
 # --------------------------------------------------------------------------
+# numpy tail of create_landcover_mask  (D:874-904, D:1003-1115)
+# --------------------------------------------------------------------------
+LANDCOVER_THRESHOLDS = {'standard': (6, 3, 7, 3), 'water heavy': (6, 3, 7, 1)}     # D:270-271
+
+
+def decimate_by_summation(image, size_y, size_x):
+    """Block sum over size_y x size_x windows (D:874-904); the dtype of the
+    input is kept (uint8 sums of 0/1 masks stay <= 9)."""
+    h, w = image.shape
+    assert h % size_y == 0 and w % size_x == 0, 'the reference is only used on exact multiples'
+    blocks = image.reshape(h // size_y, size_y, w // size_x, size_x)
+    return blocks.sum(axis=(1, 3), dtype=image.dtype)
+
+
+def landcover_aggregate(worldcover_up_3, copernicus_landcover, forest_mask_landcover_classes,
+                        year_offset, mask_type='standard'):
+    """LAND layer from the ESA WorldCover raster warped to 10 m (3x the product
+    grid) and the CGLS land-cover raster on the product grid, i.e. the
+    statements of create_landcover_mask after its two GDAL warps:
+    water {80, 90, 95}, urban 50 and tree 10 counts per 3x3 block (D:1003-1031),
+    tree counts kept only on CGLS forest classes (D:1033-1043), then the
+    hierarchy 255 -> evergreen 201 -> low intensity -> high intensity -> water
+    200, later rules overriding earlier ones (D:1045-1115)."""
+    th = LANDCOVER_THRESHOLDS[mask_type.lower()]
+    water = decimate_by_summation(np.isin(worldcover_up_3, [80, 90, 95]).astype(np.uint8), 3, 3)
+    urban = decimate_by_summation((worldcover_up_3 == 50).astype(np.uint8), 3, 3)
+    tree = decimate_by_summation((worldcover_up_3 == 10).astype(np.uint8), 3, 3)
+    forest = np.zeros(tree.shape, dtype=bool)
+    for cls in (forest_mask_landcover_classes or ()):
+        forest |= (copernicus_landcover == cls)
+    tree = np.where(forest, tree, 0)
+    land = np.full(water.shape, UINT8_FILL_VALUE, dtype=np.uint8)
+    land[tree >= th[0]] = LAND_EVERGREEN                                   # D:1062
+    land[urban >= th[1]] = 0 + year_offset                                 # D:1096-1100
+    land[urban >= th[2]] = 100 + year_offset                               # D:1102-1107
+    land[water >= th[3]] = LAND_WATER                                      # D:1109-1113
+    return land
+
+
+# --------------------------------------------------------------------------
 # the chain, in the order of generate_dswx_layers  (D:5088-5369)
 # --------------------------------------------------------------------------
 def reference_chain(raw_bands, fmask, dem_with_margin=None, landcover=None,

@@ -158,5 +158,51 @@ def main():
               f'counters {out["counters"].tolist()}')
 
 
+def make_landcover_inputs(seed, h, w):
+    rng = np.random.default_rng(seed)
+    vals = np.array([10, 20, 30, 40, 50, 60, 70, 80, 90, 95, 100, 0], np.uint8)
+    blob = np.kron(rng.integers(0, len(vals), (-(-h // 5), -(-w // 5))), np.ones((15, 15), int))[:3 * h, :3 * w]
+    noise = vals[rng.integers(0, len(vals), (3 * h, 3 * w))]
+    wc = np.where(rng.random((3 * h, 3 * w)) < 0.6, vals[blob], noise).astype(np.uint8)
+    cop = np.array([20, 50, 111, 113, 115, 116, 121, 123, 125, 126, 30, 40, 200, 0],
+                   np.uint8)[rng.integers(0, 14, (h, w))]
+    return wc, cop
+
+
+def extra_fixtures():
+    """LAND aggregation (live create_landcover_mask with its GDAL calls replaced) and the
+    float32 'scaled' diagnostic tests (live _compute_diagnostic_tests on float32 bands)."""
+    ref = ref_import.load()
+    groups = ref_import.default_runconfig_groups()
+    forest = groups['processing']['forest_mask_landcover_classes']
+    arrays = {'forest_classes': np.array(forest)}
+    for i, (seed, h, w, year, mt) in enumerate(((5, 120, 152, 2021, 'standard'), (6, 67, 93, 2020, 'water heavy'))):
+        wc, cop = make_landcover_inputs(seed, h, w)
+        arrays[f'wc{i}'], arrays[f'cop{i}'] = wc, cop
+        arrays[f'year{i}'], arrays[f'type{i}'] = np.array(year), np.array(mt)
+        arrays[f'land{i}'] = ref_import.live_create_landcover_mask(wc, cop, forest, year, mt)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, 'landcover.npz'), **arrays)
+    print('landcover:', {k: np.unique(v).tolist() for k, v in arrays.items() if k.startswith('land')})
+
+    thresholds = ref.HlsThresholds()
+    for k, v in groups['hls_thresholds'].items():
+        setattr(thresholds, k, v)
+    t = synth.make_tile(9, 96, 160)
+    # D:2298-2302: clip, then scale_factor * (float32(image) - offset) with the HLS scale 1e-4
+    scaled = [0.0001 * (np.asarray(np.clip(b, 1, None), dtype=np.float32) - 0.0) for b in t['bands']]
+    scaled = [np.asarray(b, dtype=np.float32) for b in scaled]
+    # thresholds sit in unscaled units (D:44): also exercise float bands in DN units
+    dn = [np.asarray(np.clip(b, 1, None), dtype=np.float32) for b in t['bands']]
+    out = {f'scaled{k}': b for k, b in enumerate(scaled)}
+    out.update({f'dn{k}': b for k, b in enumerate(dn)})
+    with np.errstate(all='ignore'):
+        out['diag_scaled'] = ref._compute_diagnostic_tests(*scaled, thresholds)
+        out['diag_dn'] = ref._compute_diagnostic_tests(*dn, thresholds)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, 'float_diag.npz'), **out)
+    print('float_diag: codes', np.unique(out['diag_scaled']).tolist(), np.unique(out['diag_dn']).size)
+
+
 if __name__ == '__main__':
-    main()
+    if '--extra-only' not in sys.argv:
+        main()
+    extra_fixtures()

@@ -69,3 +69,40 @@ def default_runconfig_groups():
                         'dswx_hls.yaml')
     with open(path) as f:
         return yaml.safe_load(f)['runconfig']['groups']
+
+
+def live_create_landcover_mask(worldcover_up_3, copernicus, forest_classes, year, mask_type='standard'):
+    """Run the UNMODIFIED ``create_landcover_mask`` (dswx_hls.py:911-1130) on in-memory rasters: its two
+    ``_warp`` calls (GDAL) return the given arrays and the WorldCover metadata read returns ``year``;
+    every numpy statement of the function (D:1003-1115) executes as written."""
+    import tempfile
+    ref = load()
+    calls = []
+
+    def fake_warp(*args, **kwargs):
+        calls.append(1)
+        return copernicus if len(calls) == 1 else worldcover_up_3
+
+    class _Dataset:
+        def GetMetadata(self):
+            return {'time_start': f'{year}-01-01T00:00:00Z', 'time_end': f'{year}-12-31T23:59:59Z'}
+
+    class _ColorTable:
+        def SetColorEntry(self, *a):
+            pass
+
+    saved = ref._warp
+    ref._warp = fake_warp
+    ref.gdal.Open = lambda *a, **k: _Dataset()
+    ref.gdal.ColorTable = _ColorTable
+    ref.gdal.GA_ReadOnly = 0
+    try:
+        with tempfile.TemporaryDirectory() as d:
+            f1, f2 = os.path.join(d, 'cgls.tif'), os.path.join(d, 'worldcover.tif')
+            open(f1, 'w').close()
+            open(f2, 'w').close()
+            h, w = copernicus.shape
+            return ref.create_landcover_mask(f1, f2, 'description', None, d, mask_type, (0, 30, 0, 0, 0, -30),
+                                             'projection', h, w, forest_classes, temp_files_list=[])
+    finally:
+        ref._warp = saved

@@ -22,11 +22,11 @@ EXPORTS = (
     'pb200_params_default', 'pb200_classify', 'pb200_plan_create',
     'pb200_plan_run', 'pb200_plan_destroy', 'pb200_classify_host',
     'pb200_host_alloc', 'pb200_host_free', 'pb200_invalid_and_clip',
-    'pb200_diagnostic_tests', 'pb200_interpreted_layer',
+    'pb200_diagnostic_tests', 'pb200_diagnostic_tests_f32', 'pb200_interpreted_layer',
     'pb200_binary_representation', 'pb200_preliminary_cloud',
     'pb200_aerosol_remap', 'pb200_landcover_shadow_masks',
     'pb200_snow_to_cloud', 'pb200_snow_to_cloud_cover', 'pb200_masked_dilation', 'pb200_cloud_masking', 'pb200_binary_water',
-    'pb200_confidence', 'pb200_collapse', 'pb200_shadow', 'pb200_ratio_bound',
+    'pb200_confidence', 'pb200_collapse', 'pb200_shadow', 'pb200_landcover_aggregate', 'pb200_ratio_bound',
     'pb200_ratio_sweep', 'pb200_angle_thresholds',
 )
 
@@ -126,6 +126,7 @@ def load():
     vp, i64 = C.c_void_p, C.c_int64
     lib.pb200_invalid_and_clip.argtypes = [vp, P6, vp, C.POINTER(Params), i64, P6, vp, vp]
     lib.pb200_diagnostic_tests.argtypes = [vp, P6, C.POINTER(Thresholds), i64, vp, vp]
+    lib.pb200_diagnostic_tests_f32.argtypes = [vp, P6, C.POINTER(Thresholds), i64, vp, vp]
     lib.pb200_interpreted_layer.argtypes = [vp, vp, i64, vp, vp]
     lib.pb200_binary_representation.argtypes = [vp, vp, i64, vp, vp]
     lib.pb200_preliminary_cloud.argtypes = [vp, vp, C.c_int, i64, vp, vp]
@@ -138,6 +139,7 @@ def load():
     lib.pb200_binary_water.argtypes = [vp, vp, i64, vp, vp]
     lib.pb200_confidence.argtypes = [vp, vp, vp, i64, vp, vp]
     lib.pb200_collapse.argtypes = [vp, vp, i64, vp, vp]
+    lib.pb200_landcover_aggregate.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_uint8 * 256, C.c_int, C.c_int32 * 4, vp, vp]
     lib.pb200_shadow.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(Params), vp, vp]
     _lib = lib
     return lib

@@ -23,6 +23,7 @@ SOURCES = [os.path.join(CSRC, 'pb200_api.cu')]
 HEADERS = [os.path.join(CSRC, 'pb200_kernels.cuh'),
            os.path.join(CSRC, 'pb200_fused.cuh'),
            os.path.join(CSRC, 'pb200_cover.cuh'),
+           os.path.join(CSRC, 'pb200_landcover.cuh'),
            os.path.join(CSRC, 'pb200_device.cuh'),
            os.path.join(HERE, '..', 'include', 'proteus_b200.h')]
 

@@ -22,6 +22,7 @@
 #include "pb200_kernels.cuh"
 #include "pb200_fused.cuh"
 #include "pb200_cover.cuh"
+#include "pb200_landcover.cuh"
 
 using namespace pb200;
 
@@ -1063,6 +1064,24 @@ extern "C" int pb200_diagnostic_tests(pb200_ctx *ctx, const int16_t *const band[
     LEAVE();
 }
 
+extern "C" int pb200_diagnostic_tests_f32(pb200_ctx *ctx, const float *const band[6], const pb200_thresholds *th,
+                                          int64_t n, uint16_t *diag, void *stream) {
+    ENTER(ctx);
+    EMPTY_OK(n);
+    REQUIRE(band && th && diag && n >= 0, "pb200_diagnostic_tests_f32: bad argument");
+    BandPtrsF in;
+    for (int k = 0; k < 6; ++k) {
+        REQUIRE(band[k], "pb200_diagnostic_tests_f32: band %d is NULL", k);
+        in.p[k] = band[k];
+    }
+    // numpy compares a float32 array with a Python scalar in float32 (NEP 50 weak scalar; same under 1.23)
+    ThresholdsF T{(float)th->wigt, (float)th->awgt, (float)th->pswt_1_mndwi, (float)th->pswt_1_nir,
+                  (float)th->pswt_1_swir1, (float)th->pswt_1_ndvi, (float)th->pswt_2_mndwi, (float)th->pswt_2_blue,
+                  (float)th->pswt_2_nir, (float)th->pswt_2_swir1, (float)th->pswt_2_swir2};
+    diagnostic_tests_f32_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(in, diag, n, T);
+    LEAVE();
+}
+
 extern "C" int pb200_interpreted_layer(pb200_ctx *ctx, const uint16_t *diag, int64_t n, uint8_t *wtr1, void *stream) {
     ENTER(ctx);
     EMPTY_OK(n);
@@ -1249,6 +1268,28 @@ extern "C" int pb200_shadow(pb200_ctx *ctx, const float *dem, int rows, int cols
     SunTerms S{d.sx, d.sy, d.sz, d.sin_az, d.cos_az};
     dim3 block(64, 4), grid((cols + 63) / 64, (rows + 3) / 4);
     shadow_kernel<<<grid, block, 0, st>>>(dem, rows, cols, out, S, P);
+    LEAVE();
+}
+
+extern "C" int pb200_landcover_aggregate(pb200_ctx *ctx, const uint8_t *worldcover, const uint8_t *copernicus, int rows,
+                                         int cols, const uint8_t forest[256], int year_offset,
+                                         const int32_t thresholds[4], uint8_t *land, void *stream) {
+    ENTER(ctx);
+    REQUIRE(rows >= 0 && cols >= 0, "pb200_landcover_aggregate: bad size");
+    if ((long long)rows * cols == 0) return 0;
+    REQUIRE(worldcover && copernicus && forest && thresholds && land, "pb200_landcover_aggregate: null argument");
+    REQUIRE(year_offset >= 0 && year_offset <= 99, "pb200_landcover_aggregate: year offset %d outside 0..99 (D:253-257)",
+            year_offset);
+    LandParams L;
+    L.thr_tree = thresholds[0]; L.thr_low = thresholds[1]; L.thr_high = thresholds[2]; L.thr_water = thresholds[3];
+    L.cls_tree = 201u; L.cls_low = (uint32_t)year_offset; L.cls_high = 100u + (uint32_t)year_offset; L.cls_water = 200u;
+    for (int i = 0; i < 8; ++i) L.forest_bits[i] = 0u;
+    for (int v = 0; v < 256; ++v)
+        if (forest[v]) L.forest_bits[v >> 5] |= 1u << (v & 31);
+    const bool vec = (cols % 4) == 0 && aligned(worldcover, 4) && aligned(copernicus, 4) && aligned(land, 4);
+    dim3 block(32, 8), grid(((cols + 3) / 4 + 31) / 32, (rows + 7) / 8);
+    if (vec) landcover_aggregate_kernel<true><<<grid, block, 0, st>>>(worldcover, copernicus, land, rows, cols, L);
+    else landcover_aggregate_kernel<false><<<grid, block, 0, st>>>(worldcover, copernicus, land, rows, cols, L);
     LEAVE();
 }
 

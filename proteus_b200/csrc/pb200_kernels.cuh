@@ -371,6 +371,30 @@ __global__ void diagnostic_tests_kernel(BandPtrs band, uint16_t *__restrict__ di
     }
 }
 
+// D:1840-1916 on float32 bands (--offset-and-scale-inputs, D:2300-2302): numpy evaluates every
+// operation in float32, left to right, IEEE division, thresholds cast to float32.  Explicit *_rn
+// intrinsics (and -fmad=false) keep the operation order and forbid contraction.
+struct BandPtrsF { const float *p[6]; };
+struct ThresholdsF { float wigt, awgt, p1_mndwi, p1_nir, p1_swir1, p1_ndvi, p2_mndwi, p2_blue, p2_nir, p2_swir1, p2_swir2; };
+__global__ void diagnostic_tests_f32_kernel(BandPtrsF band, uint16_t *__restrict__ diag, long long n, ThresholdsF T) {
+    PB200_GRID_STRIDE(i, n) {
+        const float B = band.p[0][i], G = band.p[1][i], R = band.p[2][i];
+        const float N = band.p[3][i], S1 = band.p[4][i], S2 = band.p[5][i];
+        const float mndwi = __fdiv_rn(__fsub_rn(G, S1), __fadd_rn(G, S1));                       // D:1872
+        const float mbsrv = __fadd_rn(G, R);                                                     // D:1875
+        const float mbsrn = __fadd_rn(N, S1);                                                    // D:1878
+        const float awesh = __fsub_rn(__fsub_rn(__fadd_rn(B, __fmul_rn(2.5f, G)), __fmul_rn(1.5f, mbsrn)),
+                                      __fmul_rn(0.25f, S2));                                     // D:1881
+        const float ndvi = __fdiv_rn(__fsub_rn(N, R), __fadd_rn(N, R));                          // D:1884
+        uint32_t d = (mndwi > T.wigt) ? 1u : 0u;                                                 // D:1893
+        d |= (mbsrv > mbsrn) ? 2u : 0u;                                                          // D:1896
+        d |= (awesh > T.awgt) ? 4u : 0u;                                                         // D:1899
+        d |= (mndwi > T.p1_mndwi && S1 < T.p1_swir1 && N < T.p1_nir && ndvi < T.p1_ndvi) ? 8u : 0u;          // D:1902
+        d |= (mndwi > T.p2_mndwi && B < T.p2_blue && S1 < T.p2_swir1 && S2 < T.p2_swir2 && N < T.p2_nir) ? 16u : 0u;
+        diag[i] = (uint16_t)d;
+    }
+}
+
 // D:1687-1707
 __global__ void interpreted_layer_kernel(const uint16_t *__restrict__ diag, uint8_t *__restrict__ wtr1,
                                          long long n) {

@@ -9,8 +9,8 @@ reference module so that ``generate_dswx_layers`` (D:4610) runs on them
 unchanged; the one-pass fused path is ``proteus_b200.classify_tile``.
 
 Scope notes (explicit errors, no silent fallback):
-  * reflectance bands must be int16 (the default, D:4640): float32 bands from
-    ``--offset-and-scale-inputs`` raise NotImplementedError;
+  * reflectance bands are int16 (the default, D:4640) or, for ``_compute_diagnostic_tests`` only, all
+    float32 (``--offset-and-scale-inputs``); the fused path is int16 only;
   * the DEM must be float32 (what the cubic warp of D:5145 produces).
 """
 from __future__ import annotations
@@ -108,7 +108,19 @@ def _compute_diagnostic_tests(blue, green, red, nir, swir1, swir2,
     ctx = get_context()
     shape = np.shape(blue)
     params = make_params(hls_thresholds)
-    dev = [_band(b, n) for b, n in zip((blue, green, red, nir, swir1, swir2),
+    all_bands = (blue, green, red, nir, swir1, swir2)
+    if all(np.asarray(b).dtype == np.float32 for b in all_bands):
+        # scaled reflectances (--offset-and-scale-inputs, D:2300-2302): float32 arithmetic in numpy's order
+        dev = [_to_device(b, np.float32, 'band') for b in all_bands]
+        for d in dev:
+            if tuple(d.shape) != tuple(shape):
+                raise ValueError('operands could not be broadcast together: all bands must have the same shape')
+        out = _empty_like_device(shape, np.uint16)
+        ptrs = (C.c_void_p * 6)(*[d.data_ptr() for d in dev])
+        _lib.check(ctx._lib.pb200_diagnostic_tests_f32(
+            ctx.handle, ptrs, C.byref(params.th), int(np.prod(shape)), out.data_ptr(), _stream()))
+        return _to_host(out, np.uint16)
+    dev = [_band(b, n) for b, n in zip(all_bands,
                                         ('blue', 'green', 'red', 'nir', 'swir1', 'swir2'))]
     for d in dev:
         if tuple(d.shape) != tuple(shape):
@@ -312,6 +324,39 @@ def _compute_opera_shadow_layer(dem, sun_azimuth_angle, sun_elevation_angle,
         ctx.handle, dev.data_ptr(), d.shape[0], d.shape[1], float(sun_azimuth_angle),
         float(sun_elevation_angle), terms, C.byref(params), out.data_ptr(), _stream()))
     return _to_host(out, np.uint8).astype(bool)
+
+
+# ---------------------------------------------------------------------------
+# D:874-904 + D:1003-1115: the numpy tail of create_landcover_mask
+# ---------------------------------------------------------------------------
+landcover_threshold_dict = {"standard": [6, 3, 7, 3], "water heavy": [6, 3, 7, 1]}     # D:270-271
+
+
+def landcover_aggregate(worldcover_array_up_3, copernicus_landcover_array,
+                        forest_mask_landcover_classes, year, mask_type='standard'):
+    """LAND layer from the two warped rasters ``create_landcover_mask`` holds at D:1003: the ESA
+    WorldCover raster at 10 m (3x the product grid, uint8) and the CGLS land cover on the product
+    grid (uint8).  ``year`` is the WorldCover map year the reference reads from the file metadata
+    (D:1064-1094).  The reference has no separate function for these statements; this one replaces
+    D:1003-1115."""
+    ctx = get_context()
+    wc = np.asarray(worldcover_array_up_3)
+    cp = np.asarray(copernicus_landcover_array)
+    if wc.ndim != 2 or cp.ndim != 2 or wc.shape != (3 * cp.shape[0], 3 * cp.shape[1]):
+        raise ValueError('worldcover_array_up_3 must be exactly 3x the CGLS / product grid')
+    th = landcover_threshold_dict[mask_type.lower()]
+    table = np.zeros(256, np.uint8)
+    for c in (forest_mask_landcover_classes or ()):
+        if 0 <= int(c) <= 255:
+            table[int(c)] = 1
+    dwc = _to_device(wc, np.uint8, 'worldcover_array_up_3')
+    dcp = _to_device(cp, np.uint8, 'copernicus_landcover_array')
+    out = _empty_like_device(cp.shape, np.uint8)
+    _lib.check(ctx._lib.pb200_landcover_aggregate(
+        ctx.handle, dwc.data_ptr(), dcp.data_ptr(), int(cp.shape[0]), int(cp.shape[1]),
+        (C.c_uint8 * 256)(*[int(v) for v in table]), int(year) - 2000, (C.c_int32 * 4)(*th),
+        out.data_ptr(), _stream()))
+    return _to_host(out, np.uint8)
 
 
 def _crop_2d_array_all_sides(input_2d_array, margin):

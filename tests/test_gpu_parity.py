@@ -382,3 +382,44 @@ def test_masked_dilation_matches_scipy(pb):
             ctx.handle, da.data_ptr(), dm.data_ptr(), shape[0], shape[1], iters, out.data_ptr(),
             scr.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         assert np.array_equal(out.cpu().numpy().astype(bool), ref), (shape, iters)
+
+
+def test_landcover_aggregate_matches_reference_fixture(pb):
+    """SURVEY 8f next #1 on the GPU: the numpy tail of create_landcover_mask."""
+    import os
+    from conftest import GOLDEN_DIR
+    import proteus_b200.dswx_hls as G
+    z = np.load(os.path.join(GOLDEN_DIR, 'landcover.npz'))
+    forest = z['forest_classes'].tolist()
+    for i in (0, 1):            # 152 columns: vector path; 93 columns: generic path
+        got = G.landcover_aggregate(z[f'wc{i}'], z[f'cop{i}'], forest, int(z[f'year{i}']), str(z[f'type{i}']))
+        assert got.dtype == np.uint8 and np.array_equal(got, z[f'land{i}']), i
+    rng = np.random.default_rng(12)
+    wc = rng.integers(0, 256, (3 * 64, 3 * 200), dtype=np.uint8)
+    wc[rng.random(wc.shape) < 0.5] = 80
+    cop = rng.integers(0, 256, (64, 200), dtype=np.uint8)
+    assert np.array_equal(G.landcover_aggregate(wc, cop, forest, 2030, 'water heavy'),
+                          O.landcover_aggregate(wc, cop, forest, 30, 'water heavy'))
+    assert np.array_equal(G.landcover_aggregate(wc, cop, None, 2000), O.landcover_aggregate(wc, cop, None, 0))
+    with pytest.raises(ValueError):
+        G.landcover_aggregate(wc[:-1], cop, forest, 2021)
+
+
+def test_float32_diagnostic_tests_match_reference_fixture(pb):
+    """_compute_diagnostic_tests on float32 bands (--offset-and-scale-inputs): float32 arithmetic in
+    numpy's operation order, IEEE division, no FMA contraction -> bit-exact codes."""
+    import os
+    from conftest import GOLDEN_DIR
+    import proteus_b200.dswx_hls as G
+    z = np.load(os.path.join(GOLDEN_DIR, 'float_diag.npz'))
+    for key in ('scaled', 'dn'):
+        got = G._compute_diagnostic_tests(*[z[f'{key}{k}'] for k in range(6)], G.HlsThresholds())
+        assert got.dtype == np.uint16 and np.array_equal(got, z[f'diag_{key}']), key
+    rng = np.random.default_rng(8)
+    bands = [(rng.standard_normal((50, 300)) * 3000).astype(np.float32) for _ in range(6)]
+    bands[1][0, :8] = 0.0
+    bands[4][0, :8] = 0.0                                  # 0/0 and x/0
+    bands[3][1, :8] = np.inf
+    with np.errstate(all='ignore'):
+        ref = O.compute_diagnostic_tests(*bands, O.default_thresholds())
+    assert np.array_equal(G._compute_diagnostic_tests(*bands, G.HlsThresholds()), ref)

@@ -120,3 +120,26 @@ def test_coverage_percentages_edge_cases():
     assert O.coverage_percentages(0, 0, 0, 100) == (0, 0, 0)
     assert O.coverage_percentages(99, 98, 100, 100) == (99, 99, 98)
     assert O.coverage_percentages(1, 1, 3, 3) == (33, 33, 100)
+
+
+def test_landcover_aggregate_matches_reference_fixture():
+    """oracle vs the live create_landcover_mask outputs (tests/golden/landcover.npz,
+    made with the function's GDAL calls replaced, oracle/ref_import.live_create_landcover_mask)."""
+    z = np.load(os.path.join(GOLDEN_DIR, 'landcover.npz'))
+    forest = z['forest_classes'].tolist()
+    for i in (0, 1):
+        got = O.landcover_aggregate(z[f'wc{i}'], z[f'cop{i}'], forest, int(z[f'year{i}']) - 2000, str(z[f'type{i}']))
+        assert got.dtype == np.uint8 and np.array_equal(got, z[f'land{i}']), i
+    a = np.arange(36, dtype=np.uint8).reshape(6, 6)
+    assert np.array_equal(O.decimate_by_summation(a, 3, 3), [[a[:3, :3].sum(), a[:3, 3:].sum() % 256],
+                                                             [a[3:, :3].sum() % 256, a[3:, 3:].sum() % 256]])
+
+
+def test_float32_diagnostic_tests_match_reference_fixture():
+    """The --offset-and-scale-inputs flavour of _compute_diagnostic_tests (float32 bands)."""
+    z = np.load(os.path.join(GOLDEN_DIR, 'float_diag.npz'))
+    th = O.default_thresholds()
+    with np.errstate(all='ignore'):
+        for key in ('scaled', 'dn'):
+            got = O.compute_diagnostic_tests(*[z[f'{key}{k}'] for k in range(6)], th)
+            assert np.array_equal(got, z[f'diag_{key}']), key

@@ -1,0 +1,88 @@
+"""The oracle against the LIVE reference imported from /root/reference (build container only; skipped
+on the GPU box, where the committed fixtures of tests/golden/ stand in).  Function by function, on
+seeds and shapes that differ from the fixtures."""
+import numpy as np
+import pytest
+
+from oracle import dswx_oracle as O
+from oracle import ref_import
+from proteus_b200 import synth
+
+pytestmark = pytest.mark.skipif(not ref_import.available(), reason='/root/reference is not present')
+
+
+@pytest.fixture(scope='module')
+def ref():
+    return ref_import.load()
+
+
+@pytest.fixture(scope='module')
+def ref_thresholds(ref):
+    th = ref.HlsThresholds()
+    for k, v in ref_import.default_runconfig_groups()['hls_thresholds'].items():
+        setattr(th, k, v)
+    return th
+
+
+def test_reference_unit_test_runs_against_the_oracle(ref):
+    """The reference's own test (tests/test_dswx_hls_units.py:7-28), with the oracle in place of
+    generate_interpreted_layer - and the reference function itself for comparison."""
+    width = len(ref.interpreted_dswx_band_dict) + 1
+    inp = np.full((1, width), 111111)
+    exp = np.full((1, width), 255)
+    for i, (k, v) in enumerate(ref.interpreted_dswx_band_dict.items()):
+        inp[0, i], exp[0, i] = k, v
+    assert np.array_equal(ref.generate_interpreted_layer(inp), exp)
+    assert np.array_equal(O.generate_interpreted_layer(inp), exp)
+
+
+@pytest.mark.parametrize('seed,adversarial', [(101, False), (102, True)])
+def test_functions_against_live_reference(ref, ref_thresholds, seed, adversarial):
+    t = synth.make_tile(seed, 96, 140, adversarial=adversarial)
+    th, oth = ref_thresholds, O.default_thresholds()
+    clipped = [np.clip(b, 1, None) for b in t['bands']]
+    with np.errstate(all='ignore'):
+        d_ref = ref._compute_diagnostic_tests(*clipped, th)
+        assert np.array_equal(O.compute_diagnostic_tests(*clipped, oth), d_ref)
+        raw = t['bands']                                   # unclipped: zero denominators occur
+        assert np.array_equal(O.compute_diagnostic_tests(*raw, oth), ref._compute_diagnostic_tests(*raw, th))
+        f32 = [b.astype(np.float32) * np.float32(1e-4) for b in clipped]
+        assert np.array_equal(O.compute_diagnostic_tests(*f32, oth), ref._compute_diagnostic_tests(*f32, th))
+    assert np.array_equal(O.get_binary_representation(d_ref), ref._get_binary_representation(d_ref))
+    for mode in ('mask', 'ignore', 'cover'):
+        assert np.array_equal(O.compute_preliminary_cloud_layer(t['fmask'], mode),
+                              ref._compute_preliminary_cloud_layer(t['fmask'], mode))
+    shad_ref = ref._compute_opera_shadow_layer(t['dem'], 133.0, 27.0, -5, 40)
+    assert np.array_equal(O.compute_opera_shadow_layer(t['dem'], 133.0, 27.0, -5, 40), shad_ref)
+    rng = np.random.default_rng(seed)
+    wtr = np.array([0, 1, 2, 3, 4, 254, 255], np.uint8)[rng.integers(0, 7, t['fmask'].shape)]
+    cloud = np.array([0, 1, 4, 5, 8, 9, 12, 13], np.uint8)[rng.integers(0, 8, t['fmask'].shape)]
+    lists = ([224, 160, 96], [224, 160, 96], [224, 192, 160, 128, 96], [224, 192, 160, 128, 96])
+    w1, c1, w2, c2 = wtr.copy(), cloud.copy(), wtr.copy(), cloud.copy()
+    ref._apply_aerosol_class_remapping(w1, clipped[3], c1, t['fmask'], *lists)
+    O.apply_aerosol_class_remapping(w2, clipped[3], c2, t['fmask'], *lists)
+    assert np.array_equal(w1, w2) and np.array_equal(c1, c2)
+    shad = ref._crop_2d_array_all_sides(shad_ref, 50)
+    for land, sh in ((t['land'], shad), (None, shad), (t['land'], None)):
+        assert np.array_equal(O.apply_landcover_and_shadow_masks(wtr, clipped[3], land, sh, oth),
+                              ref._apply_landcover_and_shadow_masks(wtr, clipped[3], land, sh, th))
+    for mode in ('mask', 'ignore', 'cover'):
+        assert np.array_equal(O.add_snow_to_cloud_layer(wtr, cloud.copy(), t['fmask'], mode),
+                              ref._add_snow_to_cloud_layer(wtr, cloud.copy(), t['fmask'], mode))
+    full = ref._add_snow_to_cloud_layer(wtr, cloud.copy(), t['fmask'], 'mask')
+    assert np.array_equal(O.apply_cloud_masking(wtr, full), ref._apply_cloud_masking(wtr, full))
+    assert np.array_equal(O.get_binary_water_layer(wtr), ref._get_binary_water_layer(wtr))
+    assert np.array_equal(O.get_confidence_layer(wtr, full), ref._get_confidence_layer(wtr, full))
+    allv = np.arange(256, dtype=np.uint8).reshape(16, 16)
+    assert np.array_equal(O.collapse_wtr_classes(allv), ref._collapse_wtr_classes(allv))
+
+
+def test_landcover_tail_against_live_reference():
+    from oracle.make_golden import make_landcover_inputs
+    forest = ref_import.default_runconfig_groups()['processing']['forest_mask_landcover_classes']
+    wc, cop = make_landcover_inputs(77, 40, 52)
+    for year, mt in ((2021, 'standard'), (2099, 'water heavy')):
+        live = ref_import.live_create_landcover_mask(wc, cop, forest, year, mt)
+        assert np.array_equal(O.landcover_aggregate(wc, cop, forest, year - 2000, mt), live)
+    assert np.array_equal(O.landcover_aggregate(wc, cop, None, 21),
+                          ref_import.live_create_landcover_mask(wc, cop, None, 2021))
