@@ -667,7 +667,10 @@ static int plan_build(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles, cons
             const uint32_t slot = (uint32_t)td[G_FAST].size();
             for (int ty = 0; ty < nty; ++ty)
                 for (int tx = 0; tx < ntx; ++tx) items.push_back(ItemDesc{slot, (uint16_t)tx, (uint16_t)ty});
-            if (d.wtr1 || d.wtr1r || d.wtr2 || d.cloud || d.shad || params->class_histogram) pl->fast_optional = true;
+            // the lean kernel variant assumes the four graded layers and the counters; anything else -> full variant
+            if (d.wtr1 || d.wtr1r || d.wtr2 || d.cloud || d.shad || params->class_histogram || !d.diag || !d.wtr ||
+                !d.bwtr || !d.conf || !d.counters)
+                pl->fast_optional = true;
         }
         pl->item_end.push_back((int)items.size());
         td[g].push_back(d);
@@ -914,7 +917,7 @@ extern "C" int pb200_classify_host(pb200_ctx *ctx, const pb200_tile *ht, const p
     uint8_t *const host_u8[8] = {ht->wtr1, ht->wtr1_remapped, ht->wtr2, ht->cloud, ht->shad, ht->wtr, ht->bwtr, ht->conf};
     uint8_t **dev_u8_field[8] = {&dt.wtr1, &dt.wtr1_remapped, &dt.wtr2, &dt.cloud, &dt.shad, &dt.wtr, &dt.bwtr, &dt.conf};
     for (int i = 0; i < 8; ++i) *dev_u8_field[i] = host_u8[i] ? p.u8out[i] : nullptr;
-    dt.counters = ht->counters ? (uint64_t *)p.counters : nullptr;
+    dt.counters = (uint64_t *)p.counters;             // always counted on the device (lean kernel variant); copied back on request
     DevParams P;
     rc = derive_params(params, &P, true);
     if (rc) return rc;

@@ -8,10 +8,10 @@
 //
 //  * a lane owns 4 consecutive pixels of a row (one 8-byte load per band - row
 //    pitch 3660 * 2 B is only 8-byte aligned - and 4-byte loads / stores of the
-//    byte rasters); a CTA is 16 warps at <= 64 registers so that 32 warps per SM
-//    hide the table-look-up, shared-memory and global-load latencies (an 8-pixel
-//    lane with 16-byte accesses needed 123 registers -> 16 warps per SM and
-//    measured 60 % issue utilisation, profiles/);
+//    byte rasters); a CTA is 8 warps at <= 80 registers, 3 CTAs per SM: the row
+//    loop does not spill, and the loads of the next row are issued in the middle
+//    of the current one (an 8-pixel lane with 16-byte accesses needed 123
+//    registers -> 16 warps per SM and measured 60 % issue utilisation, profiles/);
 //  * int16 bands stay packed two pixels per register: fill test, clip, the
 //    wrapping sums and the integer threshold tests run on the 16x2 SIMD
 //    integer pipe (VIMNMX[3].x16x2, VIADD.16x2, VIADDMNMX.S16x2); 4*awesh is
@@ -41,7 +41,14 @@ namespace pb200 {
 #define PB200_FT_ROWGROUPS 8       // warps (row groups of 4 rows) per 128-pixel half
 #endif
 #ifndef PB200_FT_MIN_CTAS
-#define PB200_FT_MIN_CTAS (1024 / (32 * PB200_FT_ROWGROUPS * PB200_FT_HALVES))
+#define PB200_FT_MIN_CTAS (768 / (32 * PB200_FT_ROWGROUPS * PB200_FT_HALVES))   // 24 warps per SM at <= 80 registers
+#endif
+#ifndef PB200_FT_PREFETCH
+// where the global loads of a row are issued: -1 at the top of that row (no prefetch), 0 at the end of the previous
+// row, 1 in the previous row before its shadow test, 2 after it, 3 a whole row ahead into a second register set.
+// Measured on B200 (profiles/README.md): 1 with 3 CTAs x 80 registers >= -1 with 4 CTAs x 64 registers > the rest;
+// any variant that spills in the row loop loses 10-15 %.
+#define PB200_FT_PREFETCH 1
 #endif
 constexpr int FT_HALVES = PB200_FT_HALVES;
 constexpr int FT_ROWGROUPS = PB200_FT_ROWGROUPS;
@@ -103,7 +110,7 @@ struct __align__(128) FastSmem {
     uint8_t  land_lut[256];
     uint8_t  kill_lut[128];
     TileDev  tile;                      // descriptor of the current tile
-    float    sun32[8];                  // float32(sin_az, cos_az, sx, sy, sz) of the current tile
+    float    sun32[12];                 // SK_* constants of the current tile
     unsigned long long mbar;
     unsigned int cnt[N_CNT];
 };
@@ -126,15 +133,16 @@ __device__ __forceinline__ void stg_stream_v4(void *p, uint32_t a, uint32_t b, u
 // certainly not, and sets *undecided when a value is too close to a decision
 // boundary (or not finite): the caller then runs the exact float64 sequence.
 // Error budget in DESIGN.md section 3.
+// per-tile float32 constants of the shortcut (FastSmem::sun32), from the float64 sun terms:
+enum { SK_SA = 0, SK_CA, SK_SX, SK_SY, SK_SZ, SK_XX, SK_YY, SK_EA, SK_EB, SK_N };
+//   kx*sin_az, ky*cos_az, kx*sx, ky*sy, sz, kx*kx, ky*ky, 1e-6*|kx*sin_az|, 1e-6*|ky*cos_az|   (kx = 0.5/dx, ky = 0.5/dy)
 __device__ __forceinline__ uint32_t shadow_fast(float l, float r, float u, float d, const FastParams &F,
-                                                float sa, float ca, float sx, float sy, float sz, bool *undecided) {
-    const float nxa = (l - r) * F.kx;                     // ~ -g_col / dx
-    const float nya = (u - d) * F.ky;                     // ~ -g_row / dy
-    const float t1 = nxa * sa, t2 = nya * ca;
-    const float diff = (t1 + t2) - F.tan32;               // ~ s - tan_thr
-    const float e = fmaf(fabsf(t1) + fabsf(t2), 1e-6f, F.e0);
-    const float dot = fmaf(nxa, sx, fmaf(nya, sy, sz));
-    const float v = fmaf(nxa, nxa, fmaf(nya, nya, 1.0f));
+                                                const float (&K)[SK_N], bool *undecided) {
+    const float a = l - r, b = u - d;                     // -2 g_col, -2 g_row: the reference's own float32 differences
+    const float diff = fmaf(a, K[SK_SA], fmaf(b, K[SK_CA], -F.tan32));          // ~ s - tan_thr
+    const float e = fmaf(fabsf(a), K[SK_EA], fmaf(fabsf(b), K[SK_EB], F.e0));   // 1e-6 (|t1| + |t2|) + e0
+    const float dot = fmaf(a, K[SK_SX], fmaf(b, K[SK_SY], K[SK_SZ]));
+    const float v = fmaf(a * a, K[SK_XX], fmaf(b * b, K[SK_YY], 1.0f));         // ~ nf^2
     const float L = dot * fabsf(dot);                     // t -> t|t| is monotone: x >= c for any sign of c
     const float D = fmaf(-F.cc32, v, L);
     const float eg = 4e-6f * v;
@@ -146,6 +154,37 @@ __device__ __forceinline__ uint32_t shadow_fast(float l, float r, float u, float
     const bool not_shadow = (diff > e) || ((D > eg) && (L < 0.99999f * v));
     *undecided = *undecided || !(is_shadow || not_shadow);
     return is_shadow ? 0x200u : 0u;
+}
+
+// Shared-memory reads through an explicit 32-bit shared address: the base is computed once per thread
+// (an opaque register), instead of being re-derived from SR_CgaCtaId in front of every group of
+// register-indexed look-ups (S2R / S2UR + LEA, profiles/).  The volatile forms are for data that changes
+// between items (tile descriptor, DEM tile); the tables are read-only after the prologue.
+__device__ __forceinline__ uint32_t lds_tab32(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_tab8(uint32_t a) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float2 lds_f32x2(uint32_t a) {
+    float2 v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a)); return v;
+}
+__device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T *lds_ptr(uint32_t a) {
+    unsigned long long v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a)); return reinterpret_cast<T *>(v);
+}
+#define FS_OFF(member) ((uint32_t)offsetof(FastSmem, member))
+#define FS_TILE(member) ((uint32_t)(offsetof(FastSmem, tile) + offsetof(TileDev, member)))
+
+// address of element `pix` of a plane: one IMAD.WIDE (FMA pipe) instead of a 64-bit add pair on the ALU pipe
+template <typename T>
+__device__ __forceinline__ T *plane_at(T *base, uint32_t pix) {
+    unsigned long long r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(pix), "n"((int)sizeof(T)), "l"(base));
+    return reinterpret_cast<T *>(r);
 }
 
 // Rare paths kept out of line so that the hot loop stays small.
@@ -177,6 +216,8 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FastSmem &s = *reinterpret_cast<FastSmem *>(smem_raw);
 #endif
+    uint32_t sb = (uint32_t)__cvta_generic_to_shared(&s);    // shared address of the block, kept in a register
+    asm volatile("mov.b32 %0, %0;" : "+r"(sb));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int half = warp % FT_HALVES;                    // which 128-pixel half of the item
     const int rgrp = warp / FT_HALVES;                    // which group of 4 rows
@@ -198,8 +239,9 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
     // when the CTA moves to another tile (and at the end): valid | cloud-and-valid << 16, not-ocean
     uint32_t acc_vc = 0, acc_nno = 0;
     unsigned long long acc_hist = 0ull;
-    unsigned long long *cur_counters = nullptr;
     auto flush_counters = [&]() {
+        // the descriptor in shared memory is still that of the tile being left (it is replaced after the flush)
+        unsigned long long *cur_counters = (cur_tile != 0xffffffffu) ? lds_ptr<unsigned long long>(sb + FS_TILE(counters)) : nullptr;
         if (cur_counters != nullptr) {
             const uint32_t wv = __reduce_add_sync(0xffffffffu, acc_vc & 0xffffu);
             const uint32_t wc = __reduce_add_sync(0xffffffffu, acc_vc >> 16);
@@ -232,19 +274,21 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
             if (tid < (int)(sizeof(TileDev) / 4)) dst[tid] = __ldg(src + tid);
             if (tid == 64) {
                 const TileDev &g = tiles[item.tile];
-                s.sun32[0] = (float)g.sin_az; s.sun32[1] = (float)g.cos_az;
-                s.sun32[2] = (float)g.sx; s.sun32[3] = (float)g.sy; s.sun32[4] = (float)g.sz;
+                const double kx = 0.5 / (double)P.dxf, ky = 0.5 / (double)P.dyf;
+                s.sun32[SK_SA] = (float)(kx * g.sin_az); s.sun32[SK_CA] = (float)(ky * g.cos_az);
+                s.sun32[SK_SX] = (float)(kx * g.sx); s.sun32[SK_SY] = (float)(ky * g.sy); s.sun32[SK_SZ] = (float)g.sz;
+                s.sun32[SK_XX] = (float)(kx * kx); s.sun32[SK_YY] = (float)(ky * ky);
+                s.sun32[SK_EA] = 1e-6f * fabsf(s.sun32[SK_SA]); s.sun32[SK_EB] = 1e-6f * fabsf(s.sun32[SK_CA]);
             }
             cur_tile = item.tile;
             __syncthreads();
-            cur_counters = s.tile.counters;
         }
         const int W = s.tile.width, H = s.tile.height;
         const int x0 = item.tx * FT_W, y0 = item.ty * FT_H;
         const bool has_dem = s.tile.dem != nullptr;
         const bool has_land = s.tile.land != nullptr;
         const bool has_ocean = s.tile.ocean != nullptr;
-        const bool has_counters = s.tile.counters != nullptr;
+        const bool has_counters = !OPTIONAL_LAYERS || s.tile.counters != nullptr;   // lean variant: checked by the host
         const int padx = DEM_PADX + (s.tile.dem_off_x & 3);
         if (has_dem && tid == 0) {
             // the generic-proxy reads of the previous item are ordered before these
@@ -258,30 +302,58 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
         }
         const bool want_shad = OPTIONAL_LAYERS && s.tile.shad != nullptr;
         // the four graded layers present: one test instead of four in the row loop
-        const bool all_graded = s.tile.diag && s.tile.wtr && s.tile.bwtr && s.tile.conf;
+        const bool all_graded = !OPTIONAL_LAYERS || (s.tile.diag && s.tile.wtr && s.tile.bwtr && s.tile.conf);
 
         bool dem_ready = !has_dem;
 
         const int x = x0 + 128 * half + 4 * lane;         // this lane's 4 pixels
-        if (x < W) {
+        const int nrows = min(FT_ROWS_PER_WARP, H - (y0 + rgrp * FT_ROWS_PER_WARP));   // warp-uniform
+        if (x < W && nrows > 0) {
+            // ---- loads: 8 bytes per band, 4 bytes per byte raster.  The input registers of a row are dead
+            // after its packed and table stages: the loads of the next row are issued there, ahead of the
+            // shadow test, the final look-ups and the stores, which hide their latency (PB200_FT_PREFETCH).
+            uint32_t w[6][2], fm4, ld4 = 0xffffffffu, oc4 = 0x01010101u;   // no LAND class / not ocean
+            uint32_t pix = (uint32_t)(y0 + rgrp * FT_ROWS_PER_WARP) * (uint32_t)W + (uint32_t)x;   // < 2^32 checked on the host
+#ifdef PB200_EXPERIMENT_FAKE_LOADS
+            // issue-rate experiment (never shipped): inputs synthesised from the pixel index, no global loads
+#define FT_LOAD_ROW(w, fm4, ld4, oc4, AT)                                                                       \
+    do {                                                                                      \
+        _Pragma("unroll") for (int k = 0; k < 6; ++k) {                                       \
+            w[k][0] = ((AT) ^ (0x01230456u * (k + 1))) & 0x0fff0fffu;                         \
+            w[k][1] = ((AT) ^ (0x06540321u * (k + 3))) & 0x0fff0fffu;                         \
+        }                                                                                     \
+        fm4 = ((AT) ^ 0x40a0c060u) & 0xe0e0e0e0u;                                             \
+        if (has_land) ld4 = (AT) | 0x80808080u;                                               \
+        if (has_ocean) oc4 = 0x01010101u & ((AT) >> 4);                                       \
+    } while (0)
+#else
+#define FT_LOAD_ROW(w, fm4, ld4, oc4, AT)                                                                                        \
+    do {                                                                                                       \
+        _Pragma("unroll") for (int k = 0; k < 6; ++k) {                                                        \
+            const int2 v = ldg_stream_v2(plane_at(lds_ptr<const int16_t>(sb + FS_TILE(band) + 8 * k), (AT)));  \
+            w[k][0] = (uint32_t)v.x; w[k][1] = (uint32_t)v.y;                                                  \
+        }                                                                                                      \
+        fm4 = ldg_stream_u32(plane_at(lds_ptr<const uint8_t>(sb + FS_TILE(fmask)), (AT)));                     \
+        if (has_land) ld4 = ldg_stream_u32(plane_at(lds_ptr<const uint8_t>(sb + FS_TILE(land)), (AT)));        \
+        if (has_ocean) oc4 = ldg_stream_u32(plane_at(lds_ptr<const uint8_t>(sb + FS_TILE(ocean)), (AT)));      \
+    } while (0)
+#endif
+#if PB200_FT_PREFETCH >= 0
+            FT_LOAD_ROW(w, fm4, ld4, oc4, pix);
+#endif
 #pragma unroll 1
-            for (int rr = 0; rr < FT_ROWS_PER_WARP; ++rr) {
+            for (int rr = 0; rr < nrows; ++rr, pix += (uint32_t)W) {
                 const int ly = rgrp * FT_ROWS_PER_WARP + rr;
-                const int y = y0 + ly;
-                if (y >= H) break;                        // warp-uniform
-                const uint32_t pix = (uint32_t)y * (uint32_t)W + (uint32_t)x;     // < 2^32 checked on the host
-
-                // ---- loads: 8 bytes per band, 4 bytes per byte raster ------------------
-                uint32_t w[6][2];
+#if PB200_FT_PREFETCH < 0
+                FT_LOAD_ROW(w, fm4, ld4, oc4, pix);       // no prefetch: 32 warps per SM hide the latency
+#endif
+#if PB200_FT_PREFETCH == 3
+                // a whole row ahead, into a second register set (needs > 64 registers: fewer, fatter warps)
+                uint32_t wn[6][2], fm4n = 0u, ld4n = 0xffffffffu, oc4n = 0x01010101u;
 #pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    const int2 v = ldg_stream_v2(s.tile.band[k] + pix);
-                    w[k][0] = (uint32_t)v.x; w[k][1] = (uint32_t)v.y;
-                }
-                const uint32_t fm4 = ldg_stream_u32(s.tile.fmask + pix);
-                uint32_t ld4 = 0xffffffffu, oc4 = 0x01010101u;          // no LAND class / not ocean
-                if (has_land) ld4 = ldg_stream_u32(s.tile.land + pix);
-                if (has_ocean) oc4 = ldg_stream_u32(s.tile.ocean + pix);
+                for (int k = 0; k < 6; ++k) wn[k][0] = wn[k][1] = 0u;
+                if (rr + 1 < nrows) FT_LOAD_ROW(wn, fm4n, ld4n, oc4n, pix + (uint32_t)W);
+#endif
 
                 uint32_t idx[4], dgw[2], k1p[2], water_any = 0u;
 #pragma unroll
@@ -293,11 +365,7 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                     {
                         uint32_t xf[6];
 #pragma unroll
-                        for (int k = 0; k < 6; ++k) xf[k] = w[k][p] ^ F.fill_xor[k];                   // D:2204-2207
-                        if (F.any_nofill) {                                   // rare: a raster without fill value
-#pragma unroll
-                            for (int k = 0; k < 6; ++k) xf[k] |= F.fill_or[k];
-                        }
+                        for (int k = 0; k < 6; ++k) xf[k] = (w[k][p] ^ F.fill_xor[k]) | F.fill_or[k];   // D:2204-2207 (one LOP3)
                         const uint32_t xfm = __byte_perm(fm4 ^ F.fmask_xor4, 0u, selb) | F.fmask_or;
                         xm = __vimin3_u16x2(__vimin3_u16x2(xf[0], xf[1], xf[2]), xf[3], xf[4]);
                         xm = __vimin3_u16x2(xm, xf[5], xfm);                  // half == 0 <=> pixel invalid
@@ -374,11 +442,11 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                     for (int hh = 0; hh < 2; ++hh) {
                         const bool hi = hh;
                         const int j = 2 * p + hh;
-                        dl[hh] = s.diag_lut[dcode[hh]];                       // D:5227-5231, 5245, 5249
+                        dl[hh] = lds_tab32(sb + FS_OFF(diag_lut) + 4u * dcode[hh]);   // D:5227-5231, 5245, 5249
                         const uint32_t k1s = dl[hh] >> 16;                    // k1 << 8
                         const uint32_t fi = hi ? ((fa >> 16) | k1s) : ((fa & 0xffffu) | k1s);
-                        const uint32_t ev = s.fk_lut[fi];                     // D:1237-1246, 1984-1991, 2081
-                        const uint32_t cat = s.land_lut[(ld4 >> (8 * j)) & 255u];
+                        const uint32_t ev = lds_tab8(sb + FS_OFF(fk_lut) + fi);       // D:1237-1246, 1984-1991, 2081
+                        const uint32_t cat = lds_tab8(sb + FS_OFF(land_lut) + ((ld4 >> (8 * j)) & 255u));
                         const uint32_t bri = hi ? (brp >> 16) : (brp & 0xffffu);
                         idx[j] = ((ev & 0x7Fu) | bri) + (cat << 7);
                         water_any |= ev;                                      // bit 7: the pixel holds a water class
@@ -386,6 +454,11 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                     dgw[p] = __byte_perm(dl[0], dl[1], 0x5410);               // two DIAG values
                     if (OPTIONAL_LAYERS) k1p[p] = __byte_perm(dl[0], dl[1], 0x4743);   // k1 of the two pixels in bytes 0 and 2
                 }
+
+                if (has_counters) acc_nno = __dp4a(oc4, 0x01010101u, acc_nno);   // D:5105; no shoreline: 1 per pixel (D:5107)
+#if PB200_FT_PREFETCH == 1
+                if (rr + 1 < nrows) FT_LOAD_ROW(w, fm4, ld4, oc4, pix + (uint32_t)W);
+#endif
 
                 // ---- terrain shadow: only where it can change the result ----------------
                 // (bit 7 of a fk_lut byte = the pixel holds a water class: only those can be masked, D:1340-1343)
@@ -395,45 +468,49 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                         mbar_wait(&s.mbar, dem_phase);
                         dem_ready = true;
                     }
-                    const int sc = 4 * lane + padx;                           // smem column of this lane's first pixel
-                    const float *rm = &s.dem[half].v[ly + 1][sc];
-                    const float *ru = &s.dem[half].v[ly][sc];
-                    const float *rd = &s.dem[half].v[ly + 2][sc];
+                    // shared address of this lane's first pixel in the middle row of the 3-row window
+                    const uint32_t am = sb + FS_OFF(dem) + (uint32_t)half * (uint32_t)sizeof(DemHalf) +
+                                        4u * (uint32_t)((ly + 1) * FT_SMW + 4 * lane + padx);
+                    constexpr uint32_t RB = 4u * FT_SMW;                      // bytes per row of the DEM tile
                     float m[6], u[4], d[4];
                     if ((padx & 1) == 0) {
                         // even DEM margins (production: 50): 8-byte vectors
-                        const float2 m0 = *reinterpret_cast<const float2 *>(rm - 2);
-                        const float2 m1 = *reinterpret_cast<const float2 *>(rm);
-                        const float2 m2 = *reinterpret_cast<const float2 *>(rm + 2);
-                        const float2 m3 = *reinterpret_cast<const float2 *>(rm + 4);
-                        m[0] = m0.y; m[1] = m1.x; m[2] = m1.y; m[3] = m2.x; m[4] = m2.y; m[5] = m3.x;
-                        const float2 u0 = *reinterpret_cast<const float2 *>(ru);
-                        const float2 u1 = *reinterpret_cast<const float2 *>(ru + 2);
-                        u[0] = u0.x; u[1] = u0.y; u[2] = u1.x; u[3] = u1.y;
-                        const float2 d0 = *reinterpret_cast<const float2 *>(rd);
-                        const float2 d1 = *reinterpret_cast<const float2 *>(rd + 2);
-                        d[0] = d0.x; d[1] = d0.y; d[2] = d1.x; d[3] = d1.y;
+                        m[0] = lds_f32(am - 4);
+                        const float2 m1 = lds_f32x2(am), m2 = lds_f32x2(am + 8);
+                        m[1] = m1.x; m[2] = m1.y; m[3] = m2.x; m[4] = m2.y;
+                        const float2 u0 = lds_f32x2(am - RB), d0 = lds_f32x2(am + RB);
+                        u[0] = u0.x; u[1] = u0.y; d[0] = d0.x; d[1] = d0.y;
+                        m[5] = lds_f32(am + 16);
+                        const float2 u1 = lds_f32x2(am - RB + 8), d1 = lds_f32x2(am + RB + 8);
+                        u[2] = u1.x; u[3] = u1.y; d[2] = d1.x; d[3] = d1.y;
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 6; ++j) m[j] = rm[j - 1];
+                        for (int j = 0; j < 6; ++j) m[j] = lds_f32(am + 4 * j - 4);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) { u[j] = ru[j]; d[j] = rd[j]; }
+                        for (int j = 0; j < 4; ++j) { u[j] = lds_f32(am - RB + 4 * j); d[j] = lds_f32(am + RB + 4 * j); }
                     }
                     bool undecided = (F.fast_shadow_ok == 0u);
-                    const float sa = s.sun32[0], ca = s.sun32[1], sx = s.sun32[2], sy = s.sun32[3], sz = s.sun32[4];
+                    float K[SK_N];
+                    {
+                        const float4 k0 = lds_f32x4(sb + FS_OFF(sun32)), k1 = lds_f32x4(sb + FS_OFF(sun32) + 16);
+                        K[0] = k0.x; K[1] = k0.y; K[2] = k0.z; K[3] = k0.w; K[4] = k1.x; K[5] = k1.y; K[6] = k1.z; K[7] = k1.w;
+                        K[8] = lds_f32(sb + FS_OFF(sun32) + 32);
+                    }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        shw[j] = shadow_fast(m[j], m[j + 2], u[j], d[j], F, sa, ca, sx, sy, sz, &undecided);
+                    for (int j = 0; j < 4; ++j) shw[j] = shadow_fast(m[j], m[j + 2], u[j], d[j], F, K, &undecided);
                     if (undecided) {
                         // rare: redo the 4 pixels with the float64 reference sequence
 #pragma unroll
                         for (int j = 0; j < 4; ++j) shw[j] = shadow_exact(m[j], m[j + 2], u[j], d[j], P, s.tile);
                     }
                 }
+#if PB200_FT_PREFETCH == 2
+                if (rr + 1 < nrows) FT_LOAD_ROW(w, fm4, ld4, oc4, pix + (uint32_t)W);
+#endif
                 // ---- final look-up (D:1331-1376, 2084-2131, 1727, 1793-1835) ------------------
                 uint32_t o[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) o[j] = s.big_lut[idx[j] | shw[j]];
+                for (int j = 0; j < 4; ++j) o[j] = lds_tab32(sb + FS_OFF(big_lut) + 4u * (idx[j] | shw[j]));
 
                 // ---- pack and store -------------------------------------------------------
                 const uint32_t t01a = __byte_perm(o[0], o[1], 0x5140);
@@ -445,10 +522,10 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                 const uint32_t conf4 = __byte_perm(t01b, t23b, 0x5410);
                 const uint32_t flag4 = __byte_perm(t01b, t23b, 0x7632);
                 if (all_graded) {
-                    stg_stream_v2(s.tile.diag + pix, dgw[0], dgw[1]);
-                    stg_stream_u32(s.tile.wtr + pix, wtr4);
-                    stg_stream_u32(s.tile.bwtr + pix, bwtr4);
-                    stg_stream_u32(s.tile.conf + pix, conf4);
+                    stg_stream_v2(plane_at(lds_ptr<uint16_t>(sb + FS_TILE(diag)), pix), dgw[0], dgw[1]);
+                    stg_stream_u32(plane_at(lds_ptr<uint8_t>(sb + FS_TILE(wtr)), pix), wtr4);
+                    stg_stream_u32(plane_at(lds_ptr<uint8_t>(sb + FS_TILE(bwtr)), pix), bwtr4);
+                    stg_stream_u32(plane_at(lds_ptr<uint8_t>(sb + FS_TILE(conf)), pix), conf4);
                 } else {
                     if (s.tile.diag) stg_stream_v2(s.tile.diag + pix, dgw[0], dgw[1]);
                     if (s.tile.wtr) stg_stream_u32(s.tile.wtr + pix, wtr4);
@@ -485,13 +562,20 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                 if (has_counters) {
                     // valid in the low half, cloud-and-valid in the high half (a thread sees < 2^16 pixels per tile)
                     acc_vc += __popc(flag4 & 0x01010101u) + (__popc(flag4 & 0x02020202u) << 16);
-                    acc_nno = __dp4a(oc4, 0x01010101u, acc_nno);               // D:5105; no shoreline: 1 per pixel (D:5107)
                     if (histogram) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) acc_hist += 1ull << (7u * ((flag4 >> (8 * j + 4)) & 15u));
                     }
                 }
+#if PB200_FT_PREFETCH == 0
+                if (rr + 1 < nrows) FT_LOAD_ROW(w, fm4, ld4, oc4, pix + (uint32_t)W);
+#elif PB200_FT_PREFETCH == 3
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { w[k][0] = wn[k][0]; w[k][1] = wn[k][1]; }
+                fm4 = fm4n; ld4 = ld4n; oc4 = oc4n;
+#endif
             }
+#undef FT_LOAD_ROW
         }
 
         // the TMA of this item must have landed before the next one is issued
