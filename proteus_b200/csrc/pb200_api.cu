@@ -456,7 +456,8 @@ struct pb200_ctx {
     int device = 0;
     int sm_count = 0;
     bool fast_ready = false;
-    int fast_ctas_per_sm = 1;
+    int fast_ctas_per_sm = 1;        // lean variant
+    int fast_ctas_per_sm_full = 1;   // variant with the optional layers
     EncodeTiledFn encode = nullptr;
     HostPipe pipe;
     std::mutex mu;
@@ -713,12 +714,8 @@ static int plan_build(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles, cons
     return 0;
 }
 
-// one 128-px half per item: FastSmem is a static __shared__ object (absolute addresses); otherwise dynamic
-#ifdef PB200_FAST_DYNAMIC_SMEM
+// FastSmem (double-buffered DEM tile + tables, 51 KB) is dynamic shared memory: above the 48 KB static limit
 constexpr size_t FAST_DYN_SMEM = sizeof(FastSmem);
-#else
-constexpr size_t FAST_DYN_SMEM = (FT_HALVES == 1) ? 0 : sizeof(FastSmem);
-#endif
 
 static int fast_kernel_setup(pb200_ctx *ctx) {
     if (ctx->fast_ready) return 0;
@@ -731,6 +728,8 @@ static int fast_kernel_setup(pb200_ctx *ctx) {
     int nb = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dswx_fused_fast_kernel<false>, FT_THREADS, FAST_DYN_SMEM));
     ctx->fast_ctas_per_sm = nb > 0 ? nb : 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dswx_fused_fast_kernel<true>, FT_THREADS, FAST_DYN_SMEM));
+    ctx->fast_ctas_per_sm_full = nb > 0 ? nb : 1;
     ctx->fast_ready = true;
     return 0;
 }
@@ -739,7 +738,8 @@ static int plan_launch(pb200_plan *pl, cudaStream_t stream) {
     if (pl->n[G_FAST]) {
         int rc = fast_kernel_setup(pl->ctx);
         if (rc) return rc;
-        const int grid = std::min(pl->n_items, pl->ctx->sm_count * pl->ctx->fast_ctas_per_sm);
+        const int grid = std::min(pl->n_items, pl->ctx->sm_count * (pl->fast_optional ? pl->ctx->fast_ctas_per_sm_full
+                                                                                       : pl->ctx->fast_ctas_per_sm));
         if (pl->fast_optional)
             dswx_fused_fast_kernel<true><<<grid, FT_THREADS, FAST_DYN_SMEM, stream>>>(
                 pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, pl->d_items, pl->n_items, pl->P, pl->F);
@@ -766,7 +766,8 @@ static int plan_launch_tile(pb200_plan *pl, int i, cudaStream_t stream) {
         int rc = fast_kernel_setup(pl->ctx);
         if (rc) return rc;
         const int n = pl->item_end[i] - pl->item_start[i];
-        const int grid = std::min(n, pl->ctx->sm_count * pl->ctx->fast_ctas_per_sm);
+        const int grid = std::min(n, pl->ctx->sm_count * (pl->fast_optional ? pl->ctx->fast_ctas_per_sm_full
+                                                                            : pl->ctx->fast_ctas_per_sm));
         const ItemDesc *it = pl->d_items + pl->item_start[i];
         if (pl->fast_optional)
             dswx_fused_fast_kernel<true><<<grid, FT_THREADS, FAST_DYN_SMEM, stream>>>(

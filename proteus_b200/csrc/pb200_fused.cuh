@@ -43,12 +43,11 @@ namespace pb200 {
 #ifndef PB200_FT_MIN_CTAS
 #define PB200_FT_MIN_CTAS (768 / (32 * PB200_FT_ROWGROUPS * PB200_FT_HALVES))   // 24 warps per SM at <= 80 registers
 #endif
-#ifndef PB200_FT_PREFETCH
-// where the global loads of a row are issued: -1 at the top of that row (no prefetch), 0 at the end of the previous
-// row, 1 in the previous row before its shadow test, 2 after it, 3 a whole row ahead into a second register set.
-// Measured on B200 (profiles/README.md): 1 with 3 CTAs x 80 registers >= -1 with 4 CTAs x 64 registers > the rest;
-// any variant that spills in the row loop loses 10-15 %.
-#define PB200_FT_PREFETCH 1
+#ifndef PB200_FT_PRODUCER_WARP
+#define PB200_FT_PRODUCER_WARP 0   // DEM requests by thread 0 (0) or by warp 0 with lane 0 issuing (1)
+#endif
+#ifndef PB200_FT_XITEM_PREFETCH
+#define PB200_FT_XITEM_PREFETCH 1  // request the first row of the next item in the last row of the current one
 #endif
 constexpr int FT_HALVES = PB200_FT_HALVES;
 constexpr int FT_ROWGROUPS = PB200_FT_ROWGROUPS;
@@ -103,7 +102,7 @@ struct __align__(128) DemHalf { float v[FT_SMH][FT_SMW]; };   // TMA destination
 constexpr uint32_t DEM_BOX_BYTES = FT_SMH * FT_SMW * sizeof(float);
 
 struct __align__(128) FastSmem {
-    DemHalf dem[FT_HALVES];             // one box per 128-px half of the item
+    DemHalf dem[2][FT_HALVES];          // double buffer: the DEM tile of item k + 1 streams in while item k is classified
     uint32_t big_lut[2048];
     uint32_t diag_lut[128];
     uint8_t  fk_lut[4096];
@@ -111,8 +110,8 @@ struct __align__(128) FastSmem {
     uint8_t  kill_lut[128];
     TileDev  tile;                      // descriptor of the current tile
     float    sun32[12];                 // SK_* constants of the current tile
-    unsigned long long mbar;
-    unsigned int cnt[N_CNT];
+    unsigned long long full[2];         // TMA transaction barriers, one per DEM buffer
+    unsigned long long empty[2];        // one arrival per warp when it is done with an item's buffer
 };
 
 __device__ __forceinline__ int sext_lo(uint32_t x) { return (int)(short)(x & 0xffffu); }
@@ -160,6 +159,9 @@ __device__ __forceinline__ uint32_t shadow_fast(float l, float r, float u, float
 // (an opaque register), instead of being re-derived from SR_CgaCtaId in front of every group of
 // register-indexed look-ups (S2R / S2UR + LEA, profiles/).  The volatile forms are for data that changes
 // between items (tile descriptor, DEM tile); the tables are read-only after the prologue.
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ uint32_t lds_tab32(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds_tab8(uint32_t a) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
@@ -206,16 +208,12 @@ __device__ __noinline__ uint32_t shadow_exact(float l, float r, float u, float d
 
 // ---------------------------------------------------------------------------
 template <bool OPTIONAL_LAYERS>
-__global__ void __launch_bounds__(FT_THREADS, FT_MIN_CTAS)
+__global__ void __launch_bounds__(FT_THREADS, OPTIONAL_LAYERS ? (FT_MIN_CTAS > 2 ? 2 : FT_MIN_CTAS) : FT_MIN_CTAS)
 dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__restrict__ tmaps,
                        const FusedTables *__restrict__ tables, const ItemDesc *__restrict__ items, int n_items,
                        const __grid_constant__ DevParams P, const __grid_constant__ FastParams F) {
-#if PB200_FT_HALVES == 1 && !defined(PB200_FAST_DYNAMIC_SMEM)
-    __shared__ FastSmem s;                                // 32 KB: static, absolute shared addresses
-#else
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];   // 51 KB: dynamic (every access goes through `sb`)
     FastSmem &s = *reinterpret_cast<FastSmem *>(smem_raw);
-#endif
     uint32_t sb = (uint32_t)__cvta_generic_to_shared(&s);    // shared address of the block, kept in a register
     asm volatile("mov.b32 %0, %0;" : "+r"(sb));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -230,11 +228,15 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                       "smem table block mirrors FusedTables");
         static_assert(offsetof(FastSmem, big_lut) % 16 == 0, "16-byte table copies");
         for (int i = tid; i < (int)(sizeof(FusedTables) / 16); i += FT_THREADS) dst[i] = __ldg(src + i);
-        if (tid == 0) mbar_init(&s.mbar, 1);
-        if (tid < N_CNT) s.cnt[tid] = 0u;
+        if (tid == 0) {
+            mbar_init(&s.full[0], 1); mbar_init(&s.full[1], 1);
+            mbar_init(&s.empty[0], FT_THREADS / 32); mbar_init(&s.empty[1], FT_THREADS / 32);
+        }
     }
     uint32_t cur_tile = 0xffffffffu;
-    uint32_t dem_phase = 0;
+    // DEM pipeline state, identical in every thread: bit b = parity of the next phase of full[b] (toggled after each
+    // item of a tile with a DEM that used buffer b), bit 2 + b = buffer b has carried a transaction
+    uint32_t fstate = 0;
     // counters accumulate in registers across the items of a tile and are flushed once per warp
     // when the CTA moves to another tile (and at the end): valid | cloud-and-valid << 16, not-ocean
     uint32_t acc_vc = 0, acc_nno = 0;
@@ -263,11 +265,46 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
     };
     const bool histogram = OPTIONAL_LAYERS && (P.flags & PF_HISTOGRAM) != 0u;   // lean variant: 3 counters only
 
+    // DEM request for the item with ordinal j of this CTA, by warp 0 (all lanes wait, lane 0 issues).  Buffer
+    // j & 1 is free when every warp has arrived on empty[] for item j - 2 and its previous transaction has landed.
+    auto request_dem = [&](uint32_t j, const ItemDesc &d, int padx) {
+        const uint32_t b = j & 1u;
+        if (j >= 2u) mbar_wait(&s.empty[b], ((j >> 1) - 1u) & 1u);
+        if (fstate & (4u << b)) mbar_wait(&s.full[b], ((fstate >> b) & 1u) ^ 1u);   // its previous transaction
+        if (PB200_FT_PRODUCER_WARP == 0 || lane == 0) {
+            // generic-proxy reads of the buffer (ordered by the empty barrier) before the async-proxy writes
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&s.full[b], (uint32_t)FT_HALVES * DEM_BOX_BYTES);
+            const int gx = s.tile.dem_off_x + d.tx * FT_W - padx, gy = s.tile.dem_off_y + d.ty * FT_H - 1;
+#pragma unroll
+            for (int hf = 0; hf < FT_HALVES; ++hf)
+                tma_load_2d(&s.dem[b][hf].v[0][0], &tmaps[d.tile], gx + 128 * hf, gy, &s.full[b]);
+        }
+        if (PB200_FT_PRODUCER_WARP) __syncwarp();
+    };
+
+    // input registers of one row of 4 pixels; they persist across items: the first row of the next item of this
+    // CTA is requested in the last row of the current one
+    uint32_t w[6][2], fm4 = 0u, ld4 = 0xffffffffu, oc4 = 0x01010101u;   // no LAND class / not ocean
+#pragma unroll
+    for (int k = 0; k < 6; ++k) w[k][0] = w[k][1] = 0u;
+    bool row_loaded = false;
+
+    ItemDesc item;
+    item.tile = 0xffffffffu; item.tx = 0; item.ty = 0;
+    if ((int)blockIdx.x < n_items) item = items[blockIdx.x];
+    uint32_t k = 0;                                       // ordinal of the item in this CTA's sequence
 #pragma unroll 1
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-        const ItemDesc item = items[it];
-        __syncthreads();                                  // previous item fully consumed (DEM tile, tile descriptor)
-        if (item.tile != cur_tile) {
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k) {
+        // descriptor of the item after this one: loaded a whole item ahead
+        ItemDesc next;
+        next.tile = 0xffffffffu; next.tx = 0; next.ty = 0;
+        if (it + (int)gridDim.x < n_items) next = items[it + gridDim.x];
+
+        const bool fresh_tile = item.tile != cur_tile;    // else: this item's DEM tile was requested during the previous item
+        if (fresh_tile) {
+            // tile change (rare: a CTA sees ~7 items per HLS tile): the only CTA-wide synchronisation
+            __syncthreads();                              // every warp is done with the previous tile
             flush_counters();                             // of the tile this CTA is leaving
             const uint32_t *src = reinterpret_cast<const uint32_t *>(&tiles[item.tile]);
             uint32_t *dst = reinterpret_cast<uint32_t *>(&s.tile);
@@ -281,6 +318,7 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                 s.sun32[SK_EA] = 1e-6f * fabsf(s.sun32[SK_SA]); s.sun32[SK_EB] = 1e-6f * fabsf(s.sun32[SK_CA]);
             }
             cur_tile = item.tile;
+            ld4 = 0xffffffffu; oc4 = 0x01010101u;         // defaults of a tile without LAND / ocean raster
             __syncthreads();
         }
         const int W = s.tile.width, H = s.tile.height;
@@ -290,15 +328,10 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
         const bool has_ocean = s.tile.ocean != nullptr;
         const bool has_counters = !OPTIONAL_LAYERS || s.tile.counters != nullptr;   // lean variant: checked by the host
         const int padx = DEM_PADX + (s.tile.dem_off_x & 3);
-        if (has_dem && tid == 0) {
-            // the generic-proxy reads of the previous item are ordered before these
-            // async-proxy writes by the barrier above plus this fence
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(&s.mbar, (uint32_t)FT_HALVES * DEM_BOX_BYTES);
-            const int gx = s.tile.dem_off_x + x0 - padx, gy = s.tile.dem_off_y + y0 - 1;
-#pragma unroll
-            for (int hf = 0; hf < FT_HALVES; ++hf)
-                tma_load_2d(&s.dem[hf].v[0][0], &tmaps[item.tile], gx + 128 * hf, gy, &s.mbar);
+        const uint32_t buf = k & 1u;
+        if (has_dem && (PB200_FT_PRODUCER_WARP ? warp == 0 : tid == 0)) {
+            if (fresh_tile) request_dem(k, item, padx);
+            if (next.tile == cur_tile) request_dem(k + 1u, next, padx);
         }
         const bool want_shad = OPTIONAL_LAYERS && s.tile.shad != nullptr;
         // the four graded layers present: one test instead of four in the row loop
@@ -310,50 +343,38 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
         const int nrows = min(FT_ROWS_PER_WARP, H - (y0 + rgrp * FT_ROWS_PER_WARP));   // warp-uniform
         if (x < W && nrows > 0) {
             // ---- loads: 8 bytes per band, 4 bytes per byte raster.  The input registers of a row are dead
-            // after its packed and table stages: the loads of the next row are issued there, ahead of the
-            // shadow test, the final look-ups and the stores, which hide their latency (PB200_FT_PREFETCH).
-            uint32_t w[6][2], fm4, ld4 = 0xffffffffu, oc4 = 0x01010101u;   // no LAND class / not ocean
+            // after its packed and table stages: the loads of the next row (of the next item, in the last row)
+            // are issued there, ahead of the shadow test, the final look-ups and the stores, which hide their latency.
             uint32_t pix = (uint32_t)(y0 + rgrp * FT_ROWS_PER_WARP) * (uint32_t)W + (uint32_t)x;   // < 2^32 checked on the host
 #ifdef PB200_EXPERIMENT_FAKE_LOADS
             // issue-rate experiment (never shipped): inputs synthesised from the pixel index, no global loads
-#define FT_LOAD_ROW(w, fm4, ld4, oc4, AT)                                                                       \
+#define FT_LOAD_ROW(AT)                                                                       \
     do {                                                                                      \
-        _Pragma("unroll") for (int k = 0; k < 6; ++k) {                                       \
-            w[k][0] = ((AT) ^ (0x01230456u * (k + 1))) & 0x0fff0fffu;                         \
-            w[k][1] = ((AT) ^ (0x06540321u * (k + 3))) & 0x0fff0fffu;                         \
+        _Pragma("unroll") for (int kk = 0; kk < 6; ++kk) {                                    \
+            w[kk][0] = ((AT) ^ (0x01230456u * (kk + 1))) & 0x0fff0fffu;                       \
+            w[kk][1] = ((AT) ^ (0x06540321u * (kk + 3))) & 0x0fff0fffu;                       \
         }                                                                                     \
         fm4 = ((AT) ^ 0x40a0c060u) & 0xe0e0e0e0u;                                             \
         if (has_land) ld4 = (AT) | 0x80808080u;                                               \
         if (has_ocean) oc4 = 0x01010101u & ((AT) >> 4);                                       \
     } while (0)
 #else
-#define FT_LOAD_ROW(w, fm4, ld4, oc4, AT)                                                                                        \
-    do {                                                                                                       \
-        _Pragma("unroll") for (int k = 0; k < 6; ++k) {                                                        \
-            const int2 v = ldg_stream_v2(plane_at(lds_ptr<const int16_t>(sb + FS_TILE(band) + 8 * k), (AT)));  \
-            w[k][0] = (uint32_t)v.x; w[k][1] = (uint32_t)v.y;                                                  \
-        }                                                                                                      \
-        fm4 = ldg_stream_u32(plane_at(lds_ptr<const uint8_t>(sb + FS_TILE(fmask)), (AT)));                     \
-        if (has_land) ld4 = ldg_stream_u32(plane_at(lds_ptr<const uint8_t>(sb + FS_TILE(land)), (AT)));        \
-        if (has_ocean) oc4 = ldg_stream_u32(plane_at(lds_ptr<const uint8_t>(sb + FS_TILE(ocean)), (AT)));      \
+#define FT_LOAD_ROW(AT)                                                                                          \
+    do {                                                                                                         \
+        _Pragma("unroll") for (int kk = 0; kk < 6; ++kk) {                                                       \
+            const int2 v = ldg_stream_v2(plane_at(lds_ptr<const int16_t>(sb + FS_TILE(band) + 8 * kk), (AT)));   \
+            w[kk][0] = (uint32_t)v.x; w[kk][1] = (uint32_t)v.y;                                                  \
+        }                                                                                                        \
+        fm4 = ldg_stream_u32(plane_at(lds_ptr<const uint8_t>(sb + FS_TILE(fmask)), (AT)));                       \
+        if (has_land) ld4 = ldg_stream_u32(plane_at(lds_ptr<const uint8_t>(sb + FS_TILE(land)), (AT)));          \
+        if (has_ocean) oc4 = ldg_stream_u32(plane_at(lds_ptr<const uint8_t>(sb + FS_TILE(ocean)), (AT)));        \
     } while (0)
 #endif
-#if PB200_FT_PREFETCH >= 0
-            FT_LOAD_ROW(w, fm4, ld4, oc4, pix);
-#endif
+            if (!row_loaded) FT_LOAD_ROW(pix);            // not requested by the previous item (first item of a tile, raster edge)
+            row_loaded = false;
 #pragma unroll 1
             for (int rr = 0; rr < nrows; ++rr, pix += (uint32_t)W) {
                 const int ly = rgrp * FT_ROWS_PER_WARP + rr;
-#if PB200_FT_PREFETCH < 0
-                FT_LOAD_ROW(w, fm4, ld4, oc4, pix);       // no prefetch: 32 warps per SM hide the latency
-#endif
-#if PB200_FT_PREFETCH == 3
-                // a whole row ahead, into a second register set (needs > 64 registers: fewer, fatter warps)
-                uint32_t wn[6][2], fm4n = 0u, ld4n = 0xffffffffu, oc4n = 0x01010101u;
-#pragma unroll
-                for (int k = 0; k < 6; ++k) wn[k][0] = wn[k][1] = 0u;
-                if (rr + 1 < nrows) FT_LOAD_ROW(wn, fm4n, ld4n, oc4n, pix + (uint32_t)W);
-#endif
 
                 uint32_t idx[4], dgw[2], k1p[2], water_any = 0u;
 #pragma unroll
@@ -456,20 +477,27 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                 }
 
                 if (has_counters) acc_nno = __dp4a(oc4, 0x01010101u, acc_nno);   // D:5105; no shoreline: 1 per pixel (D:5107)
-#if PB200_FT_PREFETCH == 1
-                if (rr + 1 < nrows) FT_LOAD_ROW(w, fm4, ld4, oc4, pix + (uint32_t)W);
-#endif
+                if (rr + 1 < nrows) {
+                    FT_LOAD_ROW(pix + (uint32_t)W);
+                } else if (PB200_FT_XITEM_PREFETCH && next.tile == cur_tile) {
+                    // last row: first row of this warp in the next item of the CTA (same tile, same planes)
+                    const int xn = next.tx * FT_W + 128 * half + 4 * lane, yn = next.ty * FT_H + rgrp * FT_ROWS_PER_WARP;
+                    if (xn < W && yn < H) {
+                        FT_LOAD_ROW((uint32_t)yn * (uint32_t)W + (uint32_t)xn);
+                        row_loaded = true;
+                    }
+                }
 
                 // ---- terrain shadow: only where it can change the result ----------------
                 // (bit 7 of a fk_lut byte = the pixel holds a water class: only those can be masked, D:1340-1343)
                 uint32_t shw[4] = {0u, 0u, 0u, 0u};                           // 0x200 = in shadow
                 if (has_dem && (want_shad || (water_any & 0x80u))) {
                     if (!dem_ready) {
-                        mbar_wait(&s.mbar, dem_phase);
+                        mbar_wait(&s.full[buf], (fstate >> buf) & 1u);
                         dem_ready = true;
                     }
                     // shared address of this lane's first pixel in the middle row of the 3-row window
-                    const uint32_t am = sb + FS_OFF(dem) + (uint32_t)half * (uint32_t)sizeof(DemHalf) +
+                    const uint32_t am = sb + FS_OFF(dem) + (buf * FT_HALVES + (uint32_t)half) * (uint32_t)sizeof(DemHalf) +
                                         4u * (uint32_t)((ly + 1) * FT_SMW + 4 * lane + padx);
                     constexpr uint32_t RB = 4u * FT_SMW;                      // bytes per row of the DEM tile
                     float m[6], u[4], d[4];
@@ -504,9 +532,6 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                         for (int j = 0; j < 4; ++j) shw[j] = shadow_exact(m[j], m[j + 2], u[j], d[j], P, s.tile);
                     }
                 }
-#if PB200_FT_PREFETCH == 2
-                if (rr + 1 < nrows) FT_LOAD_ROW(w, fm4, ld4, oc4, pix + (uint32_t)W);
-#endif
                 // ---- final look-up (D:1331-1376, 2084-2131, 1727, 1793-1835) ------------------
                 uint32_t o[4];
 #pragma unroll
@@ -567,23 +592,28 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                         for (int j = 0; j < 4; ++j) acc_hist += 1ull << (7u * ((flag4 >> (8 * j + 4)) & 15u));
                     }
                 }
-#if PB200_FT_PREFETCH == 0
-                if (rr + 1 < nrows) FT_LOAD_ROW(w, fm4, ld4, oc4, pix + (uint32_t)W);
-#elif PB200_FT_PREFETCH == 3
-#pragma unroll
-                for (int k = 0; k < 6; ++k) { w[k][0] = wn[k][0]; w[k][1] = wn[k][1]; }
-                fm4 = fm4n; ld4 = ld4n; oc4 = oc4n;
-#endif
             }
 #undef FT_LOAD_ROW
         }
 
-        // the TMA of this item must have landed before the next one is issued
-        if (has_dem && !dem_ready) mbar_wait(&s.mbar, dem_phase);
-        if (has_dem) dem_phase ^= 1u;
+        // A warp that never looked at the DEM tile (no water pixel, raster edge) must still see the item's
+        // transaction land before it arrives: the request for item k + 2 waits for all arrivals of item k, so no
+        // warp can get two items ahead and arrive twice in one phase of empty[].
+        if (has_dem && !dem_ready) mbar_wait(&s.full[buf], (fstate >> buf) & 1u);
+        // this warp is done with the item's DEM buffer (every warp arrives for every item: phases count items)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s.empty[buf]);
+        if (has_dem) fstate = (fstate ^ (1u << buf)) | (4u << buf);   // one transaction per item of a tile with a DEM
 
         // histogram bins are 7 bits wide and an item adds at most 16 pixels per thread: flush every 4 items
-        if (histogram && ((it / (int)gridDim.x) & 3) == 3) flush_counters();
+        if (histogram && (k & 3u) == 3u) flush_counters();
+        item = next;
+    }
+    // no transaction may be in flight when the CTA exits
+    if (warp == 0) {
+#pragma unroll
+        for (uint32_t b = 0; b < 2u; ++b)
+            if (fstate & (4u << b)) mbar_wait(&s.full[b], ((fstate >> b) & 1u) ^ 1u);
     }
     flush_counters();
 }
