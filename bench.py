@@ -354,11 +354,15 @@ def run_ours(args):
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.start()
+    # cudaProfilerStart/Stop bracket the timed regions: `ncu --profile-from-start off` then lists exactly the
+    # kernels launched inside them (profiles/r1_launches_gpu_time.csv); no effect without a profiler attached
+    torch.cuda.cudart().cudaProfilerStart()
     ev0.record(stream)
     for _ in range(args.steps):
         plan.run(stream)
     ev1.record(stream)
     barrier()
+    torch.cuda.cudart().cudaProfilerStop()
     sampler.pause()
     ms_total = ev0.elapsed_time(ev1)
     t = torch.tensor([ms_total], dtype=torch.float64, device='cuda')
@@ -412,11 +416,13 @@ def run_ours(args):
             host_res = host_step()
         barrier()
         sampler.start()
+        torch.cuda.cudart().cudaProfilerStart()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             host_res = host_step()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        torch.cuda.cudart().cudaProfilerStop()
         sampler.pause()
         tt = torch.tensor([dt], dtype=torch.float64, device='cuda')
         if world > 1:

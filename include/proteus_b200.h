@@ -241,6 +241,24 @@ int  pb200_landcover_aggregate(pb200_ctx *ctx, const uint8_t *worldcover_up3,
                                const uint8_t forest_class_table[256], int year_offset,
                                const int32_t thresholds[4], uint8_t *land, void *stream);
 
+/* SURVEY 8f next #4 - the point-wise tails that let the whole product leave the GPU.
+ *
+ * pb200_browse_table (host only): the 256-entry relabel table of _compute_browse_array (D:3057-3129):
+ * PSW-aggressive -> not water (exclude_psw_aggressive), collapse (D:2578), then not-water / cloud / snow /
+ * ocean-masked -> 255 as the four flags say.  pb200_byte_table applies any such table to a uint8 raster
+ * (table in HOST memory, passed by value to the kernel). */
+int  pb200_browse_table(int collapse_wtr_classes, int exclude_psw_aggressive,
+                        int set_not_water_to_nodata, int set_cloud_to_nodata,
+                        int set_snow_to_nodata, int set_ocean_masked_to_nodata,
+                        uint8_t table[256]);
+int  pb200_byte_table(pb200_ctx *ctx, const uint8_t *in, int64_t n, const uint8_t table[256],
+                      uint8_t *out, void *stream);
+/* D:2301-2302 and D:3024-3036: out = float32(scale) * (float32(band) - float32(offset)), float32
+ * arithmetic as numpy evaluates it with Python-float scalars; invalid (bool raster or NULL): NaN where
+ * set (D:3033-3036). */
+int  pb200_scale_offset(pb200_ctx *ctx, const int16_t *band, int64_t n, double scale, double offset,
+                        const uint8_t *invalid, float *out, void *stream);
+
 /* ---- helpers exported for tests ---------------------------------------- */
 /* The exact integer form of "float64(n)/float64(d) > t" (is_less = 0) or
  * "< t" (is_less = 1) for int16 n, d:  with p/q = n/d, q > 0,

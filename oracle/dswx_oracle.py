@@ -412,6 +412,35 @@ def landcover_aggregate(worldcover_up_3, copernicus_landcover, forest_mask_landc
 # --------------------------------------------------------------------------
 # the chain, in the order of generate_dswx_layers  (D:5088-5369)
 # --------------------------------------------------------------------------
+def compute_browse_array(masked_interpreted_water_layer, flag_collapse_wtr_classes=True,
+                         exclude_psw_aggressive=False, set_not_water_to_nodata=False,
+                         set_cloud_to_nodata=False, set_snow_to_nodata=False,
+                         set_ocean_masked_to_nodata=True):
+    """_compute_browse_array, dswx_hls.py:3057-3129 (SURVEY 8f next #4)."""
+    b = np.array(masked_interpreted_water_layer, copy=True)
+    if exclude_psw_aggressive:
+        b[b == 4] = 0                                     # :3107-3110
+    if flag_collapse_wtr_classes:
+        b = collapse_wtr_classes(b)                       # :3112-3113
+    if set_not_water_to_nodata:
+        b[b == 0] = 255                                   # :3115-3116
+    if set_cloud_to_nodata:
+        b[b == 253] = 255                                 # :3118-3119
+    if set_snow_to_nodata:
+        b[b == 252] = 255                                 # :3121-3122
+    if set_ocean_masked_to_nodata:
+        b[b == 254] = 255                                 # :3124-3125
+    return b
+
+
+def scale_and_offset_band(image, scale_factor, offset, invalid_ind=None):
+    """dswx_hls.py:2301-2302 and :3024-3036: float32 array arithmetic with Python-float scalars."""
+    out = float(scale_factor) * (np.asarray(image, dtype=np.float32) - float(offset))
+    if invalid_ind is not None:
+        out[invalid_ind] = np.nan
+    return out
+
+
 def reference_chain(raw_bands, fmask, dem_with_margin=None, landcover=None,
                     ocean_mask=None, sun_azimuth_angle=150.0,
                     sun_elevation_angle=45.0, thresholds=None,

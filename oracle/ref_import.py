@@ -106,3 +106,38 @@ def live_create_landcover_mask(worldcover_up_3, copernicus, forest_classes, year
                                              'projection', h, w, forest_classes, temp_files_list=[])
     finally:
         ref._warp = saved
+
+
+def live_save_output_rgb(red, green, blue, offset_dict, scale_dict, invalid_ind=None, flag_infrared=False):
+    """Run the UNMODIFIED ``_save_output_rgb_file`` (dswx_hls.py:2960-3053) with a GDAL driver stand-in that
+    captures the three arrays it writes: the float32 offset-and-scale statements (D:3024-3036) execute as written."""
+    ref = load()
+    written = []
+
+    class _Band:
+        def WriteArray(self, a):
+            written.append(a.copy())
+
+    class _Dataset:
+        def SetMetadata(self, *a): pass
+        def SetGeoTransform(self, *a): pass
+        def SetProjection(self, *a): pass
+        def GetRasterBand(self, i): return _Band()
+        def FlushCache(self): pass
+
+    class _Driver:
+        def Create(self, *a, **k): return _Dataset()
+
+    saved = (getattr(ref.gdal, 'GetDriverByName', None), ref.save_as_cog, ref._makedirs)
+    ref.gdal.GetDriverByName = lambda name: _Driver()
+    ref.save_as_cog = lambda *a, **k: None
+    ref._makedirs = lambda *a, **k: None
+    try:
+        ref._save_output_rgb_file(red, green, blue, 'rgb.tif', offset_dict, scale_dict, False, {}, (0, 30, 0, 0, 0, -30),
+                                  'projection', invalid_ind=invalid_ind, output_files_list=None,
+                                  flag_infrared=flag_infrared)
+    finally:
+        if saved[0] is not None:
+            ref.gdal.GetDriverByName = saved[0]
+        ref.save_as_cog, ref._makedirs = saved[1], saved[2]
+    return written

@@ -1248,6 +1248,53 @@ extern "C" int pb200_collapse(pb200_ctx *ctx, const uint8_t *layer, int64_t n, u
     LEAVE();
 }
 
+extern "C" int pb200_browse_table(int collapse_wtr_classes, int exclude_psw_aggressive, int set_not_water_to_nodata,
+                                  int set_cloud_to_nodata, int set_snow_to_nodata, int set_ocean_masked_to_nodata,
+                                  uint8_t table[256]) {
+    if (!table) return fail(PB200_E_INVALID_ARG, "pb200_browse_table: null table");
+    for (int v = 0; v < 256; ++v) {
+        int x = v;
+        if (exclude_psw_aggressive && x == 4) x = 0;                 // D:3107-3110
+        if (collapse_wtr_classes) {                                   // D:3112-3113, table D:201-213
+            switch (x) {
+                case 0: case 1: case 252: case 253: case 254: case 255: break;
+                case 2: x = 1; break;
+                case 3: case 4: x = 2; break;
+                default: x = 255;
+            }
+        }
+        if (set_not_water_to_nodata && x == 0) x = 255;               // D:3115-3116
+        if (set_cloud_to_nodata && x == 253) x = 255;                 // D:3118-3119
+        if (set_snow_to_nodata && x == 252) x = 255;                  // D:3121-3122
+        if (set_ocean_masked_to_nodata && x == 254) x = 255;          // D:3124-3125
+        table[v] = (uint8_t)x;
+    }
+    return 0;
+}
+
+extern "C" int pb200_byte_table(pb200_ctx *ctx, const uint8_t *in, int64_t n, const uint8_t table[256], uint8_t *out,
+                                void *stream) {
+    ENTER(ctx);
+    EMPTY_OK(n);
+    REQUIRE(in && out && table && n >= 0, "pb200_byte_table: bad argument");
+    if (n == 0) return 0;
+    ByteTable T;
+    std::memcpy(T.v, table, 256);
+    byte_table_kernel<<<grid_for(ctx, (n + 3) / 4, 256), 256, 0, st>>>(in, out, n, T);
+    LEAVE();
+}
+
+extern "C" int pb200_scale_offset(pb200_ctx *ctx, const int16_t *band, int64_t n, double scale, double offset,
+                                  const uint8_t *invalid, float *out, void *stream) {
+    ENTER(ctx);
+    EMPTY_OK(n);
+    REQUIRE(band && out && n >= 0, "pb200_scale_offset: bad argument");
+    if (n == 0) return 0;
+    // Python-float scalars are "weak" in numpy: both are rounded to float32 before the float32 array operation
+    scale_offset_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(band, invalid, out, n, (float)scale, (float)offset);
+    LEAVE();
+}
+
 extern "C" int pb200_shadow(pb200_ctx *ctx, const float *dem, int rows, int cols, double sun_azimuth,
                             double sun_elevation, const double *terms, const pb200_params *params, uint8_t *out,
                             void *stream) {

@@ -46,6 +46,9 @@ namespace pb200 {
 #ifndef PB200_FT_PRODUCER_WARP
 #define PB200_FT_PRODUCER_WARP 0   // DEM requests by thread 0 (0) or by warp 0 with lane 0 issuing (1)
 #endif
+#ifndef PB200_FT_LATE_REQUEST
+#define PB200_FT_LATE_REQUEST 1    // request the DEM tile of item k + 1 in the middle of item k instead of at its top
+#endif
 #ifndef PB200_FT_XITEM_PREFETCH
 #define PB200_FT_XITEM_PREFETCH 1  // request the first row of the next item in the last row of the current one
 #endif
@@ -331,7 +334,9 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
         const uint32_t buf = k & 1u;
         if (has_dem && (PB200_FT_PRODUCER_WARP ? warp == 0 : tid == 0)) {
             if (fresh_tile) request_dem(k, item, padx);
+#if !PB200_FT_LATE_REQUEST
             if (next.tile == cur_tile) request_dem(k + 1u, next, padx);
+#endif
         }
         const bool want_shad = OPTIONAL_LAYERS && s.tile.shad != nullptr;
         // the four graded layers present: one test instead of four in the row loop
@@ -477,6 +482,12 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                 }
 
                 if (has_counters) acc_nno = __dp4a(oc4, 0x01010101u, acc_nno);   // D:5105; no shoreline: 1 per pixel (D:5107)
+#if PB200_FT_LATE_REQUEST
+                // DEM tile of the next item: requested after this thread's second row, when the other warps have
+                // normally left item k - 1 (requested at the top of the item, thread 0 spent half its time waiting
+                // for the slowest of them, profiles/)
+                if (tid == 0 && has_dem && rr == min(1, nrows - 1) && next.tile == cur_tile) request_dem(k + 1u, next, padx);
+#endif
                 if (rr + 1 < nrows) {
                     FT_LOAD_ROW(pix + (uint32_t)W);
                 } else if (PB200_FT_XITEM_PREFETCH && next.tile == cur_tile) {

@@ -469,6 +469,32 @@ __global__ void collapse_kernel(const uint8_t *__restrict__ in, uint8_t *__restr
     PB200_GRID_STRIDE(i, n) { out[i] = (uint8_t)collapse_class(in[i]); }
 }
 
+// D:3057-3129 (browse relabel) and any other byte -> byte relabel: table by value in the constant bank
+struct ByteTable { uint8_t v[256]; };
+__global__ void byte_table_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, long long n,
+                                  const __grid_constant__ ByteTable T) {
+    __shared__ uint8_t lut[256];
+    if (threadIdx.x < 256) lut[threadIdx.x] = T.v[threadIdx.x];
+    __syncthreads();
+    const long long n4 = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 3) ? 0 : n / 4;
+    PB200_GRID_STRIDE(i, n4) {
+        const uint32_t x = ldg_stream_u32(in + 4 * i);
+        const uint32_t y = lut[x & 255u] | (lut[(x >> 8) & 255u] << 8) | (lut[(x >> 16) & 255u] << 16) | (lut[x >> 24] << 24);
+        stg_stream_u32(out + 4 * i, y);
+    }
+    for (long long i = 4 * n4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = lut[in[i]];
+}
+
+// D:2301-2302, D:3024-3036: float32 scale * (float32(x) - offset), NaN on invalid pixels
+__global__ void scale_offset_kernel(const int16_t *__restrict__ in, const uint8_t *__restrict__ invalid,
+                                    float *__restrict__ out, long long n, float scale, float offset) {
+    PB200_GRID_STRIDE(i, n) {
+        const float v = __fmul_rn(scale, __fsub_rn((float)in[i], offset));
+        out[i] = (invalid && invalid[i]) ? __int_as_float(0x7fc00000) : v;
+    }
+}
+
 // D:4215-4283 over a whole DEM incl. np.gradient's one-sided border differences
 __global__ void shadow_kernel(const float *__restrict__ dem, int rows, int cols, uint8_t *__restrict__ out,
                               SunTerms S, const __grid_constant__ DevParams P) {

@@ -50,6 +50,7 @@ REPLACED_FUNCTIONS = (
     '_add_snow_to_cloud_layer', '_apply_cloud_masking',
     '_get_binary_water_layer', '_get_confidence_layer',
     '_collapse_wtr_classes', '_compute_opera_shadow_layer',
+    '_compute_browse_array',
 )
 
 
@@ -77,7 +78,7 @@ def _to_device(a, dtype, name):
 def _empty_like_device(shape, dtype):
     torch = _torch()
     tdt = {np.dtype(np.uint8): torch.uint8, np.dtype(np.uint16): torch.int16,
-           np.dtype(np.int16): torch.int16}[np.dtype(dtype)]
+           np.dtype(np.int16): torch.int16, np.dtype(np.float32): torch.float32}[np.dtype(dtype)]
     return torch.empty(tuple(shape), dtype=tdt, device='cuda')
 
 
@@ -357,6 +358,51 @@ def landcover_aggregate(worldcover_array_up_3, copernicus_landcover_array,
         (C.c_uint8 * 256)(*[int(v) for v in table]), int(year) - 2000, (C.c_int32 * 4)(*th),
         out.data_ptr(), _stream()))
     return _to_host(out, np.uint8)
+
+
+# ---------------------------------------------------------------------------
+# D:3057-3129 browse relabel; D:2301-2302 / D:3024-3036 offset and scale
+# ---------------------------------------------------------------------------
+def _compute_browse_array(masked_interpreted_water_layer, flag_collapse_wtr_classes=True,
+                          exclude_psw_aggressive=False, set_not_water_to_nodata=False,
+                          set_cloud_to_nodata=False, set_snow_to_nodata=False,
+                          set_ocean_masked_to_nodata=True):
+    """Same signature and result as the reference function: a fresh uint8 array."""
+    ctx = get_context()
+    table = (C.c_uint8 * 256)()
+    _lib.check(ctx._lib.pb200_browse_table(
+        int(bool(flag_collapse_wtr_classes)), int(bool(exclude_psw_aggressive)),
+        int(bool(set_not_water_to_nodata)), int(bool(set_cloud_to_nodata)),
+        int(bool(set_snow_to_nodata)), int(bool(set_ocean_masked_to_nodata)), table))
+    w = _to_device(masked_interpreted_water_layer, np.uint8, 'masked_interpreted_water_layer')
+    out = _empty_like_device(w.shape, np.uint8)
+    _lib.check(ctx._lib.pb200_byte_table(
+        ctx.handle, w.data_ptr(), int(w.numel()), table, out.data_ptr(), _stream()))
+    return _to_host(out, np.uint8)
+
+
+def scale_and_offset_band(image, scale_factor, offset, invalid_ind=None):
+    """``scale_factor * (np.asarray(image, dtype=np.float32) - offset)`` (D:2301-2302, D:3024-3031) for an
+    int16 band, with ``invalid_ind`` (the ``np.where`` tuple of D:5040, or the bool raster it came from) set to NaN
+    (D:3033-3036).  The
+    reference has these statements inline in ``_load_hls_band_from_file`` and ``_save_output_rgb_file``."""
+    ctx = get_context()
+    x = _to_device(image, np.int16, 'image')
+    inv = None
+    if invalid_ind is not None:
+        if isinstance(invalid_ind, tuple):            # the np.where(...) tuple of D:5040
+            inv_np = np.zeros(tuple(x.shape), dtype=np.bool_)
+            inv_np[invalid_ind] = True
+        else:
+            inv_np = np.asarray(invalid_ind)
+        if inv_np.dtype != np.bool_ or inv_np.shape != tuple(x.shape):
+            raise NotImplementedError('invalid_ind: a bool raster of the band\'s shape or an np.where tuple')
+        inv = _to_device(inv_np.view(np.uint8), np.uint8, 'invalid_ind')
+    out = _empty_like_device(x.shape, np.float32)
+    _lib.check(ctx._lib.pb200_scale_offset(
+        ctx.handle, x.data_ptr(), int(x.numel()), float(scale_factor), float(offset),
+        inv.data_ptr() if inv is not None else None, out.data_ptr(), _stream()))
+    return _to_host(out, np.float32)
 
 
 def _crop_2d_array_all_sides(input_2d_array, margin):

@@ -423,3 +423,26 @@ def test_float32_diagnostic_tests_match_reference_fixture(pb):
     with np.errstate(all='ignore'):
         ref = O.compute_diagnostic_tests(*bands, O.default_thresholds())
     assert np.array_equal(G._compute_diagnostic_tests(*bands, G.HlsThresholds()), ref)
+
+
+def test_browse_relabel_and_scaling(pb):
+    """_compute_browse_array (all flag combinations, odd sizes) and the float32
+    offset-and-scale of the reflectance bands."""
+    import itertools
+    import proteus_b200.dswx_hls as G
+    rng = np.random.default_rng(21)
+    w = rng.integers(0, 256, (37, 53), dtype=np.uint8)
+    w[rng.random(w.shape) < 0.7] = 3
+    for flags in itertools.product([False, True], repeat=6):
+        got = G._compute_browse_array(w, *flags)
+        assert got.dtype == np.uint8 and np.array_equal(got, O.compute_browse_array(w, *flags)), flags
+    big = rng.integers(0, 5, (512, 1024), dtype=np.uint8)
+    assert np.array_equal(G._compute_browse_array(big), O.compute_browse_array(big))
+    assert G._compute_browse_array(np.zeros((0, 4), np.uint8)).shape == (0, 4)
+    x = np.arange(-32768, 32768, dtype=np.int16).reshape(256, 256)
+    inv = rng.random(x.shape) < 0.05
+    for scale, offset in ((0.0001, -0.01), (2.75e-5, 123.5), (1.0, 0.0)):
+        for invalid in (None, inv, np.where(inv)):
+            got = G.scale_and_offset_band(x, scale, offset, invalid)
+            ref = O.scale_and_offset_band(x, scale, offset, inv if invalid is not None else None)
+            assert got.dtype == np.float32 and np.array_equal(got, ref, equal_nan=True)

@@ -143,3 +143,26 @@ def test_float32_diagnostic_tests_match_reference_fixture():
         for key in ('scaled', 'dn'):
             got = O.compute_diagnostic_tests(*[z[f'{key}{k}'] for k in range(6)], th)
             assert np.array_equal(got, z[f'diag_{key}']), key
+
+
+def test_browse_relabel_and_scaling_restatements():
+    """SURVEY 8f next #4 (D:3057-3129, D:3024-3036): all 64 flag combinations on every byte value; the float32
+    offset-and-scale expression on the full int16 range.  (Live-reference comparison: test_oracle_vs_reference.py.)"""
+    import itertools
+    allv = np.arange(256, dtype=np.uint8).reshape(16, 16)
+    for flags in itertools.product([False, True], repeat=6):
+        b = O.compute_browse_array(allv, *flags)
+        collapse, no_agg, nw, cl, sn, oc = flags
+        exp = allv.copy()
+        if no_agg:
+            exp[exp == 4] = 0
+        if collapse:
+            exp = O.collapse_wtr_classes(exp)
+        for on, v in ((nw, 0), (cl, 253), (sn, 252), (oc, 254)):
+            if on:
+                exp[exp == v] = 255
+        assert np.array_equal(b, exp) and b.dtype == np.uint8
+    x = np.arange(-32768, 32768, dtype=np.int16)
+    out = O.scale_and_offset_band(x, 0.0001, -0.01)
+    assert out.dtype == np.float32
+    assert np.array_equal(out, np.float32(0.0001) * (x.astype(np.float32) - np.float32(-0.01)))

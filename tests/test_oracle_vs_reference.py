@@ -86,3 +86,20 @@ def test_landcover_tail_against_live_reference():
         assert np.array_equal(O.landcover_aggregate(wc, cop, forest, year - 2000, mt), live)
     assert np.array_equal(O.landcover_aggregate(wc, cop, None, 21),
                           ref_import.live_create_landcover_mask(wc, cop, None, 2021))
+
+
+def test_browse_and_rgb_scaling_against_live_reference(ref):
+    import itertools
+    rng = np.random.default_rng(5)
+    w = np.array([0, 1, 2, 3, 4, 252, 253, 254, 255, 7, 100], np.uint8)[rng.integers(0, 11, (48, 64))]
+    for flags in itertools.product([False, True], repeat=6):
+        assert np.array_equal(O.compute_browse_array(w, *flags), ref._compute_browse_array(w, *flags)), flags
+    bands = [rng.integers(-2000, 12000, (40, 50)).astype(np.int16) for _ in range(3)]
+    inv = rng.random((40, 50)) < 0.1
+    off = dict(red=-0.01, green=0.0, blue=123.5, swir1=0.25, nir=-3.0)
+    sc = dict(red=1e-4, green=0.0001, blue=2.75e-5, swir1=1e-4, nir=0.5)
+    for infrared in (False, True):
+        out = ref_import.live_save_output_rgb(bands[0], bands[1], bands[2], off, sc, np.where(inv), infrared)
+        keys = ('swir1', 'nir', 'red') if infrared else ('red', 'green', 'blue')
+        for a, band, kk in zip(out, bands, keys):
+            assert np.array_equal(a, O.scale_and_offset_band(band, sc[kk], off[kk], inv), equal_nan=True), kk
