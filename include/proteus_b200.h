@@ -47,8 +47,8 @@ extern "C" {
 /* mask_adjacent_to_cloud_mode (D:1929-1935) */
 #define PB200_ADJ_MASK   0
 #define PB200_ADJ_IGNORE 1
-#define PB200_ADJ_COVER  2   /* only pb200_preliminary_cloud / pb200_snow_to_cloud accept it
-                                (the dilation itself is SURVEY 8f "next #2") */
+#define PB200_ADJ_COVER  2   /* D:2055-2078: pb200_snow_to_cloud_cover + pb200_masked_dilation; the fused
+                                entry points run it as fused pass (defer_snow) -> dilations -> final pass */
 
 /* counters slot layout (uint64 each) */
 #define PB200_CNT_VALID           0  /* D:5110  n_valid                     */
