@@ -446,3 +446,31 @@ def test_browse_relabel_and_scaling(pb):
             got = G.scale_and_offset_band(x, scale, offset, invalid)
             ref = O.scale_and_offset_band(x, scale, offset, inv if invalid is not None else None)
             assert got.dtype == np.float32 and np.array_equal(got, ref, equal_nan=True)
+
+
+def test_batch_of_mixed_tiles_through_the_item_pipeline(pb):
+    """The fast kernel's item pipeline (double-buffered DEM tile, full/empty barriers, row requests across items)
+    on a batch whose tiles differ in size and in which rasters they carry: tiles with and without DEM alternate,
+    some tiles are smaller than one item, some make a CTA change tile after every item.  Both kernel variants
+    (graded layers only / all layers), two launches of the same plan."""
+    import torch
+    specs = [(21, 256, 384, {}), (22, 128, 132, dict(with_dem=False)), (23, 512, 640, dict(adversarial=True)),
+             (24, 32, 128, dict(with_land=False, with_ocean=False)), (25, 300, 260, dict(with_dem=False, with_land=False)),
+             (26, 64, 1028, {}), (27, 4, 4, {}), (28, 700, 128, dict(adversarial=True))]
+    tiles, refs = [], []
+    for seed, h, w, kw in specs:
+        t = synth.make_tile(seed, h, w, **kw)
+        refs.append(O.reference_chain(t['bands'], t['fmask'], t['dem'], t['land'], t['ocean'],
+                                      t['sun_azimuth'], t['sun_elevation']))
+        dev = {k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) else v) for k, v in t.items() if k != 'bands'}
+        dev['bands'] = [torch.from_numpy(b).cuda() for b in t['bands']]
+        tiles.append(dev)
+    for layers, names in ((pb.GRADED_LAYERS, ('DIAG', 'WTR', 'BWTR', 'CONF')), (pb.ALL_LAYERS, FUSED_LAYERS)):
+        plan = pb.Plan(tiles, pb.make_params(collapse_wtr_classes=False), layers)
+        for launch in range(2):
+            plan.zero_counters()
+            plan.run()
+            for i, ref in enumerate(refs):
+                res = plan.results(i)
+                _assert_layers(res, ref, names, f'tile {i} launch {launch} {len(layers)} layers')
+                assert np.array_equal(res['counters'][:3], ref['counters']), (i, launch)
