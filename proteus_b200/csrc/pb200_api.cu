@@ -334,7 +334,9 @@ static void build_fused_tables(const pb200_params *p, const DevParams &D, FusedT
         const bool valid = (idx >> 5) & 1u, not_ocean = (idx >> 6) & 1u;
         const uint32_t rep = valid ? (D.diag_lut[d] & 0xffffu) : 65535u;                 // D:5227, D:5231
         const uint32_t k1 = !valid ? 7u : (!not_ocean ? 6u : (D.diag_lut[d] >> 16));     // D:5229, 5245, 5249
-        T->diag_lut[idx] = rep | ((k1 << 8) << 16);
+        // k1 at bits 8-10 of the fk_lut index, and again at bits 2-4: XORed into the index it spreads the classes
+        // of neighbouring pixels over the shared-memory banks (FK_SWIZZLE in pb200_fused.cuh)
+        T->diag_lut[idx] = rep | (((k1 << 8) | (k1 << 2)) << 16);
     }
     for (uint32_t v = 0; v < 256; ++v) T->land_lut[v] = (uint8_t)land_category(v);
     const bool aerosol_on = p->apply_aerosol_class_remapping != 0;
@@ -346,7 +348,7 @@ static void build_fused_tables(const pb200_params *p, const DevParams &D, FusedT
         const uint32_t kb = remap ? 1u : k1;
         const uint32_t c = cprelim | (remap ? 8u : 0u) | (snow << 1);                    // D:1246, D:2081
         const uint32_t water = (kb >= 1u && kb <= 4u) ? 0x80u : 0u;                       // can be masked by terrain shadow
-        T->fk_lut[idx] = (uint8_t)(kb | (c << 3) | water);
+        T->fk_lut[idx ^ (k1 << 2)] = (uint8_t)(kb | (c << 3) | water);
     }
     for (uint32_t idx = 0; idx < 128; ++idx)
         T->kill_lut[idx] = (uint8_t)kill_class(idx & 7u, (idx >> 3) & 1u, (idx >> 4) & 1u, (idx >> 5) & 3u);
@@ -363,7 +365,8 @@ static void build_fused_tables(const pb200_params *p, const DevParams &D, FusedT
         const uint32_t wtr = cloud_masking(w2, c);                                       // uncollapsed WTR class
         const uint32_t bin = wtr < 5u ? wtr : wtr - 247u;                                // 252..255 -> 5..8
         uint32_t flags = (valid ? 1u : 0u) | (cv ? 2u : 0u) | (k2_lit != k2_dark ? 4u : 0u) | (bin << 4);
-        T->big_lut[idx] = out | (flags << 24);
+        // physical slot: "shadowed" and "bright" also flip bits 3 and 4 (the kernel XORs 0x208 / 0x410 in)
+        T->big_lut[idx ^ (shadowed ? (BIG_SHADOWED & 31u) : 0u) ^ (bright ? (BIG_BRIGHT & 31u) : 0u)] = out | (flags << 24);
     }
 }
 

@@ -49,6 +49,9 @@ namespace pb200 {
 #ifndef PB200_FT_LATE_REQUEST
 #define PB200_FT_LATE_REQUEST 1    // request the DEM tile of item k + 1 in the middle of item k instead of at its top
 #endif
+#ifndef PB200_FT_PATCH_SLOW
+#define PB200_FT_PATCH_SLOW 1      // evaluate the packed fast path unconditionally and patch wrapped pairs afterwards
+#endif
 #ifndef PB200_FT_XITEM_PREFETCH
 #define PB200_FT_XITEM_PREFETCH 1  // request the first row of the next item in the last row of the current one
 #endif
@@ -71,6 +74,15 @@ enum : uint32_t { LC_NONE = 0, LC_WATER = 1, LC_EVERGREEN_OR_LOW = 2, LC_HIGH = 
 // flags byte (bits 24..31) of a big_lut entry
 enum : uint32_t { FL_VALID = 1u << 24, FL_CLOUD_VALID = 1u << 25, FL_SHADOW_SENSITIVE = 1u << 26, FL_BIN_SHIFT = 28 };
 
+// big_lut index: kb | c<<3 | cat<<7 | shadowed<<9 | bright<<10, with "shadowed" and "bright" also XORed into bits 3
+// and 4 and (fk_lut) the class k1 XORed into bits 2-4 of fmask | k1<<8 | nle<<11: the bits that differ between
+// neighbouring pixels then select the bank, the bits that are spatially coherent select the row (44 % of the
+// shared wavefronts were bank-conflict replays before, profiles/).  XOR with a function of the upper bits is a
+// bijection, the host builds the tables in the same order.
+#ifndef PB200_FT_SWIZZLE_BRIGHT
+#define PB200_FT_SWIZZLE_BRIGHT 0   // measured: the extra IMAD per pair costs what the fewer bank conflicts give
+#endif
+constexpr uint32_t BIG_SHADOWED = 0x208u, BIG_BRIGHT = PB200_FT_SWIZZLE_BRIGHT ? 0x410u : 0x400u;
 struct FusedTables {               // built on the host per plan, global memory
     uint32_t big_lut[2048];        // [kb | c<<3 | cat<<7 | shadowed<<9 | bright<<10] -> WTR | BWTR<<8 | CONF<<16 | flags<<24
     uint32_t diag_lut[128];        // [code | valid<<5 | not_ocean<<6] -> DIAG value | (k1<<8)<<16
@@ -155,7 +167,7 @@ __device__ __forceinline__ uint32_t shadow_fast(float l, float r, float u, float
     const bool is_shadow = (diff < -e) && (D < -eg);
     const bool not_shadow = (diff > e) || ((D > eg) && (L < 0.99999f * v));
     *undecided = *undecided || !(is_shadow || not_shadow);
-    return is_shadow ? 0x200u : 0u;
+    return is_shadow ? BIG_SHADOWED : 0u;
 }
 
 // Shared-memory reads through an explicit 32-bit shared address: the base is computed once per thread
@@ -206,7 +218,7 @@ __device__ __noinline__ uint32_t shadow_exact(float l, float r, float u, float d
     S.sx = T.sx; S.sy = T.sy; S.sz = T.sz; S.sin_az = T.sin_az; S.cos_az = T.cos_az;
     const float g_col = __fmul_rn(__fsub_rn(r, l), 0.5f);                     // D:4255
     const float g_row = __fmul_rn(__fsub_rn(d, u), 0.5f);
-    return shadow_from_gradient(g_col, g_row, P.dxf, P.dyf, S, P.cos_thr, P.tan_thr) ? 0u : 0x200u;
+    return shadow_from_gradient(g_col, g_row, P.dxf, P.dyf, S, P.cos_thr, P.tan_thr) ? 0u : BIG_SHADOWED;
 }
 
 // ---------------------------------------------------------------------------
@@ -413,10 +425,20 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                     const uint32_t tb = __vadd2(N, F.m_lc);                   // sign <=> !(nir > lcmask)  (D:1354)
                     // fmask value | (nir <= 1000) << 11, and bright << 10, per half
                     const uint32_t fa = fmh | ((tn >> 4) & 0x08000800u);
+#if PB200_FT_SWIZZLE_BRIGHT
+                    const uint32_t brp = ((~tb >> 15) & 0x00010001u) * BIG_BRIGHT;   // per half: index bit 10 and bank bit 4
+#else
                     const uint32_t brp = (~tb >> 5) & 0x04000400u;
+#endif
 
                     uint32_t dcode[2];
+#if PB200_FT_PATCH_SLOW
+                    // the packed evaluation runs unconditionally (straight-line code the scheduler can interleave
+                    // with the look-ups of the previous pair); a pair with a wrapped sum is re-evaluated afterwards
+                    {
+#else
                     if (!slow) {
+#endif
                         bool p2h, p2l;
                         (void)__vibmax_s16x2(ns, gr, &p2h, &p2l);             // pred = mbsrn >= mbsrv: test 2 is its negation
 #pragma unroll
@@ -456,7 +478,12 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                             d = __funnelshift_l((uint32_t)x0w, d, 1);
                             dcode[hh] = d;
                         }
-                    } else {
+                    }
+#if PB200_FT_PATCH_SLOW
+                    if (slow) {
+#else
+                    else {
+#endif
                         const uint32_t dd = diag_pair_slow(B, G, R, N, S1, S2, P);
                         dcode[0] = (dd & 31u) | ((comb & 3u) << 5);
                         dcode[1] = (dd >> 8) | ((comb >> 16) << 5);
@@ -469,12 +496,12 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                         const bool hi = hh;
                         const int j = 2 * p + hh;
                         dl[hh] = lds_tab32(sb + FS_OFF(diag_lut) + 4u * dcode[hh]);   // D:5227-5231, 5245, 5249
-                        const uint32_t k1s = dl[hh] >> 16;                    // k1 << 8
-                        const uint32_t fi = hi ? ((fa >> 16) | k1s) : ((fa & 0xffffu) | k1s);
+                        const uint32_t k1s = dl[hh] >> 16;                    // k1 << 8 | k1 << 2 (bank swizzle)
+                        const uint32_t fi = hi ? ((fa >> 16) ^ k1s) : ((fa & 0xffffu) ^ k1s);
                         const uint32_t ev = lds_tab8(sb + FS_OFF(fk_lut) + fi);       // D:1237-1246, 1984-1991, 2081
                         const uint32_t cat = lds_tab8(sb + FS_OFF(land_lut) + ((ld4 >> (8 * j)) & 255u));
                         const uint32_t bri = hi ? (brp >> 16) : (brp & 0xffffu);
-                        idx[j] = ((ev & 0x7Fu) | bri) + (cat << 7);
+                        idx[j] = ((ev & 0x7Fu) ^ bri) + (cat << 7);          // bits 7-8 are still clear: the sum is an OR
                         water_any |= ev;                                      // bit 7: the pixel holds a water class
                     }
                     dgw[p] = __byte_perm(dl[0], dl[1], 0x5410);               // two DIAG values
@@ -501,7 +528,7 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
 
                 // ---- terrain shadow: only where it can change the result ----------------
                 // (bit 7 of a fk_lut byte = the pixel holds a water class: only those can be masked, D:1340-1343)
-                uint32_t shw[4] = {0u, 0u, 0u, 0u};                           // 0x200 = in shadow
+                uint32_t shw[4] = {0u, 0u, 0u, 0u};                           // BIG_SHADOWED = in shadow
                 if (has_dem && (want_shad || (water_any & 0x80u))) {
                     if (!dem_ready) {
                         mbar_wait(&s.full[buf], (fstate >> buf) & 1u);
@@ -546,7 +573,7 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                 // ---- final look-up (D:1331-1376, 2084-2131, 1727, 1793-1835) ------------------
                 uint32_t o[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) o[j] = lds_tab32(sb + FS_OFF(big_lut) + 4u * (idx[j] | shw[j]));
+                for (int j = 0; j < 4; ++j) o[j] = lds_tab32(sb + FS_OFF(big_lut) + 4u * (idx[j] ^ shw[j]));
 
                 // ---- pack and store -------------------------------------------------------
                 const uint32_t t01a = __byte_perm(o[0], o[1], 0x5140);
@@ -575,7 +602,9 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                     uint32_t sel1r = 0, sel2 = 0, c4 = 0, s4 = 0;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const uint32_t kb = idx[j] & 7u, c = (idx[j] >> 3) & 15u;
+                        // undo the bank swizzle of "bright" (index bit 10 also flipped bit 4 = bit 1 of c)
+                        const uint32_t kb = idx[j] & 7u,
+                                       c = ((idx[j] >> 3) & 15u) ^ (PB200_FT_SWIZZLE_BRIGHT ? ((idx[j] >> 9) & 2u) : 0u);
                         const uint32_t shb = shw[j] >> 9;
                         // kill_lut index: kb | shadowed<<3 | bright<<4 | cat<<5  (bright = idx bit 10, cat = idx bits 7-8)
                         const uint32_t k2 = s.kill_lut[kb | (shb << 3) | ((idx[j] >> 6) & 0x10u) | ((idx[j] >> 2) & 0x60u)];
