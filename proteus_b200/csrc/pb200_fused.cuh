@@ -205,12 +205,13 @@ __device__ __forceinline__ T *plane_at(T *base, uint32_t pix) {
 }
 
 // Rare paths kept out of line so that the hot loop stays small.
-__device__ __noinline__ uint32_t diag_pair_slow(uint32_t B, uint32_t G, uint32_t R, uint32_t N, uint32_t S1,
-                                                uint32_t S2, const DevParams &P) {
-    // some int16 sum of this pair wrapped: per-pixel evaluation with sign normalisation (D:1872-1914)
-    const uint32_t lo = diagnostic_tests<false>(sext_lo(B), sext_lo(G), sext_lo(R), sext_lo(N), sext_lo(S1), sext_lo(S2), P);
-    const uint32_t hi = diagnostic_tests<false>(sext_hi(B), sext_hi(G), sext_hi(R), sext_hi(N), sext_hi(S1), sext_hi(S2), P);
-    return lo | (hi << 8);
+__device__ __noinline__ uint32_t diag_pixel_slow(uint32_t B, uint32_t G, uint32_t R, uint32_t N, uint32_t S1,
+                                                 uint32_t S2, uint32_t hi, const DevParams &P) {
+    // some int16 sum of this pixel wrapped: scalar evaluation with sign normalisation (D:1872-1914); hi selects
+    // the pixel of the pair
+    const uint32_t sh = hi ? 16u : 0u;
+    return diagnostic_tests<false>((int)(short)(B >> sh), (int)(short)(G >> sh), (int)(short)(R >> sh),
+                                   (int)(short)(N >> sh), (int)(short)(S1 >> sh), (int)(short)(S2 >> sh), P);
 }
 __device__ __noinline__ uint32_t shadow_exact(float l, float r, float u, float d, const DevParams &P,
                                               const TileDev &T) {
@@ -484,9 +485,15 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
 #else
                     else {
 #endif
-                        const uint32_t dd = diag_pair_slow(B, G, R, N, S1, S2, P);
-                        dcode[0] = (dd & 31u) | ((comb & 3u) << 5);
-                        dcode[1] = (dd >> 8) | ((comb >> 16) << 5);
+#if PB200_FT_PATCH_SLOW
+                        // only the pixel whose sums wrapped (usually one of the two)
+                        const uint32_t wr = (gs | gr | ns | nrs) & 0x80008000u;
+                        if (wr & 0x8000u) dcode[0] = diag_pixel_slow(B, G, R, N, S1, S2, 0u, P) | ((comb & 3u) << 5);
+                        if (wr >> 31) dcode[1] = diag_pixel_slow(B, G, R, N, S1, S2, 1u, P) | ((comb >> 16) << 5);
+#else
+                        dcode[0] = diag_pixel_slow(B, G, R, N, S1, S2, 0u, P) | ((comb & 3u) << 5);
+                        dcode[1] = diag_pixel_slow(B, G, R, N, S1, S2, 1u, P) | ((comb >> 16) << 5);
+#endif
                     }
 
                     // ================= per pixel: tables ================================
