@@ -9,9 +9,11 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <mutex>
@@ -902,7 +904,29 @@ extern "C" int pb200_classify_host(pb200_ctx *ctx, const pb200_tile *ht, const p
     HostPipe &p = ctx->pipe;
     int rc = pipe_reserve(p, px, dem_elems);
     if (rc) return rc;
-    const int n_strips = (H + strip_rows - 1) / strip_rows;
+    // PB200_PIPE_TRACE=1: print where the time of this call went (host stages, H2D / kernel / D2H spans)
+    static const bool trace = std::getenv("PB200_PIPE_TRACE") != nullptr;
+    const auto t_enter = std::chrono::steady_clock::now();
+    auto ms_since = [&](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
+    cudaEvent_t tr[4] = {};
+    if (trace)
+        for (auto &e : tr) CK(cudaEventCreate(&e));
+    // strip boundaries: strip_rows each, the tail of the raster in shorter strips (down to 8 * TH rows) so that the
+    // kernel + D2H of the last strip - the only part of the pipeline that nothing overlaps - stays short
+    std::vector<int> edge;
+    edge.push_back(0);
+    for (int r = strip_rows; r < H; r += strip_rows) edge.push_back(r);
+    edge.push_back(H);
+    for (int min_rows = 8 * TH; ; ) {
+        const int n = (int)edge.size(), last = edge[n - 1] - edge[n - 2];
+        if (last <= min_rows + TH) break;
+        int cut = edge[n - 2] + ((last / 2 + TH - 1) / TH) * TH;
+        if (cut >= H) break;
+        edge.insert(edge.end() - 1, cut);
+    }
+    const int n_strips = (int)edge.size() - 1;
     while ((int)p.ev_in.size() < n_strips) {
         cudaEvent_t e;
         CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -910,6 +934,38 @@ extern "C" int pb200_classify_host(pb200_ctx *ctx, const pb200_tile *ht, const p
         CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         p.ev_k.push_back(e);
     }
+    DevParams P;
+    rc = derive_params(params, &P, true);             // argument checks before anything is in flight
+    if (rc) return rc;
+    // ---- H2D of every strip first: the copy engine starts while the host still builds tables and plan ----------
+    if (trace) { CK(cudaEventRecord(tr[0], p.s_in)); }
+    {
+        int dem_copied = 0;                 // DEM rows [.., dem_copied) are on the device
+        bool first_dem = true;
+        for (int sidx = 0; sidx < n_strips; ++sidx) {
+            const int r0 = edge[sidx], r1 = edge[sidx + 1], nr = r1 - r0;
+            const size_t off = (size_t)r0 * W, cnt = (size_t)nr * W;
+            for (int k = 0; k < 6; ++k)
+                CK(cudaMemcpyAsync(p.band[k] + off, ht->band[k] + off, cnt * 2, cudaMemcpyHostToDevice, p.s_in));
+            CK(cudaMemcpyAsync(p.fmask + off, ht->fmask + off, cnt, cudaMemcpyHostToDevice, p.s_in));
+            if (ht->land) CK(cudaMemcpyAsync(p.land + off, ht->land + off, cnt, cudaMemcpyHostToDevice, p.s_in));
+            if (ht->ocean) CK(cudaMemcpyAsync(p.ocean + off, ht->ocean + off, cnt, cudaMemcpyHostToDevice, p.s_in));
+            if (ht->dem) {
+                int d0 = ht->dem_off_y + r0 - 1, d1 = ht->dem_off_y + r1 + 1;     // rows the strip's stencil reads
+                if (!first_dem) d0 = std::max(d0, dem_copied);
+                d0 = std::max(d0, 0);
+                d1 = std::min(d1, ht->dem_rows);
+                if (d1 > d0)
+                    CK(cudaMemcpyAsync(p.dem + (size_t)d0 * ht->dem_pitch, ht->dem + (size_t)d0 * ht->dem_pitch,
+                                       (size_t)(d1 - d0) * ht->dem_pitch * 4, cudaMemcpyHostToDevice, p.s_in));
+                dem_copied = std::max(dem_copied, d1);
+                first_dem = false;
+            }
+            CK(cudaEventRecord(p.ev_in[sidx], p.s_in));
+        }
+        if (trace) { CK(cudaEventRecord(tr[1], p.s_in)); }
+    }
+    const double ms_h2d_enqueued = ms_since(t_enter);
     // validate once with a whole-tile descriptor on the device mirror
     pb200_tile dt = *ht;
     for (int k = 0; k < 6; ++k) dt.band[k] = p.band[k];
@@ -922,9 +978,6 @@ extern "C" int pb200_classify_host(pb200_ctx *ctx, const pb200_tile *ht, const p
     uint8_t **dev_u8_field[8] = {&dt.wtr1, &dt.wtr1_remapped, &dt.wtr2, &dt.cloud, &dt.shad, &dt.wtr, &dt.bwtr, &dt.conf};
     for (int i = 0; i < 8; ++i) *dev_u8_field[i] = host_u8[i] ? p.u8out[i] : nullptr;
     dt.counters = (uint64_t *)p.counters;             // always counted on the device (lean kernel variant); copied back on request
-    DevParams P;
-    rc = derive_params(params, &P, true);
-    if (rc) return rc;
     if (dt.counters) CK(cudaMemsetAsync(p.counters, 0, PB200_N_COUNTERS * sizeof(unsigned long long), p.s_k));
     {
         FusedTables T;
@@ -936,7 +989,7 @@ extern "C" int pb200_classify_host(pb200_ctx *ctx, const pb200_tile *ht, const p
     // loop the host only enqueues asynchronous work and never waits for the GPU
     std::vector<pb200_tile> strips(n_strips);
     for (int sidx = 0; sidx < n_strips; ++sidx) {
-        const int r0 = sidx * strip_rows, r1 = std::min(H, r0 + strip_rows);
+        const int r0 = edge[sidx], r1 = edge[sidx + 1];
         const size_t off = (size_t)r0 * W;
         pb200_tile &st = strips[sidx];
         st = dt;
@@ -968,31 +1021,16 @@ extern "C" int pb200_classify_host(pb200_ctx *ctx, const pb200_tile *ht, const p
     }
     pb200_plan plan;
     rc = plan_build(ctx, strips.data(), n_strips, params, &plan, p.s_k, true, p.tables, &p.arena);
-    if (rc) { plan_release(&plan, p.s_k); return rc; }
+    if (rc) {
+        plan_release(&plan, p.s_k);
+        cudaStreamSynchronize(p.s_in);                // the copies read the caller's buffers: none may outlive the call
+        return rc;
+    }
 
-    int dem_copied = 0;                 // DEM rows [.., dem_copied) are on the device
-    bool first_dem = true;
+    const double ms_prologue = ms_since(t_enter);
     for (int sidx = 0; sidx < n_strips; ++sidx) {
-        const int r0 = sidx * strip_rows, r1 = std::min(H, r0 + strip_rows), nr = r1 - r0;
+        const int r0 = edge[sidx], r1 = edge[sidx + 1], nr = r1 - r0;
         const size_t off = (size_t)r0 * W, cnt = (size_t)nr * W;
-        // ---- H2D ------------------------------------------------------------
-        for (int k = 0; k < 6; ++k)
-            CK(cudaMemcpyAsync(p.band[k] + off, ht->band[k] + off, cnt * 2, cudaMemcpyHostToDevice, p.s_in));
-        CK(cudaMemcpyAsync(p.fmask + off, ht->fmask + off, cnt, cudaMemcpyHostToDevice, p.s_in));
-        if (ht->land) CK(cudaMemcpyAsync(p.land + off, ht->land + off, cnt, cudaMemcpyHostToDevice, p.s_in));
-        if (ht->ocean) CK(cudaMemcpyAsync(p.ocean + off, ht->ocean + off, cnt, cudaMemcpyHostToDevice, p.s_in));
-        if (ht->dem) {
-            int d0 = ht->dem_off_y + r0 - 1, d1 = ht->dem_off_y + r1 + 1;     // rows the strip's stencil reads
-            if (!first_dem) d0 = std::max(d0, dem_copied);
-            d0 = std::max(d0, 0);
-            d1 = std::min(d1, ht->dem_rows);
-            if (d1 > d0)
-                CK(cudaMemcpyAsync(p.dem + (size_t)d0 * ht->dem_pitch, ht->dem + (size_t)d0 * ht->dem_pitch,
-                                   (size_t)(d1 - d0) * ht->dem_pitch * 4, cudaMemcpyHostToDevice, p.s_in));
-            dem_copied = d1;
-            first_dem = false;
-        }
-        CK(cudaEventRecord(p.ev_in[sidx], p.s_in));
         // ---- kernel on the strip -------------------------------------------
         CK(cudaStreamWaitEvent(p.s_k, p.ev_in[sidx], 0));
         rc = plan_launch_tile(&plan, sidx, p.s_k);
@@ -1005,12 +1043,25 @@ extern "C" int pb200_classify_host(pb200_ctx *ctx, const pb200_tile *ht, const p
             if (host_u8[i])
                 CK(cudaMemcpyAsync(host_u8[i] + off, p.u8out[i] + off, cnt, cudaMemcpyDeviceToHost, p.s_out));
     }
+    const double ms_enqueued = ms_since(t_enter);
+    if (trace) { CK(cudaEventRecord(tr[2], p.s_k)); }
     plan_release(&plan, p.s_k);
     if (ht->counters)
         CK(cudaMemcpyAsync(ht->counters, p.counters, PB200_N_COUNTERS * sizeof(unsigned long long),
                            cudaMemcpyDeviceToHost, p.s_out));
+    if (trace) { CK(cudaEventRecord(tr[3], p.s_out)); }
     CK(cudaStreamSynchronize(p.s_out));
     CK(cudaStreamSynchronize(p.s_k));
+    if (trace) {
+        float h2d = 0, k_end = 0, out_end = 0;
+        cudaEventElapsedTime(&h2d, tr[0], tr[1]);
+        cudaEventElapsedTime(&k_end, tr[0], tr[2]);
+        cudaEventElapsedTime(&out_end, tr[0], tr[3]);
+        std::fprintf(stderr, "[pb200 pipe] H2D enqueued at %.3f ms, tables + plan ready at %.3f ms, all work enqueued at %.3f ms, "
+                     "call %.3f ms | from first H2D: H2D done %.3f, last kernel done %.3f, last D2H done %.3f ms (%d strips)\n",
+                     ms_h2d_enqueued, ms_prologue, ms_enqueued, ms_since(t_enter), h2d, k_end, out_end, n_strips);
+        for (auto &e : tr) cudaEventDestroy(e);
+    }
     return 0;
 }
 
