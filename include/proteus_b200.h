@@ -259,6 +259,17 @@ int  pb200_byte_table(pb200_ctx *ctx, const uint8_t *in, int64_t n, const uint8_
 int  pb200_scale_offset(pb200_ctx *ctx, const int16_t *band, int64_t n, double scale, double offset,
                         const uint8_t *invalid, float *out, void *stream);
 
+/* SURVEY 8f next #3 - the numpy half of the 'otsu' shadow algorithm, _compute_otsu_threshold (D:1638-1684), for a
+ * uint8 raster (the hillshade GDAL's DEMProcessing writes, D:4206; the hillshade itself is a GDAL file operation and
+ * stays on the host).  pb200_histogram_u8: exact count of every byte value (counts[256], uint64, DEVICE memory,
+ * accumulated into - zero it first; ranks of a mosaic all-reduce these).  pb200_otsu_threshold (host only): numpy's
+ * np.histogram(image, bins=256) binning of those counts and the float64 Otsu arithmetic in numpy's operation order ->
+ * the threshold the reference compares with.  pb200_greater_than_u8: out = image > threshold (bool as uint8). */
+int  pb200_histogram_u8(pb200_ctx *ctx, const uint8_t *image, int64_t n, unsigned long long *counts, void *stream);
+int  pb200_otsu_threshold(const unsigned long long counts[256], int is_normalized, double *threshold);
+int  pb200_greater_than_u8(pb200_ctx *ctx, const uint8_t *image, int64_t n, double threshold, uint8_t *out,
+                           void *stream);
+
 /* ---- helpers exported for tests ---------------------------------------- */
 /* The exact integer form of "float64(n)/float64(d) > t" (is_less = 0) or
  * "< t" (is_less = 1) for int16 n, d:  with p/q = n/d, q > 0,

@@ -441,6 +441,26 @@ def scale_and_offset_band(image, scale_factor, offset, invalid_ind=None):
     return out
 
 
+def otsu_threshold(image, is_normalized=True):
+    """The threshold of _compute_otsu_threshold, dswx_hls.py:1638-1684: 256-bin histogram
+    between the image's extremes, class weights and means by cumulative sums, first maximum of the inter-class
+    variance, bin centre below it."""
+    counts, edges = np.histogram(image, bins=256)                         # :1663
+    h = counts.ravel() / counts.max() if is_normalized else counts        # :1666-1667
+    centres = (edges[:-1] + edges[1:]) / 2.                               # :1670
+    with np.errstate(all='ignore'):
+        w_lo, w_hi = np.cumsum(h), np.cumsum(h[::-1])[::-1]               # :1673-1674
+        mu_lo = np.cumsum(h * centres) / w_lo                             # :1677
+        mu_hi = (np.cumsum((h * centres)[::-1]) / w_hi[::-1])[::-1]       # :1679
+        between = w_lo[:-1] * w_hi[1:] * (mu_lo[:-1] - mu_hi[1:]) ** 2    # :1681
+    return centres[:-1][np.argmax(between)]                               # :1684-1686
+
+
+def compute_otsu_threshold(image, is_normalized=True):
+    """_compute_otsu_threshold: ``image > threshold`` (:1689)."""
+    return image > otsu_threshold(image, is_normalized)
+
+
 def reference_chain(raw_bands, fmask, dem_with_margin=None, landcover=None,
                     ocean_mask=None, sun_azimuth_angle=150.0,
                     sun_elevation_angle=45.0, thresholds=None,

@@ -27,7 +27,8 @@ EXPORTS = (
     'pb200_aerosol_remap', 'pb200_landcover_shadow_masks',
     'pb200_snow_to_cloud', 'pb200_snow_to_cloud_cover', 'pb200_masked_dilation', 'pb200_cloud_masking', 'pb200_binary_water',
     'pb200_confidence', 'pb200_collapse', 'pb200_shadow', 'pb200_landcover_aggregate',
-    'pb200_browse_table', 'pb200_byte_table', 'pb200_scale_offset', 'pb200_ratio_bound',
+    'pb200_browse_table', 'pb200_byte_table', 'pb200_scale_offset',
+    'pb200_histogram_u8', 'pb200_otsu_threshold', 'pb200_greater_than_u8', 'pb200_ratio_bound',
     'pb200_ratio_sweep', 'pb200_angle_thresholds',
 )
 
@@ -144,6 +145,9 @@ def load():
     lib.pb200_browse_table.argtypes = [C.c_int] * 6 + [C.c_uint8 * 256]
     lib.pb200_byte_table.argtypes = [vp, vp, i64, C.c_uint8 * 256, vp, vp]
     lib.pb200_scale_offset.argtypes = [vp, vp, i64, C.c_double, C.c_double, vp, vp, vp]
+    lib.pb200_histogram_u8.argtypes = [vp, vp, i64, vp, vp]
+    lib.pb200_otsu_threshold.argtypes = [C.c_uint64 * 256, C.c_int, C.POINTER(C.c_double)]
+    lib.pb200_greater_than_u8.argtypes = [vp, vp, i64, C.c_double, vp, vp]
     lib.pb200_shadow.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(Params), vp, vp]
     _lib = lib
     return lib

@@ -1349,6 +1349,96 @@ extern "C" int pb200_scale_offset(pb200_ctx *ctx, const int16_t *band, int64_t n
     LEAVE();
 }
 
+extern "C" int pb200_histogram_u8(pb200_ctx *ctx, const uint8_t *image, int64_t n, unsigned long long *counts,
+                                  void *stream) {
+    ENTER(ctx);
+    EMPTY_OK(n);
+    REQUIRE(image && counts && n >= 0, "pb200_histogram_u8: bad argument");
+    if (n == 0) return 0;
+    // a block counts at most 2^32 - 1 pixels per bin: grid-stride over >= 1 block per SM keeps that far away
+    histogram_u8_kernel<<<grid_for(ctx, (n + 3) / 4, 256), 256, 0, st>>>(image, n, counts);
+    LEAVE();
+}
+
+// _compute_otsu_threshold (D:1638-1684) from exact per-value counts, every float64 operation in numpy's order.
+extern "C" int pb200_otsu_threshold(const unsigned long long counts[256], int is_normalized, double *threshold) {
+    if (!counts || !threshold) return fail(PB200_E_INVALID_ARG, "pb200_otsu_threshold: null argument");
+    int vmin = -1, vmax = -1;
+    for (int v = 0; v < 256; ++v)
+        if (counts[v]) { if (vmin < 0) vmin = v; vmax = v; }
+    if (vmin < 0) return fail(PB200_E_INVALID_ARG, "pb200_otsu_threshold: empty image (np.histogram raises ValueError)");
+    constexpr int NB = 256;
+    // np.histogram(image, bins=256): outer edges (min, max), widened by 0.5 when equal; edges = linspace(first, last, 257)
+    double first = (double)vmin, last = (double)vmax;
+    if (vmin == vmax) { first -= 0.5; last += 0.5; }
+    double edges[NB + 1];
+    const double step = (last - first) / (double)NB;
+    for (int i = 0; i <= NB; ++i) edges[i] = (double)i * step + first;
+    edges[NB] = last;
+    // uniform-bin fast path of np.histogram: scaled index, then the two edge corrections
+    long long hist_i[NB] = {};
+    const double norm_denom = last - first;
+    for (int v = vmin; v <= vmax; ++v) {
+        if (!counts[v]) continue;
+        const double a = (double)v;
+        const double f = ((a - first) / norm_denom) * (double)NB;
+        long long idx = (long long)f;
+        if (idx == NB) idx -= 1;
+        if (a < edges[idx]) idx -= 1;
+        if (a >= edges[idx + 1] && idx != NB - 1) idx += 1;
+        hist_i[idx] += (long long)counts[v];
+    }
+    double hist[NB], mids[NB];
+    long long hmax = 0;
+    for (int i = 0; i < NB; ++i) hmax = std::max(hmax, hist_i[i]);
+    for (int i = 0; i < NB; ++i) {
+        hist[i] = is_normalized ? (double)hist_i[i] / (double)hmax : (double)hist_i[i];      // D:1667
+        mids[i] = (edges[i] + edges[i + 1]) / 2.0;                                            // D:1670
+    }
+    // cumulative sums, forward and backward (np.cumsum is a sequential accumulation)
+    double w1[NB], w2[NB], m1[NB], m2[NB];
+    long long w1_i[NB], w2_i[NB];
+    {
+        double acc = 0.0, accm = 0.0; long long acci = 0;
+        for (int i = 0; i < NB; ++i) {
+            acc += hist[i]; acci += hist_i[i]; accm += hist[i] * mids[i];
+            w1[i] = acc; w1_i[i] = acci; m1[i] = accm / acc;                                  // D:1673, 1677
+        }
+        acc = 0.0; accm = 0.0; acci = 0;
+        for (int i = NB - 1; i >= 0; --i) {
+            acc += hist[i]; acci += hist_i[i]; accm += hist[i] * mids[i];
+            w2[i] = acc; w2_i[i] = acci; m2[i] = accm / acc;                                  // D:1674, 1679
+        }
+    }
+    // D:1681-1684: first maximum of the inter-class variance; np.argmax returns the first NaN if there is one
+    int best = 0;
+    double best_v = 0.0;
+    for (int i = 0; i < NB - 1; ++i) {
+        const double d = m1[i] - m2[i + 1];
+        // not normalised: weight1 * weight2 is an int64 product in numpy before it meets the float64 factor
+        const double ww = is_normalized ? w1[i] * w2[i + 1] : (double)(w1_i[i] * w2_i[i + 1]);
+        const double v = ww * (d * d);
+        if (std::isnan(v)) { best = i; break; }
+        if (i == 0 || v > best_v) { best = i; best_v = v; }
+    }
+    *threshold = mids[best];
+    return 0;
+}
+
+extern "C" int pb200_greater_than_u8(pb200_ctx *ctx, const uint8_t *image, int64_t n, double threshold, uint8_t *out,
+                                     void *stream) {
+    ENTER(ctx);
+    EMPTY_OK(n);
+    REQUIRE(image && out && n >= 0, "pb200_greater_than_u8: bad argument");
+    REQUIRE(threshold == threshold, "pb200_greater_than_u8: NaN threshold");
+    if (n == 0) return 0;
+    // x > t for integer x: x >= floor(t) + 1
+    const double lim = std::floor(threshold) + 1.0;
+    const int limit = lim < 0.0 ? 0 : (lim > 256.0 ? 256 : (int)lim);
+    greater_than_u8_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(image, out, n, limit);
+    LEAVE();
+}
+
 extern "C" int pb200_shadow(pb200_ctx *ctx, const float *dem, int rows, int cols, double sun_azimuth,
                             double sun_elevation, const double *terms, const pb200_params *params, uint8_t *out,
                             void *stream) {

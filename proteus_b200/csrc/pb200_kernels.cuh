@@ -495,6 +495,32 @@ __global__ void scale_offset_kernel(const int16_t *__restrict__ in, const uint8_
     }
 }
 
+// D:1663 (np.histogram input): exact per-value counts of a uint8 raster; per-warp private histograms in shared memory
+__global__ void __launch_bounds__(256) histogram_u8_kernel(const uint8_t *__restrict__ in, long long n,
+                                                           unsigned long long *__restrict__ counts) {
+    __shared__ unsigned int h[8][256];
+    for (int i = threadIdx.x; i < 8 * 256; i += 256) (&h[0][0])[i] = 0u;
+    __syncthreads();
+    unsigned int *mine = h[threadIdx.x >> 5];
+    const long long n4 = (reinterpret_cast<uintptr_t>(in) & 3) ? 0 : n / 4;
+    PB200_GRID_STRIDE(i, n4) {
+        const uint32_t x = ldg_stream_u32(in + 4 * i);
+        atomicAdd(&mine[x & 255u], 1u); atomicAdd(&mine[(x >> 8) & 255u], 1u);
+        atomicAdd(&mine[(x >> 16) & 255u], 1u); atomicAdd(&mine[x >> 24], 1u);
+    }
+    for (long long i = 4 * n4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        atomicAdd(&mine[in[i]], 1u);
+    __syncthreads();
+    unsigned int t = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += h[w][threadIdx.x];
+    if (t) atomicAdd(&counts[threadIdx.x], (unsigned long long)t);
+}
+// D:1684: image > threshold for a uint8 image and a float64 threshold == image >= limit with an integer limit
+__global__ void greater_than_u8_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, long long n, int limit) {
+    PB200_GRID_STRIDE(i, n) { out[i] = (int)in[i] >= limit ? 1 : 0; }
+}
+
 // D:4215-4283 over a whole DEM incl. np.gradient's one-sided border differences
 __global__ void shadow_kernel(const float *__restrict__ dem, int rows, int cols, uint8_t *__restrict__ out,
                               SunTerms S, const __grid_constant__ DevParams P) {

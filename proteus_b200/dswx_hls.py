@@ -50,7 +50,7 @@ REPLACED_FUNCTIONS = (
     '_add_snow_to_cloud_layer', '_apply_cloud_masking',
     '_get_binary_water_layer', '_get_confidence_layer',
     '_collapse_wtr_classes', '_compute_opera_shadow_layer',
-    '_compute_browse_array',
+    '_compute_browse_array', '_compute_otsu_threshold',
 )
 
 
@@ -403,6 +403,45 @@ def scale_and_offset_band(image, scale_factor, offset, invalid_ind=None):
         ctx.handle, x.data_ptr(), int(x.numel()), float(scale_factor), float(offset),
         inv.data_ptr() if inv is not None else None, out.data_ptr(), _stream()))
     return _to_host(out, np.float32)
+
+
+# ---------------------------------------------------------------------------
+# D:1638-1684: the numpy half of the 'otsu' shadow algorithm
+# ---------------------------------------------------------------------------
+def _otsu_counts(image):
+    """Exact per-value counts (numpy uint64[256]) of a uint8 raster, counted on the GPU."""
+    torch = _torch()
+    ctx = get_context()
+    x = _to_device(image, np.uint8, 'image')
+    counts = torch.zeros(256, dtype=torch.int64, device='cuda')
+    _lib.check(ctx._lib.pb200_histogram_u8(ctx.handle, x.data_ptr(), int(x.numel()), counts.data_ptr(), _stream()))
+    return x, counts
+
+
+def otsu_threshold_from_counts(counts, is_normalized=True):
+    """np.histogram(image, bins=256) binning + the float64 Otsu arithmetic of D:1663-1686 on 256 exact per-value
+    counts (host; no GPU needed).  Ranks holding strips of one raster sum their counts first."""
+    arr = (C.c_uint64 * 256)(*[int(v) for v in np.asarray(counts).ravel()])
+    thr = C.c_double()
+    _lib.check(_lib.load().pb200_otsu_threshold(arr, int(bool(is_normalized)), C.byref(thr)))
+    return thr.value
+
+
+def _compute_otsu_threshold(image, is_normalized=True):
+    """Same result as the reference function for the uint8 hillshade GDAL writes (D:4206-4209): bool array
+    ``image > threshold``.  The hillshade itself is a GDAL file operation and stays on the host."""
+    img = np.asarray(image)
+    if img.dtype != np.uint8:
+        raise NotImplementedError(f'_compute_otsu_threshold: image dtype {img.dtype}; only the uint8 hillshade')
+    if img.size == 0:
+        raise ValueError('attempt to get argmax of an empty sequence')        # what numpy raises at D:1684
+    ctx = get_context()
+    x, counts = _otsu_counts(img)
+    thr = otsu_threshold_from_counts(counts.cpu().numpy(), is_normalized)
+    out = _empty_like_device(x.shape, np.uint8)
+    _lib.check(ctx._lib.pb200_greater_than_u8(
+        ctx.handle, x.data_ptr(), int(x.numel()), thr, out.data_ptr(), _stream()))
+    return _to_host(out, np.uint8).astype(bool)
 
 
 def _crop_2d_array_all_sides(input_2d_array, margin):

@@ -176,3 +176,18 @@ class MosaicStrip:
                for k, v in self.outputs.items()}
         res['counters'] = self.counters[0].cpu().numpy().astype(np.uint64)
         return res
+
+
+def otsu_threshold_of_strips(local_counts, is_normalized=True, group=None):
+    """Otsu threshold (dswx_hls.py:1638-1686) of a raster held as row strips by the ranks of ``group``: the 256
+    exact per-value counts of every strip (``dswx_hls._otsu_counts`` on the GPU, int64 tensor) are summed with ONE
+    all-reduce - the only exchange the 'otsu' shadow algorithm needs - and every rank derives
+    the same threshold from the sum."""
+    import torch
+    import torch.distributed as dist
+    from .dswx_hls import otsu_threshold_from_counts
+    counts = local_counts if isinstance(local_counts, torch.Tensor) else torch.as_tensor(np.asarray(local_counts))
+    counts = counts.to(torch.int64).clone()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    return otsu_threshold_from_counts(counts.cpu().numpy(), is_normalized)

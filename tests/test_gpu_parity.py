@@ -474,3 +474,20 @@ def test_batch_of_mixed_tiles_through_the_item_pipeline(pb):
                 res = plan.results(i)
                 _assert_layers(res, ref, names, f'tile {i} launch {launch} {len(layers)} layers')
                 assert np.array_equal(res['counters'][:3], ref['counters']), (i, launch)
+
+
+def test_otsu_threshold_dropin(pb):
+    """SURVEY 8f next #3: _compute_otsu_threshold on uint8 hillshades (GPU histogram + compare, host threshold)."""
+    import proteus_b200.dswx_hls as G
+    from test_oracle_golden import _otsu_images
+    imgs = _otsu_images()[:18]
+    rng = np.random.default_rng(3)
+    imgs.append(np.clip(rng.normal(181, 35, (1237, 2051)), 0, 255).astype(np.uint8))      # odd sizes, > 1 block
+    for img in imgs:
+        for norm in (True, False):
+            got = G._compute_otsu_threshold(img, norm)
+            assert got.dtype == np.bool_ and np.array_equal(got, O.compute_otsu_threshold(img, norm))
+    _, counts = G._otsu_counts(imgs[-1])
+    assert np.array_equal(counts.cpu().numpy(), np.bincount(imgs[-1].ravel(), minlength=256))
+    with pytest.raises(NotImplementedError):
+        G._compute_otsu_threshold(imgs[0].astype(np.float32))

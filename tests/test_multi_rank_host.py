@@ -53,8 +53,13 @@ def _worker(rank, world, port, height, width, margin, out_dir):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         counters = torch.tensor([n, rank + 1, 1], dtype=torch.int64)
         dist.all_reduce(counters, op=dist.ReduceOp.SUM)
+        # Otsu threshold of a raster split in row strips: one all-reduce of the per-value counts
+        hill = np.clip(np.random.default_rng(5).normal(170, 40, (height, width)), 0, 255).astype(np.uint8)
+        thr = mosaic.otsu_threshold_of_strips(np.bincount(hill[r0:r1].ravel(), minlength=256))
+        from oracle import dswx_oracle as O
+        otsu_ok = thr == O.otsu_threshold(hill)
         np.save(os.path.join(out_dir, f'r{rank}.npy'),
-                np.array([int(ok), r0, r1, len(mine), int(t.item()), *counters.tolist()]))
+                np.array([int(ok), r0, r1, len(mine), int(t.item()), *counters.tolist(), int(otsu_ok)]))
     finally:
         dist.destroy_process_group()
 
@@ -70,6 +75,7 @@ def test_halo_exchange_and_sharding_world2(tmp_path, height):
     assert res[0][2] % 32 == 0
     assert [r[3] for r in res] == [4, 3] and all(r[4] == 4 for r in res)         # 7 tiles round robin, max = 4
     assert all(r[5] == height and r[6] == 3 and r[7] == 2 for r in res)          # summed counters
+    assert all(r[8] == 1 for r in res), 'threshold from all-reduced strip histograms != whole-raster Otsu threshold'
 
 
 def test_strip_bounds_properties():

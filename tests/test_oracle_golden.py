@@ -166,3 +166,37 @@ def test_browse_relabel_and_scaling_restatements():
     out = O.scale_and_offset_band(x, 0.0001, -0.01)
     assert out.dtype == np.float32
     assert np.array_equal(out, np.float32(0.0001) * (x.astype(np.float32) - np.float32(-0.01)))
+
+
+def _otsu_images():
+    rng = np.random.default_rng(0)
+    out = []
+    for k in range(60):
+        kind = k % 6
+        if kind == 0:
+            img = rng.integers(0, 256, (40, 50), dtype=np.uint8)
+        elif kind == 1:
+            img = np.clip(rng.normal(180, 30, (64, 64)), 0, 255).astype(np.uint8)
+        elif kind == 2:
+            img = rng.choice([0, 255], size=(30, 30)).astype(np.uint8)
+        elif kind == 3:
+            img = np.full((8, 8), rng.integers(0, 256), np.uint8)
+        elif kind == 4:
+            lo = rng.integers(0, 200)
+            img = rng.integers(lo, lo + rng.integers(2, 56), (50, 20), dtype=np.uint8)
+        else:
+            img = np.clip(np.concatenate([rng.normal(60, 10, 2000), rng.normal(200, 20, 3000)]),
+                          0, 255).astype(np.uint8).reshape(50, 100)
+        out.append(img)
+    return out
+
+
+def test_otsu_threshold_host_function_equals_the_numpy_restatement():
+    """pb200_otsu_threshold (C, from exact per-value counts) reproduces numpy's histogram binning
+    and float64 arithmetic to the last bit, NaN cases (constant images) included."""
+    from proteus_b200.dswx_hls import otsu_threshold_from_counts
+    for img in _otsu_images():
+        for norm in (True, False):
+            t_c = otsu_threshold_from_counts(np.bincount(img.ravel(), minlength=256), norm)
+            t_np = O.otsu_threshold(img, norm)
+            assert t_c == t_np, (img.min(), img.max(), norm, t_c, t_np)

@@ -103,3 +103,14 @@ def test_browse_and_rgb_scaling_against_live_reference(ref):
         keys = ('swir1', 'nir', 'red') if infrared else ('red', 'green', 'blue')
         for a, band, kk in zip(out, bands, keys):
             assert np.array_equal(a, O.scale_and_offset_band(band, sc[kk], off[kk], inv), equal_nan=True), kk
+
+
+def test_otsu_threshold_against_live_reference(ref):
+    from test_oracle_golden import _otsu_images
+    from proteus_b200.dswx_hls import otsu_threshold_from_counts
+    for img in _otsu_images():
+        for norm in (True, False):
+            with np.errstate(all='ignore'):
+                live = ref._compute_otsu_threshold(img, norm)
+            assert np.array_equal(live, O.compute_otsu_threshold(img, norm))
+            assert np.array_equal(live, img > otsu_threshold_from_counts(np.bincount(img.ravel(), minlength=256), norm))
