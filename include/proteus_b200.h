@@ -210,6 +210,12 @@ int  pb200_snow_to_cloud_cover(pb200_ctx *ctx, const uint8_t *wtr2, uint8_t *clo
 int  pb200_masked_dilation(pb200_ctx *ctx, const uint8_t *in, const uint8_t *mask, int rows,
                            int cols, int iterations, uint8_t *out, uint8_t *scratch,
                            void *stream);
+/* Point-wise tail of the 'cover' flow in one pass: WTR = _apply_cloud_masking(WTR-2, CLOUD) (D:2089), BWTR (D:1710),
+ * CONF (D:1733) and, when collapse != 0, _collapse_wtr_classes (D:2578) of WTR, WTR-2 and the optional WTR-1 planes
+ * IN PLACE.  wtr / bwtr / conf / wtr1 / wtr1_remapped may be NULL. */
+int  pb200_cover_tail(pb200_ctx *ctx, uint8_t *wtr2, const uint8_t *cloud, int64_t n, uint8_t *wtr,
+                      uint8_t *bwtr, uint8_t *conf, uint8_t *wtr1, uint8_t *wtr1_remapped, int collapse,
+                      void *stream);
 /* D:2089-2133 _apply_cloud_masking */
 int  pb200_cloud_masking(pb200_ctx *ctx, const uint8_t *wtr2,
                          const uint8_t *cloud, int64_t n, uint8_t *wtr,

@@ -25,7 +25,7 @@ EXPORTS = (
     'pb200_diagnostic_tests', 'pb200_diagnostic_tests_f32', 'pb200_interpreted_layer',
     'pb200_binary_representation', 'pb200_preliminary_cloud',
     'pb200_aerosol_remap', 'pb200_landcover_shadow_masks',
-    'pb200_snow_to_cloud', 'pb200_snow_to_cloud_cover', 'pb200_masked_dilation', 'pb200_cloud_masking', 'pb200_binary_water',
+    'pb200_snow_to_cloud', 'pb200_snow_to_cloud_cover', 'pb200_masked_dilation', 'pb200_cover_tail', 'pb200_cloud_masking', 'pb200_binary_water',
     'pb200_confidence', 'pb200_collapse', 'pb200_shadow', 'pb200_landcover_aggregate',
     'pb200_browse_table', 'pb200_byte_table', 'pb200_scale_offset',
     'pb200_histogram_u8', 'pb200_otsu_threshold', 'pb200_greater_than_u8', 'pb200_ratio_bound',
@@ -137,6 +137,7 @@ def load():
     lib.pb200_snow_to_cloud.argtypes = [vp, vp, vp, vp, C.c_int, i64, vp]
     lib.pb200_snow_to_cloud_cover.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, vp, vp]
     lib.pb200_masked_dilation.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+    lib.pb200_cover_tail.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp, C.c_int, vp]
     lib.pb200_cloud_masking.argtypes = [vp, vp, vp, i64, vp, vp]
     lib.pb200_binary_water.argtypes = [vp, vp, i64, vp, vp]
     lib.pb200_confidence.argtypes = [vp, vp, vp, i64, vp, vp]

@@ -1218,16 +1218,21 @@ extern "C" int pb200_snow_to_cloud(pb200_ctx *ctx, const uint8_t *wtr2, uint8_t 
     LEAVE();
 }
 
-// iterations of the masked dilation, ping-pong between `a` (holds the input) and `b`; returns the
-// buffer that holds the result
-static uint8_t *run_masked_dilation(uint8_t *a, uint8_t *b, const uint8_t *mask, int rows, int cols, int iterations,
-                                    cudaStream_t st) {
-    dim3 block(64, 4), grid((cols + 63) / 64, (rows + 3) / 4);
-    for (int it = 0; it < iterations; ++it) {
-        masked_dilation_step_kernel<<<grid, block, 0, st>>>(a, mask, b, rows, cols);
-        std::swap(a, b);
+// `iterations` masked dilation steps from `a` (input) ping-ponging with `b`, MD_HALO steps per launch; returns the
+// buffer that holds the result (never the input when iterations >= 1)
+static uint8_t *run_masked_dilation(const uint8_t *a, uint8_t *b, uint8_t *c, const uint8_t *mask, int rows, int cols,
+                                    int iterations, cudaStream_t st) {
+    dim3 grid((cols + MD_TW - 1) / MD_TW, (rows + MD_TH - 1) / MD_TH);
+    const uint8_t *src = a;
+    uint8_t *dst = b;
+    while (iterations > 0) {
+        const int k = std::min(iterations, MD_HALO);
+        masked_dilation_tiled_kernel<<<grid, 256, 0, st>>>(src, mask, dst, rows, cols, k);
+        iterations -= k;
+        src = dst;
+        dst = (dst == b) ? c : b;
     }
-    return a;
+    return const_cast<uint8_t *>(src);
 }
 
 extern "C" int pb200_masked_dilation(pb200_ctx *ctx, const uint8_t *in, const uint8_t *mask, int rows, int cols,
@@ -1235,17 +1240,14 @@ extern "C" int pb200_masked_dilation(pb200_ctx *ctx, const uint8_t *in, const ui
     ENTER(ctx);
     REQUIRE(rows >= 0 && cols >= 0 && iterations >= 1, "pb200_masked_dilation: bad size / iterations");
     if ((long long)rows * cols == 0) return 0;
-    REQUIRE(in && mask && out && scratch && in != out, "pb200_masked_dilation: bad argument");
+    REQUIRE(in && mask && out && scratch && in != out && scratch != out && scratch != in,
+            "pb200_masked_dilation: bad argument");
     const size_t n = (size_t)rows * cols;
-    // arrange the ping-pong so that the last iteration writes `out`
-    uint8_t *first = (iterations % 2) ? out : scratch;
-    dim3 block(64, 4), grid((cols + 63) / 64, (rows + 3) / 4);
-    masked_dilation_step_kernel<<<grid, block, 0, st>>>(in, mask, first, rows, cols);
-    if (iterations > 1) {
-        uint8_t *other = (first == out) ? scratch : out;
-        uint8_t *res = run_masked_dilation(first, other, mask, rows, cols, iterations - 1, st);
-        if (res != out) CK(cudaMemcpyAsync(out, res, n, cudaMemcpyDeviceToDevice, st));
-    }
+    // arrange the ping-pong so that the last launch writes `out`
+    const int launches = (iterations + MD_HALO - 1) / MD_HALO;
+    uint8_t *first = (launches % 2) ? out : scratch, *second = (launches % 2) ? scratch : out;
+    uint8_t *res = run_masked_dilation(in, first, second, mask, rows, cols, iterations, st);
+    if (res != out) CK(cudaMemcpyAsync(out, res, n, cudaMemcpyDeviceToDevice, st));
     LEAVE();
 }
 
@@ -1259,11 +1261,21 @@ extern "C" int pb200_snow_to_cloud_cover(pb200_ctx *ctx, const uint8_t *wtr2, ui
     uint8_t *A = scratch, *B = scratch + n, *M = scratch + 2 * n, *S = scratch + 3 * n;
     const int g = grid_for(ctx, n, 256);
     cover_init_kernel<<<g, 256, 0, st>>>(fmask, cloud, A, M, n);                      // snow, area
-    uint8_t *snow = run_masked_dilation(A, B, M, rows, cols, 10, st);                  // D:2060
-    CK(cudaMemcpyAsync(S, snow, (size_t)n, cudaMemcpyDeviceToDevice, st));
-    cover_mid_kernel<<<g, 256, 0, st>>>(S, cloud, wtr2, M, A, n);                      // area2, not_masked
-    uint8_t *nm = run_masked_dilation(A, B, M, rows, cols, 7, st);                     // D:2075
-    cover_final_kernel<<<g, 256, 0, st>>>(S, nm, wtr2, cloud, n);
+    uint8_t *snow = run_masked_dilation(A, S, B, M, rows, cols, 10, st);               // D:2060 (one launch -> S)
+    cover_mid_kernel<<<g, 256, 0, st>>>(snow, cloud, wtr2, M, A, n);                   // area2, not_masked
+    uint8_t *nm = run_masked_dilation(A, B, nullptr, M, rows, cols, 7, st);            // D:2075 (one launch -> B)
+    cover_final_kernel<<<g, 256, 0, st>>>(snow, nm, wtr2, cloud, n);
+    LEAVE();
+}
+
+extern "C" int pb200_cover_tail(pb200_ctx *ctx, uint8_t *wtr2, const uint8_t *cloud, int64_t n, uint8_t *wtr,
+                                uint8_t *bwtr, uint8_t *conf, uint8_t *wtr1, uint8_t *wtr1_remapped, int collapse,
+                                void *stream) {
+    ENTER(ctx);
+    EMPTY_OK(n);
+    REQUIRE(wtr2 && cloud && n >= 0, "pb200_cover_tail: bad argument");
+    if (n == 0) return 0;
+    cover_tail_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(wtr2, cloud, wtr, bwtr, conf, wtr1, wtr1_remapped, collapse, n);
     LEAVE();
 }
 

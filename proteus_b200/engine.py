@@ -355,23 +355,18 @@ def classify_device_cover(tile, hls_thresholds=None, outputs=ALL_LAYERS, *, coll
     wtr = torch.empty_like(o['WTR2'])
     bwtr = torch.empty_like(o['WTR2'])
     conf = torch.empty_like(o['WTR2'])
-    _lib.check(lib.pb200_cloud_masking(ctx.handle, o['WTR2'].data_ptr(), o['CLOUD'].data_ptr(), n,
-                                       wtr.data_ptr(), stream))
-    _lib.check(lib.pb200_binary_water(ctx.handle, wtr.data_ptr(), n, bwtr.data_ptr(), stream))
-    _lib.check(lib.pb200_confidence(ctx.handle, o['WTR2'].data_ptr(), o['CLOUD'].data_ptr(), n,
-                                    conf.data_ptr(), stream))
-    res.update(BWTR=bwtr, CONF=conf)
     counters = plan.counters[0].clone()
-    if class_histogram:
+    if class_histogram:                                   # of the uncollapsed WTR (D:5104 ff. count before collapsing)
+        _lib.check(lib.pb200_cover_tail(ctx.handle, o['WTR2'].data_ptr(), o['CLOUD'].data_ptr(), n, wtr.data_ptr(),
+                                        None, None, None, None, 0, stream))
         hist = torch.bincount(wtr.reshape(-1).to(torch.int64), minlength=256)
         for k, cls in enumerate(HISTOGRAM_CLASSES):
             counters[3 + k] = hist[cls]
-    for name, t in (('WTR', wtr), ('WTR1', o['WTR1']), ('WTR1_REMAPPED', o['WTR1_REMAPPED']), ('WTR2', o['WTR2'])):
-        if collapse_wtr_classes:
-            c = torch.empty_like(t)
-            _lib.check(lib.pb200_collapse(ctx.handle, t.data_ptr(), n, c.data_ptr(), stream))
-            t = c
-        res[name] = t
+    # one pass: WTR / BWTR / CONF, and the collapsed WTR, WTR-1, WTR-1 (remapped), WTR-2 in place
+    _lib.check(lib.pb200_cover_tail(ctx.handle, o['WTR2'].data_ptr(), o['CLOUD'].data_ptr(), n, wtr.data_ptr(),
+                                    bwtr.data_ptr(), conf.data_ptr(), o['WTR1'].data_ptr(),
+                                    o['WTR1_REMAPPED'].data_ptr(), int(bool(collapse_wtr_classes)), stream))
+    res.update(BWTR=bwtr, CONF=conf, WTR=wtr, WTR1=o['WTR1'], WTR1_REMAPPED=o['WTR1_REMAPPED'], WTR2=o['WTR2'])
     res = {k: v for k, v in res.items() if k in outputs}
     res['counters'] = counters
     return res

@@ -1,0 +1,74 @@
+"""Roofline check of the kernels outside the fused hot path, device-resident inputs at HLS tile
+size, CUDA events on the launching stream.  Prints one JSON object; algorithmic bytes = each plane once."""
+import ctypes as C, json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import proteus_b200 as pb
+from proteus_b200 import _lib, synth, dswx_hls as G
+from proteus_b200.engine import get_context, classify_device_cover
+
+ctx = get_context(); lib = ctx._lib
+st = torch.cuda.current_stream(); sp = C.c_void_p(st.cuda_stream)
+PEAK = 6550.1
+try:
+    PEAK = float(json.load(open(os.path.join(os.path.dirname(__file__), '..', 'MEASURED_PEAKS.json')))['hbm_gbs'])
+except Exception:
+    pass
+S = 3660; n = S * S
+g = torch.Generator(device='cuda').manual_seed(1)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+
+def timed(fn, reps=20):
+    for _ in range(3): fn()
+    ms = []
+    for _ in range(reps):
+        flush.zero_()                                  # > L2: every timed launch starts cold
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record(st); fn(); e1.record(st); torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    return float(np.median(ms))
+
+res = {}
+def report(name, ms, nbytes, note=''):
+    gbs = nbytes / ms / 1e6
+    res[name] = dict(ms=round(ms, 4), algorithmic_MB=round(nbytes / 1e6, 1), GBps=round(gbs, 1), frac_of_hbm_peak=round(gbs / PEAK, 3), note=note)
+
+# LAND aggregation: 10980^2 WorldCover + 3660^2 CGLS -> 3660^2 LAND
+wc = torch.randint(0, 256, (3 * S, 3 * S), dtype=torch.uint8, device='cuda', generator=g)
+wc[torch.rand((3 * S, 3 * S), device='cuda', generator=g) < 0.5] = 10
+cop = torch.randint(100, 130, (S, S), dtype=torch.uint8, device='cuda', generator=g)
+land = torch.empty((S, S), dtype=torch.uint8, device='cuda')
+table = (C.c_uint8 * 256)(*[1 if v in (111, 113, 115, 116, 121, 123, 125, 126) else 0 for v in range(256)])
+th = (C.c_int32 * 4)(6, 3, 7, 3)
+report('landcover_aggregate', timed(lambda: _lib.check(lib.pb200_landcover_aggregate(
+    ctx.handle, wc.data_ptr(), cop.data_ptr(), S, S, table, 21, th, land.data_ptr(), sp))), 9 * n + n + n)
+
+# byte table (browse relabel), scale/offset, histogram, compare
+w8 = torch.randint(0, 5, (S, S), dtype=torch.uint8, device='cuda', generator=g); o8 = torch.empty_like(w8)
+tbl = (C.c_uint8 * 256)(); lib.pb200_browse_table(1, 0, 0, 0, 0, 1, tbl)
+report('byte_table (browse)', timed(lambda: _lib.check(lib.pb200_byte_table(ctx.handle, w8.data_ptr(), n, tbl, o8.data_ptr(), sp))), 2 * n)
+b16 = torch.randint(-100, 9000, (S, S), dtype=torch.int16, device='cuda', generator=g); f32 = torch.empty((S, S), dtype=torch.float32, device='cuda')
+inv = (torch.rand((S, S), device='cuda', generator=g) < 0.02).to(torch.uint8)
+report('scale_offset', timed(lambda: _lib.check(lib.pb200_scale_offset(ctx.handle, b16.data_ptr(), n, 1e-4, 0.0, inv.data_ptr(), f32.data_ptr(), sp))), 2 * n + n + 4 * n)
+hill = torch.randint(0, 256, (S + 100, S + 100), dtype=torch.uint8, device='cuda', generator=g); cnt = torch.zeros(256, dtype=torch.int64, device='cuda')
+report('histogram_u8 (otsu)', timed(lambda: _lib.check(lib.pb200_histogram_u8(ctx.handle, hill.data_ptr(), hill.numel(), cnt.data_ptr(), sp))), hill.numel(),
+       'uniform random bytes: worst case for shared-memory atomics is a constant image')
+mask = torch.empty_like(hill)
+report('greater_than_u8 (otsu)', timed(lambda: _lib.check(lib.pb200_greater_than_u8(ctx.handle, hill.data_ptr(), hill.numel(), 127.5, mask.data_ptr(), sp))), 2 * hill.numel())
+
+# float32 diagnostic tests
+fb = [torch.rand((S, S), device='cuda', generator=g) for _ in range(6)]; d16 = torch.empty((S, S), dtype=torch.int16, device='cuda')
+ptrs = (C.c_void_p * 6)(*[t.data_ptr() for t in fb]); thr = pb.make_params().th
+report('diagnostic_tests_f32', timed(lambda: _lib.check(lib.pb200_diagnostic_tests_f32(ctx.handle, ptrs, C.byref(thr), n, d16.data_ptr(), sp))), 24 * n + 2 * n)
+
+# one masked dilation step, and the whole cover-mode flow of one tile
+a = (torch.rand((S, S), device='cuda', generator=g) < 0.1).to(torch.uint8); m = (torch.rand((S, S), device='cuda', generator=g) < 0.7).to(torch.uint8)
+outd = torch.empty_like(a); scratch = torch.empty_like(a)
+report('masked_dilation x10', timed(lambda: _lib.check(lib.pb200_masked_dilation(ctx.handle, a.data_ptr(), m.data_ptr(), S, S, 10, outd.data_ptr(), scratch.data_ptr(), sp)), reps=10),
+       10 * 3 * n, '10 iterations, each reads image + mask and writes image')
+tile = synth.make_device_batch(1, S, S, device='cuda', seed=7, n_distinct=1)[0]
+torch.cuda.synchronize()
+ms = timed(lambda: classify_device_cover(tile, outputs=pb.GRADED_LAYERS), reps=5)
+res['cover_mode_tile (fused + 17 dilation steps + tail)'] = dict(ms=round(ms, 3), Mpixel_per_s=round(n / ms / 1e3, 1))
+res['hbm_peak_GBps'] = PEAK
+print(json.dumps(res, indent=1))

@@ -372,9 +372,12 @@ def test_masked_dilation_matches_scipy(pb):
     from proteus_b200 import _lib
     ctx = pb.get_context()
     rng = np.random.default_rng(3)
-    for shape, iters in (((37, 53), 1), ((64, 200), 10), ((1, 40), 7), ((50, 1), 3), ((129, 131), 4)):
-        a = rng.random(shape) < 0.05
-        m = rng.random(shape) < 0.7
+    # one launch runs up to 16 steps in shared memory (96 x 64 tiles + halo): sizes around the tile edges, iteration
+    # counts around the per-launch limit, sparse seeds in a dense mask so that fronts cross several tiles
+    for shape, iters in (((37, 53), 1), ((64, 200), 10), ((1, 40), 7), ((50, 1), 3), ((129, 131), 4),
+                         ((64, 96), 16), ((65, 97), 17), ((200, 300), 40), ((130, 200), 33)):
+        a = rng.random(shape) < (0.05 if iters < 16 else 0.002)
+        m = rng.random(shape) < (0.7 if iters < 16 else 0.97)
         ref = binary_dilation(a, iterations=iters, mask=m)
         da, dm = torch.from_numpy(a.view(np.uint8)).cuda(), torch.from_numpy(m.view(np.uint8)).cuda()
         out, scr = torch.empty_like(da), torch.empty_like(da)
