@@ -731,9 +731,9 @@ static int fast_kernel_setup(pb200_ctx *ctx) {
                                 (int)FAST_DYN_SMEM));
     }
     int nb = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dswx_fused_fast_kernel<false>, FT_THREADS, FAST_DYN_SMEM));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dswx_fused_fast_kernel<false>, FtGeom<false>::THREADS, FAST_DYN_SMEM));
     ctx->fast_ctas_per_sm = nb > 0 ? nb : 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dswx_fused_fast_kernel<true>, FT_THREADS, FAST_DYN_SMEM));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dswx_fused_fast_kernel<true>, FtGeom<true>::THREADS, FAST_DYN_SMEM));
     ctx->fast_ctas_per_sm_full = nb > 0 ? nb : 1;
     ctx->fast_ready = true;
     return 0;
@@ -746,10 +746,10 @@ static int plan_launch(pb200_plan *pl, cudaStream_t stream) {
         const int grid = std::min(pl->n_items, pl->ctx->sm_count * (pl->fast_optional ? pl->ctx->fast_ctas_per_sm_full
                                                                                        : pl->ctx->fast_ctas_per_sm));
         if (pl->fast_optional)
-            dswx_fused_fast_kernel<true><<<grid, FT_THREADS, FAST_DYN_SMEM, stream>>>(
+            dswx_fused_fast_kernel<true><<<grid, FtGeom<true>::THREADS, FAST_DYN_SMEM, stream>>>(
                 pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, pl->d_items, pl->n_items, pl->P, pl->F);
         else
-            dswx_fused_fast_kernel<false><<<grid, FT_THREADS, FAST_DYN_SMEM, stream>>>(
+            dswx_fused_fast_kernel<false><<<grid, FtGeom<false>::THREADS, FAST_DYN_SMEM, stream>>>(
                 pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, pl->d_items, pl->n_items, pl->P, pl->F);
     }
     if (pl->n[G_VEC]) {
@@ -775,10 +775,10 @@ static int plan_launch_tile(pb200_plan *pl, int i, cudaStream_t stream) {
                                                                             : pl->ctx->fast_ctas_per_sm));
         const ItemDesc *it = pl->d_items + pl->item_start[i];
         if (pl->fast_optional)
-            dswx_fused_fast_kernel<true><<<grid, FT_THREADS, FAST_DYN_SMEM, stream>>>(
+            dswx_fused_fast_kernel<true><<<grid, FtGeom<true>::THREADS, FAST_DYN_SMEM, stream>>>(
                 pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, it, n, pl->P, pl->F);
         else
-            dswx_fused_fast_kernel<false><<<grid, FT_THREADS, FAST_DYN_SMEM, stream>>>(
+            dswx_fused_fast_kernel<false><<<grid, FtGeom<false>::THREADS, FAST_DYN_SMEM, stream>>>(
                 pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, it, n, pl->P, pl->F);
     } else if (g == G_VEC) {
         dswx_fused_kernel<true><<<dim3(pl->tile_ctas[i], 1), NTHREADS, 0, stream>>>(pl->d_tiles[g] + slot,
@@ -897,7 +897,7 @@ extern "C" int pb200_classify_host(pb200_ctx *ctx, const pb200_tile *ht, const p
     CK(cudaSetDevice(ctx->device));
     const int H = ht->height, W = ht->width;
     if (H <= 0 || W <= 0) return fail(PB200_E_INVALID_ARG, "pb200_classify_host: empty raster");
-    if (strip_rows <= 0) strip_rows = 32 * TH;      // 1024 rows: 4 strips per HLS tile (measured best, scripts/e2e_probe.py)
+    if (strip_rows <= 0) strip_rows = 33 * TH;      // 1056 rows = 11 items of the fast kernel: 4-5 strips per HLS tile
     strip_rows = ((strip_rows + TH - 1) / TH) * TH;
     const size_t px = (size_t)H * W;
     const size_t dem_elems = ht->dem ? (size_t)ht->dem_rows * ht->dem_pitch : 0;

@@ -27,21 +27,26 @@
 //    it can change (flag from big_lut) or when SHAD is requested: float32 with
 //    a guard band covering every rounding error of the shortcut, and the
 //    float64 reference sequence (shadow_from_gradient) inside the band;
-//  * persistent CTAs loop over 256 x 32 pixel items; an item's DEM tile with
-//    halo arrives as two TMA boxes; the tables are loaded once per CTA.
+//  * persistent CTAs loop over 128 x 32 pixel items (a warp owns 4 rows); an item's DEM tile with halo arrives
+//    as one TMA box into a double buffer, requested one item ahead; warps synchronise through full / empty
+//    mbarriers only (no __syncthreads between the items of a tile); the tables are loaded once per CTA.
 #pragma once
 #include "pb200_kernels.cuh"
 
 namespace pb200 {
 
-#ifndef PB200_FT_HALVES
-#define PB200_FT_HALVES 1          // 128-pixel halves per item: 1 -> 256-thread CTAs (4 per SM), 2 -> 512-thread CTAs
+// Geometry: ONE persistent CTA per SM works on 128 x FT_H pixel items.  The lean variant (graded layers) runs 24
+// warps x 4 rows at <= 80 registers, the full variant (all layers, needs ~118 registers) 16 warps x 6 rows.  Measured
+// (profiles/README.md): one 24-warp CTA beats 3 x 8 and 2 x 12 warps - one copy of the tables, 98/96 instead of 34/32
+// DEM rows per item, and more of the SM's 256 KB left to L1, which the streaming loads in flight need.
+#ifndef PB200_FT_H
+#define PB200_FT_H 96
 #endif
-#ifndef PB200_FT_ROWGROUPS
-#define PB200_FT_ROWGROUPS 8       // warps (row groups of 4 rows) per 128-pixel half
+#ifndef PB200_FT_WARPS_LEAN
+#define PB200_FT_WARPS_LEAN 24
 #endif
-#ifndef PB200_FT_MIN_CTAS
-#define PB200_FT_MIN_CTAS (768 / (32 * PB200_FT_ROWGROUPS * PB200_FT_HALVES))   // 24 warps per SM at <= 80 registers
+#ifndef PB200_FT_WARPS_FULL
+#define PB200_FT_WARPS_FULL 16
 #endif
 #ifndef PB200_FT_PRODUCER_WARP
 #define PB200_FT_PRODUCER_WARP 0   // DEM requests by thread 0 (0) or by warp 0 with lane 0 issuing (1)
@@ -55,15 +60,16 @@ namespace pb200 {
 #ifndef PB200_FT_XITEM_PREFETCH
 #define PB200_FT_XITEM_PREFETCH 1  // request the first row of the next item in the last row of the current one
 #endif
-constexpr int FT_HALVES = PB200_FT_HALVES;
-constexpr int FT_ROWGROUPS = PB200_FT_ROWGROUPS;
-constexpr int FT_ROWS_PER_WARP = 4;
-constexpr int FT_W = 128 * FT_HALVES;   // item width: one warp (32 lanes x 4 px) per 128-pixel half
-constexpr int FT_H = FT_ROWS_PER_WARP * FT_ROWGROUPS;     // item height
-constexpr int FT_THREADS = 32 * FT_ROWGROUPS * FT_HALVES;
-constexpr int FT_MIN_CTAS = PB200_FT_MIN_CTAS;
-// DEM staging: one TMA box per 128-pixel half (a box is at most 256 elements
-// wide).  Box start = dem_off_x + x0 + 128*half - padx with padx = 4 +
+constexpr int FT_W = 128;          // item width: one warp = 32 lanes x 4 pixels
+constexpr int FT_H = PB200_FT_H;   // item height
+template <bool FULL> struct FtGeom {
+    static constexpr int WARPS = FULL ? PB200_FT_WARPS_FULL : PB200_FT_WARPS_LEAN;
+    static constexpr int THREADS = 32 * WARPS;
+    static constexpr int ROWS_PER_WARP = FT_H / WARPS;
+    static_assert(FT_H % WARPS == 0, "a warp owns a whole number of rows of an item");
+};
+// DEM staging: one TMA box per item (a box is at most 256 elements wide and 256
+// rows high).  Box start = dem_off_x + x0 - padx with padx = 4 +
 // (dem_off_x & 3): a multiple of 4 floats (UTMALDG needs a 16-byte aligned box
 // start on B200, scripts/tma_probe.cu), one-column halo on each side.
 constexpr int FT_SMW = 136;        // 7 (max padx) + 128 + 1 = 136 floats = 544 B
@@ -117,7 +123,7 @@ struct __align__(128) DemHalf { float v[FT_SMH][FT_SMW]; };   // TMA destination
 constexpr uint32_t DEM_BOX_BYTES = FT_SMH * FT_SMW * sizeof(float);
 
 struct __align__(128) FastSmem {
-    DemHalf dem[2][FT_HALVES];          // double buffer: the DEM tile of item k + 1 streams in while item k is classified
+    DemHalf dem[2];                     // double buffer: the DEM tile of item k + 1 streams in while item k is classified
     uint32_t big_lut[2048];
     uint32_t diag_lut[128];
     uint8_t  fk_lut[4096];
@@ -224,7 +230,7 @@ __device__ __noinline__ uint32_t shadow_exact(float l, float r, float u, float d
 
 // ---------------------------------------------------------------------------
 template <bool OPTIONAL_LAYERS>
-__global__ void __launch_bounds__(FT_THREADS, OPTIONAL_LAYERS ? (FT_MIN_CTAS > 2 ? 2 : FT_MIN_CTAS) : FT_MIN_CTAS)
+__global__ void __launch_bounds__(FtGeom<OPTIONAL_LAYERS>::THREADS, 1)
 dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__restrict__ tmaps,
                        const FusedTables *__restrict__ tables, const ItemDesc *__restrict__ items, int n_items,
                        const __grid_constant__ DevParams P, const __grid_constant__ FastParams F) {
@@ -233,8 +239,8 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
     uint32_t sb = (uint32_t)__cvta_generic_to_shared(&s);    // shared address of the block, kept in a register
     asm volatile("mov.b32 %0, %0;" : "+r"(sb));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int half = warp % FT_HALVES;                    // which 128-pixel half of the item
-    const int rgrp = warp / FT_HALVES;                    // which group of 4 rows
+    constexpr int FT_THREADS = FtGeom<OPTIONAL_LAYERS>::THREADS, FT_ROWS_PER_WARP = FtGeom<OPTIONAL_LAYERS>::ROWS_PER_WARP;
+    const int rgrp = warp;                                // which group of rows of the item
 
     // ---- tables: once per CTA -------------------------------------------------
     {
@@ -290,11 +296,9 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
         if (PB200_FT_PRODUCER_WARP == 0 || lane == 0) {
             // generic-proxy reads of the buffer (ordered by the empty barrier) before the async-proxy writes
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(&s.full[b], (uint32_t)FT_HALVES * DEM_BOX_BYTES);
+            mbar_expect_tx(&s.full[b], DEM_BOX_BYTES);
             const int gx = s.tile.dem_off_x + d.tx * FT_W - padx, gy = s.tile.dem_off_y + d.ty * FT_H - 1;
-#pragma unroll
-            for (int hf = 0; hf < FT_HALVES; ++hf)
-                tma_load_2d(&s.dem[b][hf].v[0][0], &tmaps[d.tile], gx + 128 * hf, gy, &s.full[b]);
+            tma_load_2d(&s.dem[b].v[0][0], &tmaps[d.tile], gx, gy, &s.full[b]);
         }
         if (PB200_FT_PRODUCER_WARP) __syncwarp();
     };
@@ -357,7 +361,7 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
 
         bool dem_ready = !has_dem;
 
-        const int x = x0 + 128 * half + 4 * lane;         // this lane's 4 pixels
+        const int x = x0 + 4 * lane;                      // this lane's 4 pixels
         const int nrows = min(FT_ROWS_PER_WARP, H - (y0 + rgrp * FT_ROWS_PER_WARP));   // warp-uniform
         if (x < W && nrows > 0) {
             // ---- loads: 8 bytes per band, 4 bytes per byte raster.  The input registers of a row are dead
@@ -526,7 +530,7 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                     FT_LOAD_ROW(pix + (uint32_t)W);
                 } else if (PB200_FT_XITEM_PREFETCH && next.tile == cur_tile) {
                     // last row: first row of this warp in the next item of the CTA (same tile, same planes)
-                    const int xn = next.tx * FT_W + 128 * half + 4 * lane, yn = next.ty * FT_H + rgrp * FT_ROWS_PER_WARP;
+                    const int xn = next.tx * FT_W + 4 * lane, yn = next.ty * FT_H + rgrp * FT_ROWS_PER_WARP;
                     if (xn < W && yn < H) {
                         FT_LOAD_ROW((uint32_t)yn * (uint32_t)W + (uint32_t)xn);
                         row_loaded = true;
@@ -542,7 +546,7 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                         dem_ready = true;
                     }
                     // shared address of this lane's first pixel in the middle row of the 3-row window
-                    const uint32_t am = sb + FS_OFF(dem) + (buf * FT_HALVES + (uint32_t)half) * (uint32_t)sizeof(DemHalf) +
+                    const uint32_t am = sb + FS_OFF(dem) + buf * (uint32_t)sizeof(DemHalf) +
                                         4u * (uint32_t)((ly + 1) * FT_SMW + 4 * lane + padx);
                     constexpr uint32_t RB = 4u * FT_SMW;                      // bytes per row of the DEM tile
                     float m[6], u[4], d[4];
@@ -652,7 +656,7 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
         if (lane == 0) mbar_arrive(&s.empty[buf]);
         if (has_dem) fstate = (fstate ^ (1u << buf)) | (4u << buf);   // one transaction per item of a tile with a DEM
 
-        // histogram bins are 7 bits wide and an item adds at most 16 pixels per thread: flush every 4 items
+        // histogram bins are 7 bits wide and an item adds at most 24 pixels per thread: flush every 4 items
         if (histogram && (k & 3u) == 3u) flush_counters();
         item = next;
     }
