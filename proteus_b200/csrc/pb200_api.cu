@@ -418,7 +418,8 @@ static void build_fast_params(const pb200_params *p, const DevParams &D, FastPar
     F->kx = 0.5f / D.dxf;
     F->ky = 0.5f / D.dyf;
     const bool ok = std::isfinite(D.cos_thr) && std::fabs(D.cos_thr) <= 1.0 && std::isfinite(D.tan_thr) &&
-                    std::fabs(D.tan_thr) < 1e6 && std::isfinite(F->kx) && std::isfinite(F->ky);
+                    std::fabs(D.tan_thr) < 1e6 && std::isfinite(F->kx) && std::isfinite(F->ky) &&
+                    std::fabs(D.dxf) == std::fabs(D.dyf);     // square pixels: the shortcut shares kx^2 = ky^2
     F->fast_shadow_ok = ok ? 1u : 0u;
     F->tan32 = ok ? (float)D.tan_thr : 0.0f;
     F->e0 = 1e-6f * std::fabs(F->tan32) + 1e-30f;

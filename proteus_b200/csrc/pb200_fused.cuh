@@ -154,15 +154,16 @@ __device__ __forceinline__ void stg_stream_v4(void *p, uint32_t a, uint32_t b, u
 // boundary (or not finite): the caller then runs the exact float64 sequence.
 // Error budget in DESIGN.md section 3.
 // per-tile float32 constants of the shortcut (FastSmem::sun32), from the float64 sun terms:
-enum { SK_SA = 0, SK_CA, SK_SX, SK_SY, SK_SZ, SK_XX, SK_YY, SK_EA, SK_EB, SK_N };
-//   kx*sin_az, ky*cos_az, kx*sx, ky*sy, sz, kx*kx, ky*ky, 1e-6*|kx*sin_az|, 1e-6*|ky*cos_az|   (kx = 0.5/dx, ky = 0.5/dy)
+enum { SK_SA = 0, SK_CA, SK_SX, SK_SY, SK_SZ, SK_XX, SK_EA, SK_EB, SK_N };
+//   kx*sin_az, ky*cos_az, kx*sx, ky*sy, sz, kx*kx (= ky*ky: square pixels, else fast_shadow_ok = 0),
+//   1e-6*|kx*sin_az|, 1e-6*|ky*cos_az|   (kx = 0.5/dx, ky = 0.5/dy)
 __device__ __forceinline__ uint32_t shadow_fast(float l, float r, float u, float d, const FastParams &F,
                                                 const float (&K)[SK_N], bool *undecided) {
     const float a = l - r, b = u - d;                     // -2 g_col, -2 g_row: the reference's own float32 differences
     const float diff = fmaf(a, K[SK_SA], fmaf(b, K[SK_CA], -F.tan32));          // ~ s - tan_thr
     const float e = fmaf(fabsf(a), K[SK_EA], fmaf(fabsf(b), K[SK_EB], F.e0));   // 1e-6 (|t1| + |t2|) + e0
     const float dot = fmaf(a, K[SK_SX], fmaf(b, K[SK_SY], K[SK_SZ]));
-    const float v = fmaf(a * a, K[SK_XX], fmaf(b * b, K[SK_YY], 1.0f));         // ~ nf^2
+    const float v = fmaf(fmaf(a, a, b * b), K[SK_XX], 1.0f);                    // ~ nf^2 = 1 + k^2 (a^2 + b^2)
     const float L = dot * fabsf(dot);                     // t -> t|t| is monotone: x >= c for any sign of c
     const float D = fmaf(-F.cc32, v, L);
     const float eg = 4e-6f * v;
@@ -334,7 +335,7 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                 const double kx = 0.5 / (double)P.dxf, ky = 0.5 / (double)P.dyf;
                 s.sun32[SK_SA] = (float)(kx * g.sin_az); s.sun32[SK_CA] = (float)(ky * g.cos_az);
                 s.sun32[SK_SX] = (float)(kx * g.sx); s.sun32[SK_SY] = (float)(ky * g.sy); s.sun32[SK_SZ] = (float)g.sz;
-                s.sun32[SK_XX] = (float)(kx * kx); s.sun32[SK_YY] = (float)(ky * ky);
+                s.sun32[SK_XX] = (float)(kx * kx);
                 s.sun32[SK_EA] = 1e-6f * fabsf(s.sun32[SK_SA]); s.sun32[SK_EB] = 1e-6f * fabsf(s.sun32[SK_CA]);
             }
             cur_tile = item.tile;
@@ -571,7 +572,7 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                     {
                         const float4 k0 = lds_f32x4(sb + FS_OFF(sun32)), k1 = lds_f32x4(sb + FS_OFF(sun32) + 16);
                         K[0] = k0.x; K[1] = k0.y; K[2] = k0.z; K[3] = k0.w; K[4] = k1.x; K[5] = k1.y; K[6] = k1.z; K[7] = k1.w;
-                        K[8] = lds_f32(sb + FS_OFF(sun32) + 32);
+                        static_assert(SK_N == 8, "two 16-byte loads");
                     }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) shw[j] = shadow_fast(m[j], m[j + 2], u[j], d[j], F, K, &undecided);

@@ -494,3 +494,21 @@ def test_otsu_threshold_dropin(pb):
     assert np.array_equal(counts.cpu().numpy(), np.bincount(imgs[-1].ravel(), minlength=256))
     with pytest.raises(NotImplementedError):
         G._compute_otsu_threshold(imgs[0].astype(np.float32))
+
+
+def test_non_square_pixels_run_the_exact_shadow_sequence(pb):
+    """The float32 shadow shortcut assumes square pixels; any other spacing sends every pixel through the exact
+    float64 sequence of the fused kernel (the reference itself always uses 30 m x 30 m, dswx_hls.py:5161)."""
+    t = synth.make_tile(31, 96, 256)
+    m = t['dem_margin']
+    for spacing in ((30, 20), (10, 30)):
+        params = pb.make_params(pixel_spacing=spacing, collapse_wtr_classes=False)
+        got = pb.classify_tile(t['bands'], t['fmask'], t['dem'], t['land'], t['ocean'], t['sun_azimuth'],
+                               t['sun_elevation'], params=params, outputs=('SHAD', 'WTR2', 'WTR'))
+        shad = O.compute_opera_shadow_layer(t['dem'], t['sun_azimuth'], t['sun_elevation'], -5, 40, *spacing)
+        shad = O.crop_2d_array_all_sides(shad, m)
+        assert np.array_equal(got['SHAD'].astype(bool), shad), spacing
+        ref = O.reference_chain(t['bands'], t['fmask'], None, t['land'], t['ocean'], t['sun_azimuth'], t['sun_elevation'])
+        w1 = ref['WTR1_REMAPPED']
+        w2 = O.apply_landcover_and_shadow_masks(w1, np.clip(t['bands'][3], 1, None), t['land'], shad, O.default_thresholds())
+        assert np.array_equal(got['WTR2'], w2), spacing
