@@ -512,3 +512,39 @@ def test_non_square_pixels_run_the_exact_shadow_sequence(pb):
         w1 = ref['WTR1_REMAPPED']
         w2 = O.apply_landcover_and_shadow_masks(w1, np.clip(t['bands'][3], 1, None), t['land'], shad, O.default_thresholds())
         assert np.array_equal(got['WTR2'], w2), spacing
+
+
+def test_full_size_mosaic_strips_equal_the_whole_raster(pb):
+    """BASELINE config 5 at full size (21 960 x 21 960 px, DEM 22 060 x 22 060): the raster classified as 8 row strips
+    (each with its own DEM rows and one halo row per neighbour, as 8 ranks hold it) equals the raster classified as
+    one tile - every graded layer bit for bit, counters summed; plus layer relations the oracle defines."""
+    import torch
+    from proteus_b200 import mosaic
+    size, m, world = 21960, 50, 8
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 * 2 ** 30:
+        pytest.skip('needs 40 GB of free device memory')
+    t = synth.make_device_batch(1, size, size, device='cuda', seed=77, n_distinct=1)[0]
+    params = pb.make_params(collapse_wtr_classes=True)
+    whole = pb.Plan([t], params, pb.GRADED_LAYERS)
+    whole.run()
+    torch.cuda.synchronize()
+    ref = whole.outputs[0]
+    ref_counters = whole.counters[0].clone()
+    summed = torch.zeros_like(ref_counters)
+    for rank, (r0, r1) in enumerate(mosaic.strip_bounds(size, world)):
+        d0, d1 = mosaic.dem_rows_for_strip(r0, r1, size, m)
+        strip = mosaic.MosaicStrip([b[r0:r1] for b in t['bands']], t['fmask'][r0:r1], t['dem'][d0:d1].clone(),
+                                   t['land'][r0:r1], t['ocean'][r0:r1], r0, r1, size,
+                                   sun_azimuth=t['sun_azimuth'], sun_elevation=t['sun_elevation'],
+                                   params=params, outputs=pb.GRADED_LAYERS, rank=rank, world=world)
+        strip.run(halo=(t['dem'][m + r0 - 1] if rank > 0 else None, t['dem'][m + r1] if rank < world - 1 else None))
+        torch.cuda.synchronize()
+        for name in pb.GRADED_LAYERS:
+            assert torch.equal(strip.outputs[name], ref[name][r0:r1]), (name, rank)
+        summed += strip.counters.reshape(-1)[:summed.numel()]
+        del strip
+    assert torch.equal(summed[:3], ref_counters[:3])
+    wtr, bwtr = ref['WTR'], ref['BWTR']
+    assert torch.equal(torch.where((wtr >= 1) & (wtr <= 2), torch.ones_like(wtr), wtr), bwtr)      # D:1727 on collapsed WTR
+    assert int(ref_counters[0]) == int(((ref['DIAG'].view(torch.int16) != -1) & (t['ocean'] != 0)).sum())
