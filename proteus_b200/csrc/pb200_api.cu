@@ -1347,7 +1347,7 @@ extern "C" int pb200_byte_table(pb200_ctx *ctx, const uint8_t *in, int64_t n, co
     if (n == 0) return 0;
     ByteTable T;
     std::memcpy(T.v, table, 256);
-    byte_table_kernel<<<grid_for(ctx, (n + 3) / 4, 256), 256, 0, st>>>(in, out, n, T);
+    byte_table_kernel<<<grid_for(ctx, (n + 15) / 16, 256), 256, 0, st>>>(in, out, n, T);
     LEAVE();
 }
 
@@ -1358,7 +1358,7 @@ extern "C" int pb200_scale_offset(pb200_ctx *ctx, const int16_t *band, int64_t n
     REQUIRE(band && out && n >= 0, "pb200_scale_offset: bad argument");
     if (n == 0) return 0;
     // Python-float scalars are "weak" in numpy: both are rounded to float32 before the float32 array operation
-    scale_offset_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(band, invalid, out, n, (float)scale, (float)offset);
+    scale_offset_kernel<<<grid_for(ctx, (n + 7) / 8, 256), 256, 0, st>>>(band, invalid, out, n, (float)scale, (float)offset);
     LEAVE();
 }
 
@@ -1448,7 +1448,7 @@ extern "C" int pb200_greater_than_u8(pb200_ctx *ctx, const uint8_t *image, int64
     // x > t for integer x: x >= floor(t) + 1
     const double lim = std::floor(threshold) + 1.0;
     const int limit = lim < 0.0 ? 0 : (lim > 256.0 ? 256 : (int)lim);
-    greater_than_u8_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(image, out, n, limit);
+    greater_than_u8_kernel<<<grid_for(ctx, (n + 15) / 16, 256), 256, 0, st>>>(image, out, n, limit);
     LEAVE();
 }
 

@@ -250,6 +250,15 @@ __device__ __forceinline__ uint32_t ldg_stream_u32(const void *p) {
 __device__ __forceinline__ void stg_stream_u32(void *p, uint32_t v) {
     asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v));
 }
+__device__ __forceinline__ int4 ldg_stream_v4(const void *p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream_v4(void *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d));
+}
 __device__ __forceinline__ void stg_stream_v2(void *p, uint32_t a, uint32_t b) {
     asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b));
 }

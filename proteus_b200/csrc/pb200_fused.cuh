@@ -138,15 +138,6 @@ struct __align__(128) FastSmem {
 __device__ __forceinline__ int sext_lo(uint32_t x) { return (int)(short)(x & 0xffffu); }
 __device__ __forceinline__ int sext_hi(uint32_t x) { return ((int)x) >> 16; }
 
-__device__ __forceinline__ int4 ldg_stream_v4(const void *p) {
-    int4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ void stg_stream_v4(void *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d));
-}
 
 // float32 shortcut of the shadow test (branch-free).  Returns 0x200 (the big_lut
 // index bit) when the pixel is CERTAINLY in terrain shadow, 0 when it is

@@ -52,7 +52,10 @@ inv = (torch.rand((S, S), device='cuda', generator=g) < 0.02).to(torch.uint8)
 report('scale_offset', timed(lambda: _lib.check(lib.pb200_scale_offset(ctx.handle, b16.data_ptr(), n, 1e-4, 0.0, inv.data_ptr(), f32.data_ptr(), sp))), 2 * n + n + 4 * n)
 hill = torch.randint(0, 256, (S + 100, S + 100), dtype=torch.uint8, device='cuda', generator=g); cnt = torch.zeros(256, dtype=torch.int64, device='cuda')
 report('histogram_u8 (otsu)', timed(lambda: _lib.check(lib.pb200_histogram_u8(ctx.handle, hill.data_ptr(), hill.numel(), cnt.data_ptr(), sp))), hill.numel(),
-       'uniform random bytes: worst case for shared-memory atomics is a constant image')
+       'uniform random bytes: one shared-memory atomic per pixel')
+smooth = (torch.arange(hill.numel(), device='cuda') // 4096 % 256).to(torch.uint8).reshape(hill.shape)
+report('histogram_u8 (otsu), smooth raster', timed(lambda: _lib.check(lib.pb200_histogram_u8(ctx.handle, smooth.data_ptr(), smooth.numel(), cnt.data_ptr(), sp))), smooth.numel(),
+       'runs of 4096 equal bytes: a warp holding one value adds once')
 mask = torch.empty_like(hill)
 report('greater_than_u8 (otsu)', timed(lambda: _lib.check(lib.pb200_greater_than_u8(ctx.handle, hill.data_ptr(), hill.numel(), 127.5, mask.data_ptr(), sp))), 2 * hill.numel())
 
