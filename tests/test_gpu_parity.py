@@ -548,3 +548,42 @@ def test_full_size_mosaic_strips_equal_the_whole_raster(pb):
     wtr, bwtr = ref['WTR'], ref['BWTR']
     assert torch.equal(torch.where((wtr >= 1) & (wtr <= 2), torch.ones_like(wtr), wtr), bwtr)      # D:1727 on collapsed WTR
     assert int(ref_counters[0]) == int(((ref['DIAG'].view(torch.int16) != -1) & (t['ocean'] != 0)).sum())
+
+
+def test_full_size_l30_minimal_fused_equals_function_chain(pb):
+    """BASELINE config 1 at full size (3660 x 3660, no DEM / LAND / ocean, outputs DIAG + WTR): the fused fast kernel
+    against the chain of function-granular kernels called in the reference's order (D:5088-5369) - two independent
+    code paths over the same 13.4 Mpixel."""
+    import torch
+    import proteus_b200.dswx_hls as G
+    t = synth.make_device_batch(1, 3660, 3660, device='cuda', seed=5, n_distinct=1, full_product=False)[0]
+    assert t.get('dem') is None and t.get('land') is None and t.get('ocean') is None
+    plan = pb.Plan([t], pb.make_params(collapse_wtr_classes=False), ('DIAG', 'WTR'))
+    plan.run()
+    got = plan.results(0)
+    raw = [b.cpu().numpy() for b in t['bands']]
+    fmask = t['fmask'].cpu().numpy()
+    invalid = fmask == 255
+    for b in raw:
+        invalid |= b == -9999                                                       # D:2203-2209
+    bands = [np.clip(b, 1, None) for b in raw]                                      # D:2298-2299
+    th = G.HlsThresholds()
+    diag = G._compute_diagnostic_tests(*bands, th)
+    diag[invalid] = 32                                                              # D:5227
+    wtr1 = G.generate_interpreted_layer(diag)
+    wtr1[invalid] = 255                                                             # D:5249
+    cloud = G._compute_preliminary_cloud_layer(fmask, 'mask')
+    pr = O.default_processing()
+    G._apply_aerosol_class_remapping(
+        wtr1, bands[3], cloud, fmask,
+        pr['aerosol_not_water_to_high_conf_water_fmask_values'],
+        pr['aerosol_water_moderate_conf_to_high_conf_water_fmask_values'],
+        pr['aerosol_partial_surface_water_conservative_to_high_conf_water_fmask_values'],
+        pr['aerosol_partial_surface_aggressive_to_high_conf_water_fmask_values'])
+    wtr2 = G._apply_landcover_and_shadow_masks(wtr1, bands[3], None, None, th)
+    cloud = G._add_snow_to_cloud_layer(wtr2, cloud, fmask, 'mask')
+    wtr = G._apply_cloud_masking(wtr2, cloud)
+    assert np.array_equal(got['DIAG'], G._get_binary_representation(diag))
+    assert np.array_equal(got['WTR'], wtr)
+    cov = got['coverage']
+    assert cov['n_valid'] == int((~invalid).sum())
