@@ -22,8 +22,7 @@ import threading
 import numpy as np
 
 from . import _lib
-from .params import (DEM_MARGIN_IN_PIXELS, HlsThresholds, make_params,
-                     sun_terms)
+from .params import DEM_MARGIN_IN_PIXELS, make_params, sun_terms
 
 LAYERS = ('DIAG', 'WTR1', 'WTR1_REMAPPED', 'WTR2', 'CLOUD', 'SHAD', 'WTR',
           'BWTR', 'CONF')

@@ -128,9 +128,6 @@ class MosaicStrip:
             outs = {k: v[a:b] for k, v in self.outputs.items()}
             return t, outs
 
-        pieces = []
-        if n > 2:
-            pieces.append(('interior', (1, n - 1)))
         edge_rows = [(0, 1)] + ([(n - 1, n)] if n > 1 else [])
         self._interior = None
         if n > 2:
