@@ -467,7 +467,7 @@ def run_ours(args):
                          'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                          'algorithmic_bytes_per_launch': algo_bytes, 'kernel_ms': kernel_ms,
                          'frac_of_nominal_8TBs': achieved / 8000.0,
-                         'kernel': 'pb200::dswx_fused_fast_kernel<false>'},
+                         'kernel': 'pb200::dswx_fused_fast_kernel<false, true>'},
             'e2e': e2e, 'cpu_baseline': cpu_baseline, 'parity': parity,
             'gpu_launches': args.steps, 'clocks': clocks,
         }

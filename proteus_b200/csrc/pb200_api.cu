@@ -485,6 +485,7 @@ struct pb200_plan {
     ItemDesc *d_items = nullptr;
     int n_items = 0;
     bool fast_optional = false;                      // some fast tile wants WTR-1 / WTR-2 / CLOUD / SHAD
+    bool fast_all_graded = true;                     // every fast tile writes DIAG, WTR, BWTR and CONF
     bool stream_ordered = false;                     // allocated with cudaMallocAsync
     bool from_arena = false;                         // allocated from a caller-owned arena: nothing to free
     // per input tile: where it went (for launching one tile of the plan on its own)
@@ -674,10 +675,11 @@ static int plan_build(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles, cons
             const uint32_t slot = (uint32_t)td[G_FAST].size();
             for (int ty = 0; ty < nty; ++ty)
                 for (int tx = 0; tx < ntx; ++tx) items.push_back(ItemDesc{slot, (uint16_t)tx, (uint16_t)ty});
-            // the lean kernel variant assumes the four graded layers and the counters; anything else -> full variant
-            if (d.wtr1 || d.wtr1r || d.wtr2 || d.cloud || d.shad || params->class_histogram || !d.diag || !d.wtr ||
-                !d.bwtr || !d.conf || !d.counters)
+            // the lean kernel variant writes any subset of the four graded layers and assumes the counters;
+            // anything else -> full variant
+            if (d.wtr1 || d.wtr1r || d.wtr2 || d.cloud || d.shad || params->class_histogram || !d.counters)
                 pl->fast_optional = true;
+            if (!d.diag || !d.wtr || !d.bwtr || !d.conf) pl->fast_all_graded = false;
         }
         pl->item_end.push_back((int)items.size());
         td[g].push_back(d);
@@ -730,6 +732,8 @@ static int fast_kernel_setup(pb200_ctx *ctx) {
                                 (int)FAST_DYN_SMEM));
         CK(cudaFuncSetAttribute(dswx_fused_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)FAST_DYN_SMEM));
+        CK(cudaFuncSetAttribute(dswx_fused_fast_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)FAST_DYN_SMEM));
     }
     int nb = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dswx_fused_fast_kernel<false>, FtGeom<false>::THREADS, FAST_DYN_SMEM));
@@ -748,6 +752,9 @@ static int plan_launch(pb200_plan *pl, cudaStream_t stream) {
                                                                                        : pl->ctx->fast_ctas_per_sm));
         if (pl->fast_optional)
             dswx_fused_fast_kernel<true><<<grid, FtGeom<true>::THREADS, FAST_DYN_SMEM, stream>>>(
+                pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, pl->d_items, pl->n_items, pl->P, pl->F);
+        else if (pl->fast_all_graded)
+            dswx_fused_fast_kernel<false, true><<<grid, FtGeom<false>::THREADS, FAST_DYN_SMEM, stream>>>(
                 pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, pl->d_items, pl->n_items, pl->P, pl->F);
         else
             dswx_fused_fast_kernel<false><<<grid, FtGeom<false>::THREADS, FAST_DYN_SMEM, stream>>>(
@@ -777,6 +784,9 @@ static int plan_launch_tile(pb200_plan *pl, int i, cudaStream_t stream) {
         const ItemDesc *it = pl->d_items + pl->item_start[i];
         if (pl->fast_optional)
             dswx_fused_fast_kernel<true><<<grid, FtGeom<true>::THREADS, FAST_DYN_SMEM, stream>>>(
+                pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, it, n, pl->P, pl->F);
+        else if (pl->fast_all_graded)
+            dswx_fused_fast_kernel<false, true><<<grid, FtGeom<false>::THREADS, FAST_DYN_SMEM, stream>>>(
                 pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, it, n, pl->P, pl->F);
         else
             dswx_fused_fast_kernel<false><<<grid, FtGeom<false>::THREADS, FAST_DYN_SMEM, stream>>>(

@@ -221,7 +221,10 @@ __device__ __noinline__ uint32_t shadow_exact(float l, float r, float u, float d
 }
 
 // ---------------------------------------------------------------------------
-template <bool OPTIONAL_LAYERS>
+// ALL_GRADED: the tile batch writes all four graded layers (the product's configuration): no pointer tests in the row
+// loop.  The lean kernel is also instantiated without it for subsets such as DIAG + WTR (BASELINE configs[0]); a
+// run-time test in the one instantiation measured 2.5 % slower on the full product.
+template <bool OPTIONAL_LAYERS, bool ALL_GRADED = false>
 __global__ void __launch_bounds__(FtGeom<OPTIONAL_LAYERS>::THREADS, 1)
 dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__restrict__ tmaps,
                        const FusedTables *__restrict__ tables, const ItemDesc *__restrict__ items, int n_items,
@@ -349,7 +352,7 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
         }
         const bool want_shad = OPTIONAL_LAYERS && s.tile.shad != nullptr;
         // the four graded layers present: one test instead of four in the row loop
-        const bool all_graded = !OPTIONAL_LAYERS || (s.tile.diag && s.tile.wtr && s.tile.bwtr && s.tile.conf);
+        const bool all_graded = ALL_GRADED || (s.tile.diag && s.tile.wtr && s.tile.bwtr && s.tile.conf);
 
         bool dem_ready = !has_dem;
 
