@@ -158,6 +158,15 @@ int  pb200_plan_destroy(pb200_plan *plan);
  * memory.  Buffers from pb200_host_alloc (pinned) copy at full PCIe rate. */
 int  pb200_classify_host(pb200_ctx *ctx, const pb200_tile *host_tile,
                          const pb200_params *params, int strip_rows);
+/* Time series (BASELINE configs[3]: many acquisitions of one MGRS tile share DEM, LAND and ocean mask): with
+ * PB200_HOST_REUSE_ANCILLARY the DEM / LAND / ocean rasters uploaded by the previous successful pb200_classify_host*
+ * call on this context are used again and not copied - only the bands and Fmask cross PCIe (174 MB instead of 256 MB
+ * per HLS tile).  The tile must have the same size, DEM geometry and the same rasters present as that call
+ * (PB200_E_INVALID_ARG otherwise); that their CONTENT is unchanged is the caller's statement.  flags = 0 is
+ * pb200_classify_host. */
+#define PB200_HOST_REUSE_ANCILLARY 1
+int  pb200_classify_host_ex(pb200_ctx *ctx, const pb200_tile *host_tile,
+                            const pb200_params *params, int strip_rows, int flags);
 int  pb200_host_alloc(size_t bytes, void **out);
 int  pb200_host_free(void *p);
 

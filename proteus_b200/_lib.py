@@ -20,7 +20,7 @@ E_INVALID_ARG, E_BAD_MODE, E_UNSUPPORTED, E_NO_DRIVER_API, E_ALIGNMENT = -1, -2,
 EXPORTS = (
     'pb200_version', 'pb200_last_error', 'pb200_ctx_create', 'pb200_ctx_destroy',
     'pb200_params_default', 'pb200_classify', 'pb200_plan_create',
-    'pb200_plan_run', 'pb200_plan_destroy', 'pb200_classify_host',
+    'pb200_plan_run', 'pb200_plan_destroy', 'pb200_classify_host', 'pb200_classify_host_ex',
     'pb200_host_alloc', 'pb200_host_free', 'pb200_invalid_and_clip',
     'pb200_diagnostic_tests', 'pb200_diagnostic_tests_f32', 'pb200_interpreted_layer',
     'pb200_binary_representation', 'pb200_preliminary_cloud',
@@ -122,6 +122,7 @@ def load():
     lib.pb200_plan_run.argtypes = [C.c_void_p, C.c_void_p]
     lib.pb200_plan_destroy.argtypes = [C.c_void_p]
     lib.pb200_classify_host.argtypes = [C.c_void_p, C.POINTER(Tile), C.POINTER(Params), C.c_int]
+    lib.pb200_classify_host_ex.argtypes = [C.c_void_p, C.POINTER(Tile), C.POINTER(Params), C.c_int, C.c_int]
     lib.pb200_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
     lib.pb200_host_free.argtypes = [C.c_void_p]
     P6 = C.c_void_p * 6

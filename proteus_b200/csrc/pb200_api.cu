@@ -456,6 +456,9 @@ struct HostPipe {               // device mirror of one host tile (pb200_classif
     Arena arena;                        // strip descriptors, tensor maps, item list
     cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_k;
+    // ancillary rasters left on the device by the last successful call (PB200_HOST_REUSE_ANCILLARY)
+    bool anc_valid = false, anc_dem = false, anc_land = false, anc_ocean = false;
+    int anc_h = 0, anc_w = 0, anc_dem_rows = 0, anc_dem_pitch = 0, anc_dem_off_y = 0, anc_dem_off_x = 0;
 };
 
 struct pb200_ctx {
@@ -903,7 +906,14 @@ static int pipe_reserve(HostPipe &p, size_t px, size_t dem_elems) {
 
 extern "C" int pb200_classify_host(pb200_ctx *ctx, const pb200_tile *ht, const pb200_params *params,
                                    int strip_rows) {
+    return pb200_classify_host_ex(ctx, ht, params, strip_rows, 0);
+}
+
+extern "C" int pb200_classify_host_ex(pb200_ctx *ctx, const pb200_tile *ht, const pb200_params *params,
+                                      int strip_rows, int flags) {
     if (!ctx || !ht || !params) return fail(PB200_E_INVALID_ARG, "pb200_classify_host: null argument");
+    if (flags & ~PB200_HOST_REUSE_ANCILLARY) return fail(PB200_E_INVALID_ARG, "pb200_classify_host_ex: unknown flag");
+    const bool reuse = (flags & PB200_HOST_REUSE_ANCILLARY) != 0;
     std::lock_guard<std::mutex> lock(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     const int H = ht->height, W = ht->width;
@@ -913,6 +923,16 @@ extern "C" int pb200_classify_host(pb200_ctx *ctx, const pb200_tile *ht, const p
     const size_t px = (size_t)H * W;
     const size_t dem_elems = ht->dem ? (size_t)ht->dem_rows * ht->dem_pitch : 0;
     HostPipe &p = ctx->pipe;
+    if (reuse) {
+        const bool same = p.anc_valid && p.anc_h == H && p.anc_w == W && p.anc_dem == (ht->dem != nullptr) &&
+                          p.anc_land == (ht->land != nullptr) && p.anc_ocean == (ht->ocean != nullptr) &&
+                          (!ht->dem || (p.anc_dem_rows == ht->dem_rows && p.anc_dem_pitch == ht->dem_pitch &&
+                                        p.anc_dem_off_y == ht->dem_off_y && p.anc_dem_off_x == ht->dem_off_x));
+        if (!same)
+            return fail(PB200_E_INVALID_ARG, "pb200_classify_host_ex: PB200_HOST_REUSE_ANCILLARY needs a previous "
+                        "successful call on this context with the same tile size, DEM geometry and rasters present");
+    }
+    p.anc_valid = false;                                  // until this call has succeeded
     int rc = pipe_reserve(p, px, dem_elems);
     if (rc) return rc;
     // PB200_PIPE_TRACE=1: print where the time of this call went (host stages, H2D / kernel / D2H spans)
@@ -959,9 +979,9 @@ extern "C" int pb200_classify_host(pb200_ctx *ctx, const pb200_tile *ht, const p
             for (int k = 0; k < 6; ++k)
                 CK(cudaMemcpyAsync(p.band[k] + off, ht->band[k] + off, cnt * 2, cudaMemcpyHostToDevice, p.s_in));
             CK(cudaMemcpyAsync(p.fmask + off, ht->fmask + off, cnt, cudaMemcpyHostToDevice, p.s_in));
-            if (ht->land) CK(cudaMemcpyAsync(p.land + off, ht->land + off, cnt, cudaMemcpyHostToDevice, p.s_in));
-            if (ht->ocean) CK(cudaMemcpyAsync(p.ocean + off, ht->ocean + off, cnt, cudaMemcpyHostToDevice, p.s_in));
-            if (ht->dem) {
+            if (ht->land && !reuse) CK(cudaMemcpyAsync(p.land + off, ht->land + off, cnt, cudaMemcpyHostToDevice, p.s_in));
+            if (ht->ocean && !reuse) CK(cudaMemcpyAsync(p.ocean + off, ht->ocean + off, cnt, cudaMemcpyHostToDevice, p.s_in));
+            if (ht->dem && !reuse) {
                 int d0 = ht->dem_off_y + r0 - 1, d1 = ht->dem_off_y + r1 + 1;     // rows the strip's stencil reads
                 if (!first_dem) d0 = std::max(d0, dem_copied);
                 d0 = std::max(d0, 0);
@@ -1063,6 +1083,11 @@ extern "C" int pb200_classify_host(pb200_ctx *ctx, const pb200_tile *ht, const p
     if (trace) { CK(cudaEventRecord(tr[3], p.s_out)); }
     CK(cudaStreamSynchronize(p.s_out));
     CK(cudaStreamSynchronize(p.s_k));
+    p.anc_valid = true;
+    p.anc_h = H; p.anc_w = W;
+    p.anc_dem = ht->dem != nullptr; p.anc_land = ht->land != nullptr; p.anc_ocean = ht->ocean != nullptr;
+    p.anc_dem_rows = ht->dem_rows; p.anc_dem_pitch = ht->dem_pitch;
+    p.anc_dem_off_y = ht->dem_off_y; p.anc_dem_off_x = ht->dem_off_x;
     if (trace) {
         float h2d = 0, k_end = 0, out_end = 0;
         cudaEventElapsedTime(&h2d, tr[0], tr[1]);

@@ -385,7 +385,7 @@ def classify_tile(bands, fmask, dem_with_margin=None, landcover_mask=None,
                   ocean_mask=None, sun_azimuth_angle=0.0,
                   sun_elevation_angle=90.0, hls_thresholds=None, *,
                   outputs=ALL_LAYERS, params=None, dem_margin=DEM_MARGIN_IN_PIXELS,
-                  dem_off=None, out=None, strip_rows=0, ctx=None,
+                  dem_off=None, out=None, strip_rows=0, ctx=None, reuse_ancillary=False,
                   **processing):
     """Classify one tile held in host memory.
 
@@ -398,6 +398,10 @@ def classify_tile(bands, fmask, dem_with_margin=None, landcover_mask=None,
     ``apply_aerosol_class_remapping``, ``aerosol_fmask_values``,
     ``min_slope_angle``, ``max_sun_local_inc_angle``, ``band_fill``,
     ``fmask_fill``, ``collapse_wtr_classes``, ``class_histogram``.
+
+    ``reuse_ancillary=True`` (time series: the next acquisition of the same MGRS tile): the DEM, LAND and ocean
+    rasters the previous call on this context uploaded are used again, only bands and Fmask are copied; the arrays
+    must still be passed (same shapes) and be unchanged.
 
     Returns a dict: requested layers (numpy, pinned), 'counters' (uint64[12])
     and 'coverage' (the three percentages of D:5115-5124)."""
@@ -463,8 +467,8 @@ def classify_tile(bands, fmask, dem_with_margin=None, landcover_mask=None,
                sun=(sun_azimuth_angle, sun_elevation_angle),
                out_ptrs={k: v.ctypes.data for k, v in res.items()},
                counters_ptr=counters.ctypes.data)
-    _lib.check(ctx._lib.pb200_classify_host(ctx.handle, C.byref(tile), C.byref(params),
-                                            int(strip_rows)))
+    _lib.check(ctx._lib.pb200_classify_host_ex(ctx.handle, C.byref(tile), C.byref(params), int(strip_rows),
+                                               1 if reuse_ancillary else 0))
     res['counters'] = counters
     res['coverage'] = counters_to_dict(counters, h * w, ocean_mask is not None)
     return res

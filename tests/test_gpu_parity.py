@@ -587,3 +587,32 @@ def test_full_size_l30_minimal_fused_equals_function_chain(pb):
     assert np.array_equal(got['WTR'], wtr)
     cov = got['coverage']
     assert cov['n_valid'] == int((~invalid).sum())
+
+
+def test_host_path_reuses_resident_ancillary_rasters(pb):
+    """Time series (BASELINE configs[3]): the second acquisition of a tile reuses the DEM / LAND / ocean rasters the
+    first call left on the device (reuse_ancillary=True) and still matches the oracle; a call that does not fit the
+    resident rasters is refused."""
+    from proteus_b200 import _lib
+    a = synth.make_tile(41, 200, 264)
+    b = synth.make_tile(42, 200, 264)
+    b['dem'], b['land'], b['ocean'] = a['dem'], a['land'], a['ocean']            # same MGRS tile, other acquisition
+    first = pb.classify_tile(a['bands'], a['fmask'], a['dem'], a['land'], a['ocean'], a['sun_azimuth'],
+                             a['sun_elevation'], collapse_wtr_classes=False)
+    ref_a = O.reference_chain(a['bands'], a['fmask'], a['dem'], a['land'], a['ocean'], a['sun_azimuth'], a['sun_elevation'])
+    _assert_layers(first, ref_a, FUSED_LAYERS, 'first acquisition')
+    # poison the host copies: a re-upload would now change the result
+    poisoned = dict(dem=np.zeros_like(a['dem']), land=np.full_like(a['land'], 255), ocean=np.ones_like(a['ocean']))
+    second = pb.classify_tile(b['bands'], b['fmask'], poisoned['dem'], poisoned['land'], poisoned['ocean'],
+                              b['sun_azimuth'], b['sun_elevation'], collapse_wtr_classes=False, reuse_ancillary=True)
+    ref_b = O.reference_chain(b['bands'], b['fmask'], a['dem'], a['land'], a['ocean'], b['sun_azimuth'], b['sun_elevation'])
+    _assert_layers(second, ref_b, FUSED_LAYERS, 'second acquisition, resident ancillary')
+    assert np.array_equal(second['counters'][:3], ref_b['counters'])
+    c = synth.make_tile(43, 96, 128)
+    with pytest.raises(_lib.Pb200Error):
+        pb.classify_tile(c['bands'], c['fmask'], c['dem'], c['land'], c['ocean'], c['sun_azimuth'], c['sun_elevation'],
+                         reuse_ancillary=True)
+    # a refused call uploads nothing and leaves the resident rasters usable
+    third = pb.classify_tile(b['bands'], b['fmask'], poisoned['dem'], poisoned['land'], poisoned['ocean'],
+                             b['sun_azimuth'], b['sun_elevation'], collapse_wtr_classes=False, reuse_ancillary=True)
+    _assert_layers(third, ref_b, FUSED_LAYERS, 'after a refused call')
