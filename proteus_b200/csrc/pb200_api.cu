@@ -1035,7 +1035,7 @@ extern "C" int pb200_classify_host_ex(pb200_ctx *ctx, const pb200_tile *ht, cons
         for (int i = 0; i < 8; ++i)
             if (*sf[i]) *sf[i] += off;
     }
-    // worst case per strip: descriptor + tensor map + one item per 128 x 32 pixels
+    // worst case per strip: descriptor + tensor map + one item per FT_W x FT_H pixels
     {
         const size_t items_max = (size_t)((W + FT_W - 1) / FT_W) * (size_t)((H + FT_H - 1) / FT_H + n_strips);
         const size_t need = (size_t)n_strips * (sizeof(TileDev) + sizeof(CUtensorMap) + 1024) +

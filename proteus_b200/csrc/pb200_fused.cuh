@@ -8,7 +8,7 @@
 //
 //  * a lane owns 4 consecutive pixels of a row (one 8-byte load per band - row
 //    pitch 3660 * 2 B is only 8-byte aligned - and 4-byte loads / stores of the
-//    byte rasters); a CTA is 8 warps at <= 80 registers, 3 CTAs per SM: the row
+//    byte rasters); one CTA of 24 warps at <= 80 registers per SM: the row
 //    loop does not spill, and the loads of the next row are issued in the middle
 //    of the current one (an 8-pixel lane with 16-byte accesses needed 123
 //    registers -> 16 warps per SM and measured 60 % issue utilisation, profiles/);
@@ -27,7 +27,7 @@
 //    it can change (flag from big_lut) or when SHAD is requested: float32 with
 //    a guard band covering every rounding error of the shortcut, and the
 //    float64 reference sequence (shadow_from_gradient) inside the band;
-//  * persistent CTAs loop over 128 x 32 pixel items (a warp owns 4 rows); an item's DEM tile with halo arrives
+//  * persistent CTAs loop over 128 x 96 pixel items (a warp owns 4 rows); an item's DEM tile with halo arrives
 //    as one TMA box into a double buffer, requested one item ahead; warps synchronise through full / empty
 //    mbarriers only (no __syncthreads between the items of a tile); the tables are loaded once per CTA.
 #pragma once
