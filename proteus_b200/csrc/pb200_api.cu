@@ -837,7 +837,9 @@ extern "C" int pb200_plan_create(pb200_ctx *ctx, const pb200_tile *tiles, int n_
     if (!out) return fail(PB200_E_INVALID_ARG, "pb200_plan_create: null output");
     *out = nullptr;
     pb200_plan *pl = new pb200_plan();
-    int rc = plan_build(ctx, tiles, n_tiles, params, pl, nullptr, false);
+    // stream-ordered allocations from the context's memory pool (release threshold: never): after the first plan a
+    // create / destroy pair costs no cudaMalloc / cudaFree (those took ~1 ms per pair)
+    int rc = plan_build(ctx, tiles, n_tiles, params, pl, nullptr, true);
     if (rc == 0) {
         cudaError_t e = cudaStreamSynchronize(nullptr);
         if (e != cudaSuccess) rc = fail_cuda(e, "plan upload");
@@ -857,6 +859,9 @@ extern "C" int pb200_plan_run(pb200_plan *plan, void *stream) {
 extern "C" int pb200_plan_destroy(pb200_plan *plan) {
     if (!plan) return 0;
     cudaSetDevice(plan->ctx->device);
+    // the plan may still be running on any stream: wait for the device (what cudaFree used to do implicitly), then
+    // hand the buffers back to the pool
+    cudaDeviceSynchronize();
     plan_release(plan, nullptr);
     delete plan;
     return 0;
