@@ -277,7 +277,7 @@ static int derive_params(const pb200_params *p, DevParams *D, bool fused) {
     for (int k = 0; k < 6; ++k) D->band_fill[k] = p->band_fill[k];
     D->fmask_fill = p->fmask_fill;
     D->flags = (p->apply_aerosol_class_remapping ? PF_AEROSOL : 0u) | (p->collapse_wtr_classes ? PF_COLLAPSE : 0u) |
-               (p->class_histogram ? PF_HISTOGRAM : 0u);
+               (p->class_histogram ? PF_HISTOGRAM : 0u) | (p->defer_snow ? PF_DEFER_SNOW : 0u);
     D->dxf = (float)p->pixel_spacing_x;
     D->dyf = -std::fabs((float)p->pixel_spacing_y);
     double c, t;
@@ -305,7 +305,9 @@ static int derive_params(const pb200_params *p, DevParams *D, bool fused) {
             uint32_t wtr = cloud_masking(w2, c4);
             const uint32_t bw = binary_water(wtr);
             const uint32_t cf = confidence(w2, c4);
-            const uint32_t cl = (w2 == 255u) ? 255u : c4;
+            // D:2084 (cloud[wtr2 == 255] = 255) comes AFTER the dilations of the 'cover' branch (D:2057-2078), which test
+            // cloud == 0 on the preliminary values: with the snow bit deferred the fill pixels keep them too
+            const uint32_t cl = (w2 == 255u && !p->defer_snow) ? 255u : c4;
             if (collapse) wtr = collapse_class(wtr);
             D->out_lut[k * 16 + c4] = wtr | (bw << 8) | (cf << 16) | (cl << 24);
         }
@@ -468,6 +470,8 @@ struct pb200_ctx {
     int fast_ctas_per_sm = 1;        // lean variant
     int fast_ctas_per_sm_full = 1;   // variant with the optional layers
     EncodeTiledFn encode = nullptr;
+    cudaMemPool_t pool = nullptr;    // private stream-ordered pool: plan descriptors, tensor maps, item lists
+    cudaStream_t s_plan = nullptr;   // private non-blocking stream: uploads of pb200_plan_create
     HostPipe pipe;
     std::mutex mu;
 };
@@ -520,13 +524,26 @@ extern "C" int pb200_ctx_create(int device, pb200_ctx **out) {
     }
     c->encode = (EncodeTiledFn)fn;
     {
-        // pb200_classify allocates its descriptors stream-ordered: keep the pool's memory between calls
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        // descriptors are allocated stream-ordered from a pool that belongs to this context (the device's default
+        // pool, shared with every other cudaMallocAsync user of the process, is left alone); it keeps its memory
+        // between calls, so that after the first plan no call reaches the OS allocator
+        cudaMemPoolProps props;
+        std::memset(&props, 0, sizeof(props));
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        cudaError_t pe = cudaMemPoolCreate(&c->pool, &props);
+        if (pe == cudaSuccess) {
             unsigned long long keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            pe = cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
-        cudaGetLastError();
+        if (pe == cudaSuccess) pe = cudaStreamCreateWithFlags(&c->s_plan, cudaStreamNonBlocking);
+        if (pe != cudaSuccess) {
+            if (c->pool) cudaMemPoolDestroy(c->pool);
+            delete c;
+            return fail_cuda(pe, "pb200_ctx_create: memory pool / stream");
+        }
     }
     *out = c;
     return 0;
@@ -553,6 +570,8 @@ extern "C" int pb200_ctx_destroy(pb200_ctx *ctx) {
     if (p.s_out) cudaStreamDestroy(p.s_out);
     for (auto e : p.ev_in) cudaEventDestroy(e);
     for (auto e : p.ev_k) cudaEventDestroy(e);
+    if (ctx->s_plan) cudaStreamDestroy(ctx->s_plan);
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     delete ctx;
     return 0;
 }
@@ -696,7 +715,7 @@ static int plan_build(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles, cons
             *ptr = arena->take(bytes);
             return *ptr ? cudaSuccess : cudaErrorMemoryAllocation;
         }
-        return stream_ordered ? cudaMallocAsync(ptr, bytes, stream) : cudaMalloc(ptr, bytes);
+        return stream_ordered ? cudaMallocFromPoolAsync(ptr, bytes, ctx->pool, stream) : cudaMalloc(ptr, bytes);
     };
     for (int g = 0; g < N_GROUPS; ++g) {
         pl->n[g] = (int)td[g].size();
@@ -838,14 +857,18 @@ extern "C" int pb200_plan_create(pb200_ctx *ctx, const pb200_tile *tiles, int n_
     *out = nullptr;
     pb200_plan *pl = new pb200_plan();
     // stream-ordered allocations from the context's memory pool (release threshold: never): after the first plan a
-    // create / destroy pair costs no cudaMalloc / cudaFree (those took ~1 ms per pair)
-    int rc = plan_build(ctx, tiles, n_tiles, params, pl, nullptr, true);
+    // create / destroy pair costs no cudaMalloc / cudaFree (those took ~1 ms per pair).  Uploads run on the context's
+    // own non-blocking stream (never the legacy NULL stream, which would serialise with every blocking stream of the
+    // host application and cannot be captured); the plan is complete when this call returns.
+    if (!ctx) { delete pl; return fail(PB200_E_INVALID_ARG, "pb200_plan_create: null context"); }
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    int rc = plan_build(ctx, tiles, n_tiles, params, pl, ctx->s_plan, true);
     if (rc == 0) {
-        cudaError_t e = cudaStreamSynchronize(nullptr);
+        cudaError_t e = cudaStreamSynchronize(ctx->s_plan);
         if (e != cudaSuccess) rc = fail_cuda(e, "plan upload");
     }
     if (rc) {
-        plan_release(pl, nullptr);
+        plan_release(pl, ctx->s_plan);
         delete pl;
         return rc;
     }
@@ -862,7 +885,7 @@ extern "C" int pb200_plan_destroy(pb200_plan *plan) {
     // the plan may still be running on any stream: wait for the device (what cudaFree used to do implicitly), then
     // hand the buffers back to the pool
     cudaDeviceSynchronize();
-    plan_release(plan, nullptr);
+    plan_release(plan, plan->ctx->s_plan);
     delete plan;
     return 0;
 }
@@ -889,8 +912,13 @@ static int pipe_reserve(HostPipe &p, size_t px, size_t dem_elems) {
         CK(cudaMalloc((void **)&p.tables, sizeof(FusedTables)));
     }
     if (px > p.cap_px) {
+        // capacity and pointers are cleared BEFORE anything is freed: a failed cudaMalloc below leaves an empty
+        // mirror (the next call reallocates), never freed pointers behind a stale capacity
+        p.cap_px = 0;
+        p.anc_valid = false;
         for (auto &b : p.band) { cudaFree(b); b = nullptr; }
         cudaFree(p.fmask); cudaFree(p.land); cudaFree(p.ocean); cudaFree(p.diag);
+        p.fmask = p.land = p.ocean = nullptr; p.diag = nullptr;
         for (auto &b : p.u8out) { cudaFree(b); b = nullptr; }
         for (auto &b : p.band) CK(cudaMalloc((void **)&b, px * 2));
         CK(cudaMalloc((void **)&p.fmask, px));
@@ -901,6 +929,8 @@ static int pipe_reserve(HostPipe &p, size_t px, size_t dem_elems) {
         p.cap_px = px;
     }
     if (dem_elems > p.cap_dem) {
+        p.cap_dem = 0;
+        p.anc_valid = false;
         cudaFree(p.dem);
         p.dem = nullptr;
         CK(cudaMalloc((void **)&p.dem, dem_elems * 4));
@@ -908,6 +938,22 @@ static int pipe_reserve(HostPipe &p, size_t px, size_t dem_elems) {
     }
     return 0;
 }
+
+// error path of the host pipeline: asynchronous copies from / into the caller's buffers may be in flight on the three
+// streams; none may outlive the call
+static void pipe_drain(HostPipe &p) {
+    if (p.s_in) cudaStreamSynchronize(p.s_in);
+    if (p.s_k) cudaStreamSynchronize(p.s_k);
+    if (p.s_out) cudaStreamSynchronize(p.s_out);
+}
+#define CKP(call)                                             \
+    do {                                                      \
+        cudaError_t e_ = (call);                              \
+        if (e_ != cudaSuccess) {                              \
+            pipe_drain(p);                                    \
+            return fail_cuda(e_, #call);                      \
+        }                                                     \
+    } while (0)
 
 extern "C" int pb200_classify_host(pb200_ctx *ctx, const pb200_tile *ht, const pb200_params *params,
                                    int strip_rows) {
@@ -974,7 +1020,7 @@ extern "C" int pb200_classify_host_ex(pb200_ctx *ctx, const pb200_tile *ht, cons
     rc = derive_params(params, &P, true);             // argument checks before anything is in flight
     if (rc) return rc;
     // ---- H2D of every strip first: the copy engine starts while the host still builds tables and plan ----------
-    if (trace) { CK(cudaEventRecord(tr[0], p.s_in)); }
+    if (trace) { CKP(cudaEventRecord(tr[0], p.s_in)); }
     {
         int dem_copied = 0;                 // DEM rows [.., dem_copied) are on the device
         bool first_dem = true;
@@ -982,24 +1028,24 @@ extern "C" int pb200_classify_host_ex(pb200_ctx *ctx, const pb200_tile *ht, cons
             const int r0 = edge[sidx], r1 = edge[sidx + 1], nr = r1 - r0;
             const size_t off = (size_t)r0 * W, cnt = (size_t)nr * W;
             for (int k = 0; k < 6; ++k)
-                CK(cudaMemcpyAsync(p.band[k] + off, ht->band[k] + off, cnt * 2, cudaMemcpyHostToDevice, p.s_in));
-            CK(cudaMemcpyAsync(p.fmask + off, ht->fmask + off, cnt, cudaMemcpyHostToDevice, p.s_in));
-            if (ht->land && !reuse) CK(cudaMemcpyAsync(p.land + off, ht->land + off, cnt, cudaMemcpyHostToDevice, p.s_in));
-            if (ht->ocean && !reuse) CK(cudaMemcpyAsync(p.ocean + off, ht->ocean + off, cnt, cudaMemcpyHostToDevice, p.s_in));
+                CKP(cudaMemcpyAsync(p.band[k] + off, ht->band[k] + off, cnt * 2, cudaMemcpyHostToDevice, p.s_in));
+            CKP(cudaMemcpyAsync(p.fmask + off, ht->fmask + off, cnt, cudaMemcpyHostToDevice, p.s_in));
+            if (ht->land && !reuse) CKP(cudaMemcpyAsync(p.land + off, ht->land + off, cnt, cudaMemcpyHostToDevice, p.s_in));
+            if (ht->ocean && !reuse) CKP(cudaMemcpyAsync(p.ocean + off, ht->ocean + off, cnt, cudaMemcpyHostToDevice, p.s_in));
             if (ht->dem && !reuse) {
                 int d0 = ht->dem_off_y + r0 - 1, d1 = ht->dem_off_y + r1 + 1;     // rows the strip's stencil reads
                 if (!first_dem) d0 = std::max(d0, dem_copied);
                 d0 = std::max(d0, 0);
                 d1 = std::min(d1, ht->dem_rows);
                 if (d1 > d0)
-                    CK(cudaMemcpyAsync(p.dem + (size_t)d0 * ht->dem_pitch, ht->dem + (size_t)d0 * ht->dem_pitch,
+                    CKP(cudaMemcpyAsync(p.dem + (size_t)d0 * ht->dem_pitch, ht->dem + (size_t)d0 * ht->dem_pitch,
                                        (size_t)(d1 - d0) * ht->dem_pitch * 4, cudaMemcpyHostToDevice, p.s_in));
                 dem_copied = std::max(dem_copied, d1);
                 first_dem = false;
             }
-            CK(cudaEventRecord(p.ev_in[sidx], p.s_in));
+            CKP(cudaEventRecord(p.ev_in[sidx], p.s_in));
         }
-        if (trace) { CK(cudaEventRecord(tr[1], p.s_in)); }
+        if (trace) { CKP(cudaEventRecord(tr[1], p.s_in)); }
     }
     const double ms_h2d_enqueued = ms_since(t_enter);
     // validate once with a whole-tile descriptor on the device mirror
@@ -1014,11 +1060,11 @@ extern "C" int pb200_classify_host_ex(pb200_ctx *ctx, const pb200_tile *ht, cons
     uint8_t **dev_u8_field[8] = {&dt.wtr1, &dt.wtr1_remapped, &dt.wtr2, &dt.cloud, &dt.shad, &dt.wtr, &dt.bwtr, &dt.conf};
     for (int i = 0; i < 8; ++i) *dev_u8_field[i] = host_u8[i] ? p.u8out[i] : nullptr;
     dt.counters = (uint64_t *)p.counters;             // always counted on the device (lean kernel variant); copied back on request
-    if (dt.counters) CK(cudaMemsetAsync(p.counters, 0, PB200_N_COUNTERS * sizeof(unsigned long long), p.s_k));
+    if (dt.counters) CKP(cudaMemsetAsync(p.counters, 0, PB200_N_COUNTERS * sizeof(unsigned long long), p.s_k));
     {
         FusedTables T;
         build_fused_tables(params, P, &T);
-        CK(cudaMemcpyAsync(p.tables, &T, sizeof(T), cudaMemcpyHostToDevice, p.s_k));
+        CKP(cudaMemcpyAsync(p.tables, &T, sizeof(T), cudaMemcpyHostToDevice, p.s_k));
     }
 
     // descriptors of ALL strips in one plan, uploaded before the pipeline starts: inside the
@@ -1046,11 +1092,11 @@ extern "C" int pb200_classify_host_ex(pb200_ctx *ctx, const pb200_tile *ht, cons
         const size_t need = (size_t)n_strips * (sizeof(TileDev) + sizeof(CUtensorMap) + 1024) +
                             items_max * sizeof(ItemDesc) + 8192;
         if (need > p.arena.cap) {
-            CK(cudaStreamSynchronize(p.s_k));
+            CKP(cudaStreamSynchronize(p.s_k));
             cudaFree(p.arena.base);
             p.arena.base = nullptr;
             p.arena.cap = 0;
-            CK(cudaMalloc((void **)&p.arena.base, need * 2));
+            CKP(cudaMalloc((void **)&p.arena.base, need * 2));
             p.arena.cap = need * 2;
         }
         p.arena.used = 0;
@@ -1059,7 +1105,7 @@ extern "C" int pb200_classify_host_ex(pb200_ctx *ctx, const pb200_tile *ht, cons
     rc = plan_build(ctx, strips.data(), n_strips, params, &plan, p.s_k, true, p.tables, &p.arena);
     if (rc) {
         plan_release(&plan, p.s_k);
-        cudaStreamSynchronize(p.s_in);                // the copies read the caller's buffers: none may outlive the call
+        pipe_drain(p);                                // the copies read the caller's buffers: none may outlive the call
         return rc;
     }
 
@@ -1068,26 +1114,26 @@ extern "C" int pb200_classify_host_ex(pb200_ctx *ctx, const pb200_tile *ht, cons
         const int r0 = edge[sidx], r1 = edge[sidx + 1], nr = r1 - r0;
         const size_t off = (size_t)r0 * W, cnt = (size_t)nr * W;
         // ---- kernel on the strip -------------------------------------------
-        CK(cudaStreamWaitEvent(p.s_k, p.ev_in[sidx], 0));
+        CKP(cudaStreamWaitEvent(p.s_k, p.ev_in[sidx], 0));
         rc = plan_launch_tile(&plan, sidx, p.s_k);
-        if (rc) { cudaDeviceSynchronize(); plan_release(&plan, p.s_k); return rc; }
-        CK(cudaEventRecord(p.ev_k[sidx], p.s_k));
+        if (rc) { pipe_drain(p); plan_release(&plan, p.s_k); return rc; }
+        CKP(cudaEventRecord(p.ev_k[sidx], p.s_k));
         // ---- D2H --------------------------------------------------------------
-        CK(cudaStreamWaitEvent(p.s_out, p.ev_k[sidx], 0));
-        if (ht->diag) CK(cudaMemcpyAsync(ht->diag + off, p.diag + off, cnt * 2, cudaMemcpyDeviceToHost, p.s_out));
+        CKP(cudaStreamWaitEvent(p.s_out, p.ev_k[sidx], 0));
+        if (ht->diag) CKP(cudaMemcpyAsync(ht->diag + off, p.diag + off, cnt * 2, cudaMemcpyDeviceToHost, p.s_out));
         for (int i = 0; i < 8; ++i)
             if (host_u8[i])
-                CK(cudaMemcpyAsync(host_u8[i] + off, p.u8out[i] + off, cnt, cudaMemcpyDeviceToHost, p.s_out));
+                CKP(cudaMemcpyAsync(host_u8[i] + off, p.u8out[i] + off, cnt, cudaMemcpyDeviceToHost, p.s_out));
     }
     const double ms_enqueued = ms_since(t_enter);
-    if (trace) { CK(cudaEventRecord(tr[2], p.s_k)); }
+    if (trace) { CKP(cudaEventRecord(tr[2], p.s_k)); }
     plan_release(&plan, p.s_k);
     if (ht->counters)
-        CK(cudaMemcpyAsync(ht->counters, p.counters, PB200_N_COUNTERS * sizeof(unsigned long long),
+        CKP(cudaMemcpyAsync(ht->counters, p.counters, PB200_N_COUNTERS * sizeof(unsigned long long),
                            cudaMemcpyDeviceToHost, p.s_out));
-    if (trace) { CK(cudaEventRecord(tr[3], p.s_out)); }
-    CK(cudaStreamSynchronize(p.s_out));
-    CK(cudaStreamSynchronize(p.s_k));
+    if (trace) { CKP(cudaEventRecord(tr[3], p.s_out)); }
+    CKP(cudaStreamSynchronize(p.s_out));
+    CKP(cudaStreamSynchronize(p.s_k));
     p.anc_valid = true;
     p.anc_h = H; p.anc_w = W;
     p.anc_dem = ht->dem != nullptr; p.anc_land = ht->land != nullptr; p.anc_ocean = ht->ocean != nullptr;
@@ -1240,8 +1286,8 @@ extern "C" int pb200_landcover_shadow_masks(pb200_ctx *ctx, const uint8_t *wtr1,
     REQUIRE(wtr1 && wtr2 && n >= 0, "pb200_landcover_shadow_masks: bad argument");
     REQUIRE(nir || !land, "pb200_landcover_shadow_masks: nir is required with a land-cover raster");
     if (n == 0) return 0;
-    landcover_shadow_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(wtr1, nir ? nir : (const int16_t *)wtr1, land,
-                                                                    shad, gt_threshold(lcmask_nir), wtr2, n);
+    landcover_shadow_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(wtr1, nir, land, shad, gt_threshold(lcmask_nir),
+                                                                    wtr2, n);
     LEAVE();
 }
 

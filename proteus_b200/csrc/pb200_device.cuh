@@ -25,7 +25,8 @@ __device__ __forceinline__ uint32_t expand_class(uint32_t k) {
 }
 
 enum : int { RB_WIGT = 0, RB_P1_MNDWI = 1, RB_P2_MNDWI = 2, RB_P1_NDVI = 3 };
-enum : uint32_t { PF_AEROSOL = 1u, PF_COLLAPSE = 2u, PF_HISTOGRAM = 4u };
+enum : uint32_t { PF_AEROSOL = 1u, PF_COLLAPSE = 2u, PF_HISTOGRAM = 4u,
+                  PF_DEFER_SNOW = 8u };   // 'cover' flow, phase 1: CLOUD stays the preliminary layer (+ aerosol bit), also on fill pixels
 
 // fmask_lut entry layout
 //   bits 0-2 : preliminary CLOUD value (0, 1, 4, 5)          D:1984-1991
@@ -131,8 +132,8 @@ __device__ __forceinline__ uint32_t binary_representation(uint32_t d) {
 // D:97-143 as bit planes over the 32 codes (bit i of plane j = bit j of the
 // class of code i).  Used by the table builder and the function-level kernel.
 __host__ __device__ __forceinline__ uint32_t interpreted_class(uint32_t d) {
-    // popcount-free closed form of the table: see tests/test_lut.py which
-    // checks it against the reference's own dict.
+    // closed form of the table: tests/test_oracle_golden.py and tests/test_gpu_parity.py check it against the
+    // reference's own dict (tests/golden/reference_tables.json) through generate_interpreted_layer.
     constexpr uint32_t C1 = (1u << 0b01111) | (1u << 0b10111) | (1u << 0b11011) |
                             (1u << 0b11101) | (1u << 0b11110) | (1u << 0b11111);
     constexpr uint32_t C2 = (1u << 0b00111) | (1u << 0b01011) | (1u << 0b01101) |

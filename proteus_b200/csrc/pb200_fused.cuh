@@ -616,7 +616,7 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                         const uint32_t k2 = s.kill_lut[kb | (shb << 3) | ((idx[j] >> 6) & 0x10u) | ((idx[j] >> 2) & 0x60u)];
                         sel1r |= kb << (4 * j);
                         sel2 |= k2 << (4 * j);
-                        c4 |= (k2 == 7u ? 255u : c) << (8 * j);                                    // D:2084
+                        c4 |= ((k2 == 7u && !(P.flags & PF_DEFER_SNOW)) ? 255u : c) << (8 * j);    // D:2084 ('cover': after the dilations)
                         s4 |= (shb ^ 1u) << (8 * j);
                     }
                     // k1p[p]: byte 0 = k1 of pixel 2p, byte 2 = k1 of pixel 2p+1

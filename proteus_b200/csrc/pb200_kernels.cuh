@@ -438,7 +438,8 @@ __global__ void landcover_shadow_kernel(const uint8_t *__restrict__ wtr1, const 
                                         const uint8_t *__restrict__ land, const uint8_t *__restrict__ shad,
                                         int lc_nir, uint8_t *__restrict__ wtr2, long long n) {
     PB200_GRID_STRIDE(i, n) {
-        wtr2[i] = (uint8_t)landcover_shadow(wtr1[i], nir[i], land != nullptr, land ? land[i] : 255u,
+        // nir is only looked at together with a land-cover raster (D:1354-1362); it may be null without one
+        wtr2[i] = (uint8_t)landcover_shadow(wtr1[i], land != nullptr ? (int)nir[i] : 0, land != nullptr, land ? land[i] : 255u,
                                             shad != nullptr, shad ? shad[i] : 1u, lc_nir);
     }
 }

@@ -206,6 +206,11 @@ def test_function_level_dropins_match_oracle(pb):
     for l, s in ((land, shad), (None, shad), (land, None), (None, None)):
         assert np.array_equal(G._apply_landcover_and_shadow_masks(wtr1, nir, l, s, gth),
                               O.apply_landcover_and_shadow_masks(wtr1, nir, l, s, th))
+    # nir is not looked at without a land-cover raster (D:1354-1362): None must not be dereferenced
+    big = wtr_vals[rng.integers(0, len(wtr_vals), (700, 1000))]
+    big_shad = rng.integers(0, 2, big.shape).astype(bool)
+    assert np.array_equal(G._apply_landcover_and_shadow_masks(big, None, None, big_shad, gth),
+                          O.apply_landcover_and_shadow_masks(big, np.zeros(big.shape, np.int16), None, big_shad, th))
     for mode in ('mask', 'ignore'):
         c_ref = O.add_snow_to_cloud_layer(wtr1, cloud.copy(), fmask, mode)
         c_in = cloud.copy()
@@ -363,6 +368,38 @@ def test_cover_mode_matches_reference_fixture(pb):
     g = pb.classify_tile(t['bands'], t['fmask'], t['dem'], t['land'], t['ocean'], t['sun_azimuth'],
                          t['sun_elevation'], mask_adjacent_to_cloud_mode='cover', collapse_wtr_classes=False)
     _assert_layers(g, o, FUSED_LAYERS, 'cover adversarial')
+
+
+def test_cover_mode_dilates_through_band_fill_pixels(pb):
+    """D:2084 (cloud[wtr2 == 255] = 255) runs AFTER the dilations of D:2057-2078, which test cloud == 0 on
+    the preliminary values.  A pixel that is fill in a band but carries a plain Fmask value (adjacent bit only) is
+    part of areas_to_dilate in the reference: the snow front must pass through it."""
+    t = synth.make_tile(77, 96, 256, with_dem=False, with_land=False, with_ocean=False)
+    for b, v in zip(t['bands'], (300, 500, 400, 3000, 2000, 1000)):      # left half: land (class 0) - no dilation back
+        b[...] = v
+    for b, v in zip(t['bands'], (400, 500, 300, 200, 100, 50)):          # right half: water (class 1) - D:2070-2076 apply
+        b[:, 128:] = v
+    t['fmask'][...] = 4                                                  # adjacent to cloud everywhere: the dilation area
+    t['fmask'][10, 5] = t['fmask'][10, 200] = 4 | 16                     # one snow seed per half ...
+    for b in t['bands']:
+        b[10, 8] = b[10, 203] = -9999                                    # ... a band-only fill pixel 3 px further on
+        b[12:14, 0:40] = -9999                                           # and a fill band across the front's way
+    ref = O.reference_chain(t['bands'], t['fmask'], None, None, None, t['sun_azimuth'], t['sun_elevation'],
+                            processing=dict(mask_adjacent_to_cloud_mode='cover'))
+    assert ref['WTR1'][10, 5] == 0 and ref['WTR1'][10, 201] == 1
+    assert ref['CLOUD'][10, 8] == 255 and ref['CLOUD'][10, 11] == 2      # snow reached the far side of the fill pixel
+    assert ref['CLOUD'][15, 5] == 2                                      # and crossed the fill band
+    got = pb.classify_tile(t['bands'], t['fmask'], None, None, None, t['sun_azimuth'], t['sun_elevation'],
+                           mask_adjacent_to_cloud_mode='cover', collapse_wtr_classes=False)
+    _assert_layers(got, ref, FUSED_LAYERS, 'cover through fill')
+    # the advisor's search: adversarial tiles (full-range bands: many band-only fill pixels with arbitrary Fmask)
+    for seed in range(100, 130):
+        t = synth.make_tile(seed, 150, 212, adversarial=True)
+        o = O.reference_chain(t['bands'], t['fmask'], t['dem'], t['land'], t['ocean'], t['sun_azimuth'],
+                              t['sun_elevation'], processing=dict(mask_adjacent_to_cloud_mode='cover'))
+        g = pb.classify_tile(t['bands'], t['fmask'], t['dem'], t['land'], t['ocean'], t['sun_azimuth'],
+                             t['sun_elevation'], mask_adjacent_to_cloud_mode='cover', collapse_wtr_classes=False)
+        _assert_layers(g, o, FUSED_LAYERS, f'cover adversarial seed {seed}')
 
 
 def test_masked_dilation_matches_scipy(pb):
