@@ -176,57 +176,102 @@ def _pool_job(args):
     return int(out['counters'][0]), int(out['WTR'].astype('int64').sum())
 
 
+def _load_synth_without_the_library():
+    """proteus_b200/synth.py by path: importing the package would map libproteus_b200.so into this process, and the
+    reference arm must not hold any product code (only numpy + oracle/)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('pb200_synth_standalone',
+                                                  os.path.join(ROOT, 'proteus_b200', 'synth.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+# Per core, the numpy port (oracle/dswx_oracle.py: look-up tables instead of one pass per class, explicit differences
+# instead of np.gradient) is faster than the reference's own functions called in generate_dswx_layers' order; measured
+# in the build container (8 vCPU) on the same synthetic tile by scripts/port_vs_reference.py ->
+# profiles/r2_port_vs_reference.json.  The reference arm therefore flatters the CPU side by about this factor.
+PORT_VS_REFERENCE_PER_CORE = None
+
+
+def _port_vs_reference():
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r2_port_vs_reference.json')) as f:
+            d = json.load(f)
+        return {'ratio': d['port_vs_reference_per_core'], 'source': 'profiles/r2_port_vs_reference.json '
+                '(scripts/port_vs_reference.py: live unmodified reference vs the port, same tile, one core, '
+                f"build container, {d.get('rows')} rows)"}
+    except Exception:
+        return {'ratio': 4.0, 'source': 'SURVEY.md section 6 probe: reference 1.65 Mpixel/s/core vs port 6.6'}
+
+
 def run_reference_arm(args):
     """--impl reference: the reference's CPU algorithm (numpy port; the
     reference itself is not installable here and does not exist on the GPU
-    box) on all host cores, one tile per step split into row strips."""
+    box) on all host cores; one step = ONE WHOLE tile of the GPU arm's
+    config, split into row strips over the processes."""
     global _G_TILE
     import multiprocessing as mp
     import numpy as np
-    from proteus_b200 import synth
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return 0
+    synth = _load_synth_without_the_library()
+    assert 'proteus_b200' not in sys.modules, 'the reference arm must not import the product package'
     cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
     size = args.size
-    # bounded sample: a band of rows sized so that one step is ~2-4 s on this box
-    rows = min(size, max(64, int(150 * cores)))
-    rows = args.cpu_rows or rows
+    rows = args.cpu_rows or size                     # default: the whole tile (same config as the GPU arm)
     tile = synth.make_tile(0, size, size)
     _G_TILE = tile
-    n_jobs = min(cores, max(1, rows // 32))
+    n_procs = max(1, min(cores, rows // 8))
+    # 4 strips per process: the fill wedge and the water share differ between strips, smaller strips balance the pool
+    n_jobs = max(1, min(rows // 8, 4 * n_procs))
     bounds = np.linspace(0, rows, n_jobs + 1).astype(int)
     jobs = [(int(bounds[i]), int(bounds[i + 1])) for i in range(n_jobs) if bounds[i + 1] > bounds[i]]
-    steps = max(1, min(args.steps, 5))
-    warm = 1 if args.warmup > 0 else 0
+    steps, warm = max(1, args.steps), max(0, args.warmup)
     ctx = mp.get_context('fork')
-    with ctx.Pool(len(jobs)) as pool:
+    with ctx.Pool(n_procs) as pool:
         for _ in range(warm):
-            pool.map(_pool_job, jobs)
+            pool.map(_pool_job, jobs, chunksize=1)
         t0 = time.perf_counter()
         for _ in range(steps):
-            pool.map(_pool_job, jobs)
+            pool.map(_pool_job, jobs, chunksize=1)
         dt = time.perf_counter() - t0
     mpx = rows * size / 1e6
     value = mpx * steps / dt
-    sample = (f'{steps} steps x rows 0..{rows} of one synthetic S30 {size}x{size} tile (full product) split into '
-              f'{len(jobs)} row strips over {len(jobs)} processes; numpy port of dswx_hls.py:5088-5369')
+    pvr = _port_vs_reference()
+    sample = (f'{steps} steps x {"the whole" if rows == size else f"rows 0..{rows} of one"} synthetic S30 {size}x{size} tile '
+              f'(full product), {len(jobs)} row strips over {n_procs} processes; numpy port of dswx_hls.py:5088-5369')
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': steps, 'warmup': warm, 'ms_per_step': 1e3 * dt / steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int16', 'data': 'synthetic',
         'tiles_per_s': value * 1e6 / (size * size),
-        'config': {'workload': 'configs[1]: synthetic HLS S30 tile 3660x3660 full product (bounded CPU sample)',
-                   'tile': [size, size], 'layers_out': ['WTR', 'BWTR', 'CONF', 'DIAG'],
-                   'bytes_per_pixel': ALGO_BYTES_PER_PX},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': len(jobs), 'kind': 'port', 'sample': sample},
+        'config': _config_block(size, args.tiles, args.gpus, args.workload),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': n_procs, 'kind': 'port', 'sample': sample,
+                         'port_vs_reference_per_core': pvr['ratio'], 'port_vs_reference_source': pvr['source']},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
         'note': 'reference is pure Python + GDAL; GDAL/yamale are absent so it cannot be pip-installed; '
-                'its per-pixel numpy chain is timed through the validated port (oracle/)',
+                'its per-pixel numpy chain is timed through the validated port (oracle/), which is '
+                f"~{pvr['ratio']:.1f}x faster per core than the reference's own functions: the ratio against this arm is conservative",
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+def _config_block(size, n_tiles, world, workload='tiles'):
+    """The `config` object: identical in both arms (the driver compares them)."""
+    px = size * size
+    return {
+        'workload': ('configs[3] time series (shared DEM/LAND/ocean): ' if workload == 'timeseries' else '') +
+                    f'configs[1]: synthetic HLS S30 tile {size}x{size} full product '
+                    f'(6 int16 bands + Fmask + DEM + LAND + ocean -> WTR/BWTR/CONF/DIAG + counters), '
+                    f'{n_tiles} distinct device-resident tiles per GPU per step, sharded by tile',
+        'tile': [size, size], 'tiles_per_gpu_per_step': n_tiles,
+        'layers_out': ['WTR', 'BWTR', 'CONF', 'DIAG'], 'bytes_per_pixel': ALGO_BYTES_PER_PX,
+        'l2_policy': f'inputs per step {n_tiles * px * BYTES_IN_PER_PX / 1e9:.2f} GB >> 126 MB L2; no flush needed',
+        'parallelism': f'tile-sharded x{world}, no data-path collective'}
 
 
 # ---------------------------------------------------------------------------
@@ -460,15 +505,7 @@ def run_ours(args):
             'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int16', 'data': 'synthetic',
             'tiles_per_s': value * 1e6 / px_per_tile,
-            'config': {
-                'workload': ('configs[3] time series (shared DEM/LAND/ocean): ' if args.workload == 'timeseries' else '') +
-                            f'configs[1]: synthetic HLS S30 tile {size}x{size} full product '
-                            f'(6 int16 bands + Fmask + DEM + LAND + ocean -> WTR/BWTR/CONF/DIAG + counters), '
-                            f'{n_tiles} distinct device-resident tiles per GPU per step, sharded by tile',
-                'tile': [size, size], 'tiles_per_gpu_per_step': n_tiles,
-                'layers_out': list(pb.GRADED_LAYERS), 'bytes_per_pixel': ALGO_BYTES_PER_PX,
-                'l2_policy': f'inputs per step {n_tiles * px_per_tile * BYTES_IN_PER_PX / 1e9:.2f} GB >> 126 MB L2; no flush needed',
-                'parallelism': f'tile-sharded x{world}, no data-path collective'},
+            'config': _config_block(size, n_tiles, world, args.workload),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                          'algorithmic_bytes_per_launch': algo_bytes, 'kernel_ms': kernel_ms,
