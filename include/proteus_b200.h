@@ -39,6 +39,7 @@ extern "C" {
 #define PB200_E_UNSUPPORTED   (-3)
 #define PB200_E_NO_DRIVER_API (-4)
 #define PB200_E_ALIGNMENT     (-5)
+#define PB200_E_NCCL          (-6)   /* NCCL missing or an ncclResult_t != ncclSuccess (text in pb200_last_error) */
 
 /* "this raster has no fill value" (D:2196-2199 always yields one, but the
  * function-granular entry points are also used on already-clean data) */
@@ -284,6 +285,31 @@ int  pb200_histogram_u8(pb200_ctx *ctx, const uint8_t *image, int64_t n, unsigne
 int  pb200_otsu_threshold(const unsigned long long counts[256], int is_normalized, double *threshold);
 int  pb200_greater_than_u8(pb200_ctx *ctx, const uint8_t *image, int64_t n, double threshold, uint8_t *out,
                            void *stream);
+
+/* ---- multi-GPU: one oversized raster in row strips (BASELINE configs[4]) -------------------------
+ * Every function of the path is point-wise except the one-row stencil of np.gradient inside
+ * _compute_opera_shadow_layer (D:4255): the rank that owns pixel rows [r0, r1) needs DEM rows r0 - 1 and r1.  The
+ * reference never splits a raster; parity is defined against the reference run on the whole raster.
+ *
+ * One process per GPU.  Rank 0 calls pb200_comm_unique_id and hands the 128 bytes to the other ranks over any host
+ * channel (MPI, torch.distributed, a file); every rank then calls pb200_comm_init on its context (collective).  NCCL
+ * is bound at run time (dlopen of libnccl.so.2, preferring the copy already in the process; PB200_NCCL_PATH
+ * overrides): PB200_E_NCCL if it cannot be found.
+ *
+ * pb200_halo_exchange_dem: dem_ext is the strip's DEM as (n_rows + 2) x pitch float32 on the device, rows 1..n_rows
+ * = the strip's own DEM rows (column margins included), row 0 / row n_rows + 1 = the halo rows.  Sends row 1 to rank
+ * - 1 and row n_rows to rank + 1, receives row 0 from rank - 1 and row n_rows + 1 from rank + 1 (ncclSend / ncclRecv
+ * in one group, asynchronous on `stream`; NVLink on one box).  Rank 0 keeps its own row 0 and the last rank its own
+ * last row (both come from the DEM margin the host supplies).  Then classify with a pb200_tile whose dem = dem_ext,
+ * dem_rows = n_rows + 2, dem_off_y = 1.
+ * pb200_comm_allreduce_u64: in-place sum over the ranks (the three coverage counters, D:5104-5111; the 256 Otsu
+ * histogram counts). */
+#define PB200_COMM_ID_BYTES 128
+int  pb200_comm_unique_id(uint8_t id[PB200_COMM_ID_BYTES]);
+int  pb200_comm_init(pb200_ctx *ctx, const uint8_t id[PB200_COMM_ID_BYTES], int rank, int nranks);
+int  pb200_halo_exchange_dem(pb200_ctx *ctx, float *dem_ext, int n_rows, int pitch, void *stream);
+int  pb200_comm_allreduce_u64(pb200_ctx *ctx, uint64_t *values, int n, void *stream);
+int  pb200_comm_destroy(pb200_ctx *ctx);
 
 /* ---- helpers exported for tests ---------------------------------------- */
 /* The exact integer form of "float64(n)/float64(d) > t" (is_less = 0) or

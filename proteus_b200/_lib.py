@@ -15,7 +15,8 @@ ABI_VERSION = 1
 NO_FILL = -2 ** 31
 ADJ_MODES = {'mask': 0, 'ignore': 1, 'cover': 2}
 N_COUNTERS = 12
-E_INVALID_ARG, E_BAD_MODE, E_UNSUPPORTED, E_NO_DRIVER_API, E_ALIGNMENT = -1, -2, -3, -4, -5
+E_INVALID_ARG, E_BAD_MODE, E_UNSUPPORTED, E_NO_DRIVER_API, E_ALIGNMENT, E_NCCL = -1, -2, -3, -4, -5, -6
+COMM_ID_BYTES = 128
 
 EXPORTS = (
     'pb200_version', 'pb200_last_error', 'pb200_ctx_create', 'pb200_ctx_destroy',
@@ -30,6 +31,8 @@ EXPORTS = (
     'pb200_browse_table', 'pb200_byte_table', 'pb200_scale_offset',
     'pb200_histogram_u8', 'pb200_otsu_threshold', 'pb200_greater_than_u8', 'pb200_ratio_bound',
     'pb200_ratio_sweep', 'pb200_angle_thresholds',
+    'pb200_comm_unique_id', 'pb200_comm_init', 'pb200_halo_exchange_dem', 'pb200_comm_allreduce_u64',
+    'pb200_comm_destroy',
 )
 
 
@@ -151,6 +154,11 @@ def load():
     lib.pb200_otsu_threshold.argtypes = [C.c_uint64 * 256, C.c_int, C.POINTER(C.c_double)]
     lib.pb200_greater_than_u8.argtypes = [vp, vp, i64, C.c_double, vp, vp]
     lib.pb200_shadow.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(Params), vp, vp]
+    lib.pb200_comm_unique_id.argtypes = [C.c_uint8 * COMM_ID_BYTES]
+    lib.pb200_comm_init.argtypes = [vp, C.c_uint8 * COMM_ID_BYTES, C.c_int, C.c_int]
+    lib.pb200_halo_exchange_dem.argtypes = [vp, vp, C.c_int, C.c_int, vp]
+    lib.pb200_comm_allreduce_u64.argtypes = [vp, vp, C.c_int, vp]
+    lib.pb200_comm_destroy.argtypes = [vp]
     _lib = lib
     return lib
 

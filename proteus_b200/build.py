@@ -25,6 +25,7 @@ HEADERS = [os.path.join(CSRC, 'pb200_kernels.cuh'),
            os.path.join(CSRC, 'pb200_cover.cuh'),
            os.path.join(CSRC, 'pb200_landcover.cuh'),
            os.path.join(CSRC, 'pb200_device.cuh'),
+           os.path.join(CSRC, 'pb200_comm.cuh'),
            os.path.join(HERE, '..', 'include', 'proteus_b200.h')]
 
 NVCC_FLAGS = [

@@ -25,6 +25,7 @@
 #include "pb200_fused.cuh"
 #include "pb200_cover.cuh"
 #include "pb200_landcover.cuh"
+#include "pb200_comm.cuh"
 
 using namespace pb200;
 
@@ -472,6 +473,7 @@ struct pb200_ctx {
     EncodeTiledFn encode = nullptr;
     cudaMemPool_t pool = nullptr;    // private stream-ordered pool: plan descriptors, tensor maps, item lists
     cudaStream_t s_plan = nullptr;   // private non-blocking stream: uploads of pb200_plan_create
+    Comm comm;                       // NCCL communicator of a row-stripped raster (pb200_comm_init), else empty
     HostPipe pipe;
     std::mutex mu;
 };
@@ -570,6 +572,7 @@ extern "C" int pb200_ctx_destroy(pb200_ctx *ctx) {
     if (p.s_out) cudaStreamDestroy(p.s_out);
     for (auto e : p.ev_in) cudaEventDestroy(e);
     for (auto e : p.ev_k) cudaEventDestroy(e);
+    if (ctx->comm.comm) pb200_comm_destroy(ctx);
     if (ctx->s_plan) cudaStreamDestroy(ctx->s_plan);
     if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     delete ctx;
@@ -1600,5 +1603,112 @@ extern "C" int pb200_ratio_sweep(pb200_ctx *ctx, double t, int is_less, uint64_t
     cudaError_t e = cudaMemcpy(mismatches, d, 8, cudaMemcpyDeviceToHost);
     cudaFree(d);
     if (e != cudaSuccess) return fail_cuda(e, "pb200_ratio_sweep");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// multi-GPU: NCCL DEM halo exchange of a row-stripped raster
+// ---------------------------------------------------------------------------
+static int fail_nccl(int r, const char *what) {
+    NcclApi *api = nccl_api();
+    g_err = std::string(what) + ": NCCL error " + std::to_string(r) + " - " +
+            ((api->handle && api->GetErrorString) ? api->GetErrorString(r) : "?");
+    return PB200_E_NCCL;
+}
+#define CKN(call)                                          \
+    do {                                                   \
+        int r_ = (call);                                   \
+        if (r_ != NCCL_SUCCESS) return fail_nccl(r_, #call); \
+    } while (0)
+static int need_nccl(NcclApi **out) {
+    NcclApi *api = nccl_api();
+    if (!api->handle) return fail(PB200_E_NCCL, "%s", api->error.c_str());
+    *out = api;
+    return 0;
+}
+
+extern "C" int pb200_comm_unique_id(uint8_t id[PB200_COMM_ID_BYTES]) {
+    if (!id) return fail(PB200_E_INVALID_ARG, "pb200_comm_unique_id: null output");
+    NcclApi *api;
+    int rc = need_nccl(&api);
+    if (rc) return rc;
+    static_assert(sizeof(NcclUniqueId) == PB200_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+    NcclUniqueId u;
+    CKN(api->GetUniqueId(&u));
+    std::memcpy(id, &u, sizeof(u));
+    return 0;
+}
+
+extern "C" int pb200_comm_init(pb200_ctx *ctx, const uint8_t id[PB200_COMM_ID_BYTES], int rank, int nranks) {
+    if (!ctx || !id) return fail(PB200_E_INVALID_ARG, "pb200_comm_init: null argument");
+    if (nranks < 1 || rank < 0 || rank >= nranks)
+        return fail(PB200_E_INVALID_ARG, "pb200_comm_init: rank %d of %d", rank, nranks);
+    if (ctx->comm.comm) return fail(PB200_E_INVALID_ARG, "pb200_comm_init: the context already has a communicator");
+    NcclApi *api;
+    int rc = need_nccl(&api);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    NcclUniqueId u;
+    std::memcpy(&u, id, sizeof(u));
+    NcclComm c = nullptr;
+    CKN(api->CommInitRank(&c, nranks, u, rank));
+    ctx->comm.comm = c;
+    ctx->comm.rank = rank;
+    ctx->comm.nranks = nranks;
+    return 0;
+}
+
+extern "C" int pb200_comm_destroy(pb200_ctx *ctx) {
+    if (!ctx || !ctx->comm.comm) return 0;
+    NcclApi *api;
+    int rc = need_nccl(&api);
+    if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    NcclComm c = ctx->comm.comm;
+    ctx->comm = Comm();
+    CKN(api->CommDestroy(c));
+    return 0;
+}
+
+extern "C" int pb200_halo_exchange_dem(pb200_ctx *ctx, float *dem_ext, int n_rows, int pitch, void *stream) {
+    if (!ctx || !dem_ext || n_rows < 1 || pitch < 1)
+        return fail(PB200_E_INVALID_ARG, "pb200_halo_exchange_dem: bad argument");
+    if (!ctx->comm.comm) return fail(PB200_E_INVALID_ARG, "pb200_halo_exchange_dem: pb200_comm_init has not been called");
+    NcclApi *api;
+    int rc = need_nccl(&api);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const int rank = ctx->comm.rank, n = ctx->comm.nranks;
+    if (n == 1) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    NcclComm c = ctx->comm.comm;
+    const size_t cnt = (size_t)pitch;
+    float *first = dem_ext + (size_t)pitch, *last = dem_ext + (size_t)n_rows * pitch;   // own rows 1 and n_rows
+    float *above = dem_ext, *below = dem_ext + (size_t)(n_rows + 1) * pitch;            // halo rows 0 and n_rows + 1
+    CKN(api->GroupStart());
+    int r = NCCL_SUCCESS;
+    if (rank > 0) {
+        if (r == NCCL_SUCCESS) r = api->Send(first, cnt, NCCL_FLOAT32, rank - 1, c, st);
+        if (r == NCCL_SUCCESS) r = api->Recv(above, cnt, NCCL_FLOAT32, rank - 1, c, st);
+    }
+    if (rank < n - 1) {
+        if (r == NCCL_SUCCESS) r = api->Send(last, cnt, NCCL_FLOAT32, rank + 1, c, st);
+        if (r == NCCL_SUCCESS) r = api->Recv(below, cnt, NCCL_FLOAT32, rank + 1, c, st);
+    }
+    const int re = api->GroupEnd();
+    if (r != NCCL_SUCCESS) return fail_nccl(r, "ncclSend / ncclRecv");
+    if (re != NCCL_SUCCESS) return fail_nccl(re, "ncclGroupEnd");
+    return 0;
+}
+
+extern "C" int pb200_comm_allreduce_u64(pb200_ctx *ctx, uint64_t *values, int n, void *stream) {
+    if (!ctx || !values || n < 1) return fail(PB200_E_INVALID_ARG, "pb200_comm_allreduce_u64: bad argument");
+    if (!ctx->comm.comm) return fail(PB200_E_INVALID_ARG, "pb200_comm_allreduce_u64: pb200_comm_init has not been called");
+    NcclApi *api;
+    int rc = need_nccl(&api);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->comm.nranks == 1) return 0;
+    CKN(api->AllReduce(values, values, (size_t)n, NCCL_UINT64, NCCL_SUM, ctx->comm.comm, (cudaStream_t)stream));
     return 0;
 }

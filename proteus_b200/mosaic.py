@@ -75,8 +75,33 @@ def exchange_dem_halo(dem_ext, n_rows, rank, world, group=None):
     return dist.batch_isend_irecv(ops) if ops else []
 
 
+def init_library_comm(ctx, rank, world, group=None):
+    """Give ``ctx`` (a ``proteus_b200.Context``) the NCCL communicator of the C ABI (``pb200_comm_init``): rank 0
+    draws the unique id, ``torch.distributed`` (any backend - here it is only the host channel for 128 bytes) hands it
+    round, every rank joins.  Collective over ``group``."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from . import _lib
+    lib = ctx._lib
+    idb = (C.c_uint8 * _lib.COMM_ID_BYTES)()
+    if rank == 0:
+        _lib.check(lib.pb200_comm_unique_id(idb))
+    if world > 1:
+        box = [bytes(idb) if rank == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        idb = (C.c_uint8 * _lib.COMM_ID_BYTES)(*box[0])
+    _lib.check(lib.pb200_comm_init(ctx.handle, idb, int(rank), int(world)))
+    return ctx
+
+
 class MosaicStrip:
     """One rank's row strip of an oversized raster, device resident.
+
+    ``exchange``: 'torch' - ``torch.distributed`` P2P batch (NCCL on GPUs, gloo in the CPU tests); 'library' - the C
+    ABI's own exchange (``pb200_halo_exchange_dem`` on the communicator of ``init_library_comm``), what a non-Python
+    host uses.  ``overlap``: True - exchange on a side stream while the interior rows are classified, the two
+    boundary rows afterwards (two launches); False - exchange first, then ONE launch over the whole strip.
 
     Parameters
     ----------
@@ -88,11 +113,15 @@ class MosaicStrip:
 
     def __init__(self, bands, fmask, dem_local, land, ocean, r0, r1, height, *,
                  sun_azimuth, sun_elevation, params=None, outputs=None,
-                 margin=DEM_MARGIN_IN_PIXELS, rank=0, world=1, group=None, ctx=None):
+                 margin=DEM_MARGIN_IN_PIXELS, rank=0, world=1, group=None, ctx=None,
+                 exchange='torch', overlap=True):
         import torch
         from .engine import GRADED_LAYERS, Plan, get_context
         from .params import make_params
         self.rank, self.world, self.group = int(rank), int(world), group
+        if exchange not in ('torch', 'library'):
+            raise ValueError("exchange: 'torch' or 'library'")
+        self.exchange, self.overlap = exchange, bool(overlap)
         self.r0, self.r1, self.height = int(r0), int(r1), int(height)
         n = self.r1 - self.r0
         self.n_rows = n
@@ -112,6 +141,7 @@ class MosaicStrip:
         self.params = params if params is not None else make_params()
         self.layers = tuple(outputs or GRADED_LAYERS)
         ctx = ctx or get_context()
+        self.ctx = ctx
         dev = fmask.device
         self.outputs = {name: torch.empty((n, w), device=dev,
                                           dtype=torch.int16 if name == 'DIAG' else torch.uint8)
@@ -128,40 +158,72 @@ class MosaicStrip:
             outs = {k: v[a:b] for k, v in self.outputs.items()}
             return t, outs
 
-        edge_rows = [(0, 1)] + ([(n - 1, n)] if n > 1 else [])
-        self._interior = None
-        if n > 2:
-            t, o = sub((1, n - 1))
-            self._interior = Plan([t], self.params, self.layers, ctx=ctx, outputs_into=[o],
-                                  counters_into=self.counters)
-        tiles, outs = zip(*[sub(r) for r in edge_rows])
-        self._edges = Plan(list(tiles), self.params, self.layers, ctx=ctx, outputs_into=list(outs),
-                           counters_into=self.counters.expand(len(tiles), 12))
+        self._interior = self._edges = self._whole = None
+        if self.overlap:
+            edge_rows = [(0, 1)] + ([(n - 1, n)] if n > 1 else [])
+            if n > 2:
+                t, o = sub((1, n - 1))
+                self._interior = Plan([t], self.params, self.layers, ctx=ctx, outputs_into=[o],
+                                      counters_into=self.counters)
+            tiles, outs = zip(*[sub(r) for r in edge_rows])
+            self._edges = Plan(list(tiles), self.params, self.layers, ctx=ctx, outputs_into=list(outs),
+                               counters_into=self.counters.expand(len(tiles), 12))
+        else:
+            t, o = sub((0, n))
+            self._whole = Plan([t], self.params, self.layers, ctx=ctx, outputs_into=[o], counters_into=self.counters)
         self._side = torch.cuda.Stream(device=dev) if fmask.is_cuda else None
 
+    def _exchange(self, halo, stream):
+        """Fill the two halo rows of ``dem_ext`` on ``stream`` (the current stream of the caller's context)."""
+        import ctypes as C
+        from . import _lib
+        if halo is not None:
+            if halo[0] is not None:
+                self.dem_ext[0].copy_(halo[0])
+            if halo[1] is not None:
+                self.dem_ext[self.n_rows + 1].copy_(halo[1])
+        elif self.exchange == 'library':
+            _lib.check(self.ctx._lib.pb200_halo_exchange_dem(
+                self.ctx.handle, self.dem_ext.data_ptr(), self.n_rows, int(self.dem_ext.shape[1]),
+                C.c_void_p(stream.cuda_stream)))
+        else:
+            for r in exchange_dem_halo(self.dem_ext, self.n_rows, self.rank, self.world, self.group):
+                r.wait()
+
     def run(self, halo=None):
-        """Halo exchange overlapped with the interior rows, then the two
-        boundary rows.  Asynchronous on the current stream.
+        """One classification of the strip, asynchronous on the current stream: the halo exchange (overlapped with
+        the interior rows when ``overlap``), then the rows that need it.
 
         ``halo`` = (row_above, row_below) tensors (either may be None) replaces
         the exchange - used to emulate several ranks inside one process."""
         import torch
         cur = torch.cuda.current_stream()
+        if not self.overlap:
+            self._exchange(halo, cur)
+            self._whole.run(cur)
+            return
         self._side.wait_stream(cur)
         with torch.cuda.stream(self._side):
-            if halo is not None:
-                if halo[0] is not None:
-                    self.dem_ext[0].copy_(halo[0])
-                if halo[1] is not None:
-                    self.dem_ext[self.n_rows + 1].copy_(halo[1])
-            else:
-                reqs = exchange_dem_halo(self.dem_ext, self.n_rows, self.rank, self.world, self.group)
-                for r in reqs:
-                    r.wait()
+            self._exchange(halo, self._side)
         if self._interior is not None:
             self._interior.run(cur)
         cur.wait_stream(self._side)
         self._edges.run(cur)
+
+    def allreduce_counters(self):
+        """Raster-wide coverage counters on every rank (D:5104-5111 over the whole raster): one 3 x uint64 sum."""
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        if self.world == 1:
+            return self.counters
+        if self.exchange == 'library':
+            _lib.check(self.ctx._lib.pb200_comm_allreduce_u64(
+                self.ctx.handle, self.counters.data_ptr(), 3, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        else:
+            dist.all_reduce(self.counters, op=dist.ReduceOp.SUM, group=self.group)
+        return self.counters
 
     def zero_counters(self):
         self.counters.zero_()

@@ -569,7 +569,10 @@ def test_full_size_mosaic_strips_equal_the_whole_raster(pb):
     ref = whole.outputs[0]
     ref_counters = whole.counters[0].clone()
     summed = torch.zeros_like(ref_counters)
-    for rank, (r0, r1) in enumerate(mosaic.strip_bounds(size, world)):
+    bounds = mosaic.strip_bounds(size, world)
+    half = 32                                      # rows kept on either side of a seam for the oracle
+    kept = {}                                      # row -> {layer: numpy row}, taken from the STRIP outputs
+    for rank, (r0, r1) in enumerate(bounds):
         d0, d1 = mosaic.dem_rows_for_strip(r0, r1, size, m)
         strip = mosaic.MosaicStrip([b[r0:r1] for b in t['bands']], t['fmask'][r0:r1], t['dem'][d0:d1].clone(),
                                    t['land'][r0:r1], t['ocean'][r0:r1], r0, r1, size,
@@ -579,8 +582,24 @@ def test_full_size_mosaic_strips_equal_the_whole_raster(pb):
         torch.cuda.synchronize()
         for name in pb.GRADED_LAYERS:
             assert torch.equal(strip.outputs[name], ref[name][r0:r1]), (name, rank)
+        for a, b in ((0, half), (r1 - r0 - half, r1 - r0)):
+            block = {name: strip.outputs[name][a:b].cpu().numpy() for name in pb.GRADED_LAYERS}
+            for i in range(b - a):
+                kept[r0 + a + i] = {name: block[name][i] for name in pb.GRADED_LAYERS}
         summed += strip.counters.reshape(-1)[:summed.numel()]
         del strip
+    # the seams against the ORACLE: 32 rows on either side of each of the 7 strip boundaries, the rows whose DEM
+    # stencil (D:4255) reaches into the neighbouring rank's rows - taken from the strips' own outputs
+    keymap = {'WTR': 'WTR_COLLAPSED', 'BWTR': 'BWTR', 'CONF': 'CONF', 'DIAG': 'DIAG'}
+    for (_, seam) in bounds[:-1]:
+        a, b = seam - half, seam + half
+        o = O.reference_chain([x[a:b].cpu().numpy() for x in t['bands']], t['fmask'][a:b].cpu().numpy(),
+                              t['dem'][a:b + 2 * m].cpu().numpy(), t['land'][a:b].cpu().numpy(),
+                              t['ocean'][a:b].cpu().numpy(), t['sun_azimuth'], t['sun_elevation'])
+        for name, key in keymap.items():
+            got = np.stack([kept[r][name] for r in range(a, b)])
+            got = got.view(np.uint16) if name == 'DIAG' else got
+            assert np.array_equal(got, o[key]), (name, seam, int((got != o[key]).sum()))
     assert torch.equal(summed[:3], ref_counters[:3])
     wtr, bwtr = ref['WTR'], ref['BWTR']
     assert torch.equal(torch.where((wtr >= 1) & (wtr <= 2), torch.ones_like(wtr), wtr), bwtr)      # D:1727 on collapsed WTR
@@ -624,6 +643,11 @@ def test_full_size_l30_minimal_fused_equals_function_chain(pb):
     assert np.array_equal(got['WTR'], wtr)
     cov = got['coverage']
     assert cov['n_valid'] == int((~invalid).sum())
+    # ... and the whole tile against the ORACLE (the numpy chain without DEM / LAND / ocean runs in a few seconds)
+    ref = O.reference_chain(raw, fmask, None, None, None, 150.0, 45.0)
+    assert np.array_equal(got['DIAG'], ref['DIAG'])
+    assert np.array_equal(got['WTR'], ref['WTR'])
+    assert np.array_equal(got['counters'][:3], ref['counters'])
 
 
 def test_host_path_reuses_resident_ancillary_rasters(pb):
