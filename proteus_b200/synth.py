@@ -158,13 +158,17 @@ def make_tile(tile_id=0, height=HLS_TILE, width=HLS_TILE, *, with_dem=True,
 def make_device_batch(n_tiles, height=HLS_TILE, width=HLS_TILE, *,
                       device='cuda', seed=1000, n_distinct=4,
                       shared_ancillary=False, dem_margin=DEM_MARGIN,
-                      full_product=True):
+                      full_product=True, adversarial=False):
     """Fill ``n_tiles`` device-resident tiles with torch RNG (benchmark data).
 
     Cheap, blocky but representative: surface type per 64x64 cell, per-pixel
     uniform noise inside the type's range, the same outlier / wrap / fill
     shares as ``make_tile``.  Only ``n_distinct`` different tiles are drawn;
     the rest are rolled copies (distinct memory, so nothing is cache-hot).
+
+    ``adversarial=True``: full-range int16 noise in every band (the int16 sums of about 40 % of the pixels wrap
+    and take the kernel's scalar patch path) and uniform random Fmask / LAND bytes, like ``make_tile``'s - the
+    data-dependent worst case.
 
     Returns a list of dicts of torch tensors with the ``make_tile`` keys."""
     import torch
@@ -200,6 +204,8 @@ def make_device_batch(n_tiles, height=HLS_TILE, width=HLS_TILE, *,
                                 generator=g, dtype=torch.int16)
             val = torch.where(outlier < 0.10, noise, val)
             val = torch.where(outlier > 0.999, sat, val)
+            if adversarial:
+                val = torch.randint(-32768, 32768, (h, w), device=device, generator=g, dtype=torch.int16)
             val = torch.where(wedge, torch.full_like(val, -9999), val)
             bands.append(val.contiguous())
         cl_c = torch.rand((ch, cw), device=device, generator=g)
@@ -212,6 +218,8 @@ def make_device_batch(n_tiles, height=HLS_TILE, width=HLS_TILE, *,
         fmask = ((cloud.to(torch.uint8) << 1) | (adj.to(torch.uint8) << 2) |
                  (shd.to(torch.uint8) << 3) | (snow.to(torch.uint8) << 4) |
                  ((tix == 0).to(torch.uint8) << 5) | (aer << 6))
+        if adversarial:
+            fmask = torch.randint(0, 256, (h, w), device=device, generator=g, dtype=torch.uint8)
         fmask = torch.where(wedge, torch.full_like(fmask, 255), fmask).contiguous()
         d = dict(height=h, width=w, bands=bands, fmask=fmask, dem=None,
                  land=None, ocean=None, dem_margin=m)
@@ -233,6 +241,8 @@ def make_device_batch(n_tiles, height=HLS_TILE, width=HLS_TILE, *,
         ).reshape(-(-h // 32), -(-w // 32))
         land = torch.tensor([255, 200, 201, 21, 121], dtype=torch.uint8,
                             device=device)[coarse_to_full(lc, h, w, 32)].contiguous()
+        if adversarial:
+            land = torch.randint(0, 256, (h, w), device=device, generator=g, dtype=torch.uint8)
         shore = 0.9 * w + 0.03 * w * torch.sin(
             torch.arange(h, device=device) / max(h, 1) * 9.0)
         ocean = (torch.arange(w, device=device)[None, :] <
