@@ -427,6 +427,46 @@ static void build_fast_params(const pb200_params *p, const DevParams &D, FastPar
     F->tan32 = ok ? (float)D.tan_thr : 0.0f;
     F->e0 = 1e-6f * std::fabs(F->tan32) + 1e-30f;
     F->cc32 = ok ? (float)(D.cos_thr * std::fabs(D.cos_thr)) : 0.0f;
+
+    // ---- FAST8: the kernel variant for parameters shaped like the defaults (pb200_fused.cuh) ------------------------
+    bool f8 = ok && !F->any_nofill;
+    for (int k = 0; k < 6; ++k) {
+        const uint32_t h = (uint32_t)(-p->band_fill[k]) & 0xffffu;
+        F->nfill[k] = h | (h << 16);
+    }
+    // rational tests as one dp2a on a per-pixel pack.  x = sa*q + nsb*n < 0 <=> test true (strict forms above).
+    //   MNDWI: q = gs = G + S1, n = G - S1 = -dg  ->  sa * gs + (-nsb) * dg        on the pack (gs, dg)
+    //   NDVI:  q = N + R, n = N - R               ->  (nsb + sa) * N + (sa - nsb) * R   on the pack (N, R)
+    auto bytes = [](int b0, int b1) { return (uint32_t)(b0 & 0xff) | ((uint32_t)(b1 & 0xff) << 8); };
+    auto fits_s8 = [](int v) { return v >= -128 && v <= 127; };
+    auto fits_u8 = [](int v) { return v >= 0 && v <= 255; };
+    {
+        const int q0 = F->sa[RB_WIGT], d0 = -F->nsb[RB_WIGT];
+        f8 = f8 && fits_u8(q0) && fits_u8(d0);
+        F->c_wigt = bytes(q0, d0);
+        const int q1 = F->sa[RB_P1_MNDWI], d1 = -F->nsb[RB_P1_MNDWI];
+        f8 = f8 && fits_s8(q1) && fits_s8(d1);
+        F->c_p1 = bytes(q1, d1);
+        const int q2 = F->sa[RB_P2_MNDWI], d2 = -F->nsb[RB_P2_MNDWI];
+        f8 = f8 && fits_s8(q2) && fits_s8(d2);
+        F->c_p2 = bytes(q2, d2);
+        const int cn = F->nsb[RB_P1_NDVI] + F->sa[RB_P1_NDVI], cr = F->sa[RB_P1_NDVI] - F->nsb[RB_P1_NDVI];
+        f8 = f8 && fits_s8(cn) && fits_s8(cr);
+        F->c_ndvi = bytes(cn, cr);
+        F->c_aw_gd = bytes(-2, 8);      // -2 gs + 8 dg = -10 G + 6 S1
+        F->c_aw_nr = bytes(6, 0);       // 6 N
+        F->c_aw_b = 0xFC0000FCu;        // -4 B
+        F->c_aw_s2 = 0x01000001u;       // + S2
+    }
+    // shadow shortcut on sign bits: needs cos_thr > 0 (dot^2 form) and tan_thr < 0 with a margin ("x <= 1" is implied)
+    f8 = f8 && D.cos_thr > 0.01 && D.cos_thr <= 1.0 && D.tan_thr <= -0.005;
+    F->sh_c7 = 7.08e-7f;
+    {
+        const double cc = D.cos_thr * D.cos_thr;
+        F->ncc_hi = -(float)(cc + 4e-6);
+        F->ncc_lo = -(float)(cc - 4e-6);
+    }
+    F->fast8 = f8 ? 1u : 0u;
 }
 
 // ---------------------------------------------------------------------------
@@ -495,6 +535,7 @@ struct pb200_plan {
     int n_items = 0;
     bool fast_optional = false;                      // some fast tile wants WTR-1 / WTR-2 / CLOUD / SHAD
     bool fast_all_graded = true;                     // every fast tile writes DIAG, WTR, BWTR and CONF
+    bool no_fast8 = false;                           // PB200_NO_FAST8=1: run the general variant (A/B, tests)
     bool stream_ordered = false;                     // allocated with cudaMallocAsync
     bool from_arena = false;                         // allocated from a caller-owned arena: nothing to free
     // per input tile: where it went (for launching one tile of the plan on its own)
@@ -663,6 +704,10 @@ static int plan_build(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles, cons
     build_fast_params(params, pl->P, &pl->F);
     pl->ctx = ctx;
     pl->stream_ordered = stream_ordered;
+    {
+        const char *e = std::getenv("PB200_NO_FAST8");
+        pl->no_fast8 = e && *e && *e != '0';
+    }
     std::vector<TileDev> td[N_GROUPS];
     std::vector<CUtensorMap> tm[N_GROUPS];
     std::vector<ItemDesc> items;
@@ -759,6 +804,12 @@ static int fast_kernel_setup(pb200_ctx *ctx) {
                                 (int)FAST_DYN_SMEM));
         CK(cudaFuncSetAttribute(dswx_fused_fast_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)FAST_DYN_SMEM));
+        CK(cudaFuncSetAttribute(dswx_fused_fast_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)FAST_DYN_SMEM));
+        CK(cudaFuncSetAttribute(dswx_fused_fast_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)FAST_DYN_SMEM));
+        CK(cudaFuncSetAttribute(dswx_fused_fast_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)FAST_DYN_SMEM));
     }
     int nb = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dswx_fused_fast_kernel<false>, FtGeom<false>::THREADS, FAST_DYN_SMEM));
@@ -769,21 +820,25 @@ static int fast_kernel_setup(pb200_ctx *ctx) {
     return 0;
 }
 
+// the fast kernel over `n` items: variant by what the tiles write and by the shape of the parameters
+static void launch_fast(pb200_plan *pl, const ItemDesc *it, int n, cudaStream_t stream) {
+    const pb200_ctx *ctx = pl->ctx;
+    const int grid = std::min(n, ctx->sm_count * (pl->fast_optional ? ctx->fast_ctas_per_sm_full : ctx->fast_ctas_per_sm));
+    const bool f8 = pl->F.fast8 != 0u && !pl->no_fast8;
+#define PB200_LAUNCH_FAST(OPT, GRADED, F8)                                                                         \
+    dswx_fused_fast_kernel<OPT, GRADED, F8><<<grid, FtGeom<OPT>::THREADS, FAST_DYN_SMEM, stream>>>(                 \
+        pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, it, n, pl->P, pl->F)
+    if (pl->fast_optional) { if (f8) PB200_LAUNCH_FAST(true, false, true); else PB200_LAUNCH_FAST(true, false, false); }
+    else if (pl->fast_all_graded) { if (f8) PB200_LAUNCH_FAST(false, true, true); else PB200_LAUNCH_FAST(false, true, false); }
+    else { if (f8) PB200_LAUNCH_FAST(false, false, true); else PB200_LAUNCH_FAST(false, false, false); }
+#undef PB200_LAUNCH_FAST
+}
+
 static int plan_launch(pb200_plan *pl, cudaStream_t stream) {
     if (pl->n[G_FAST]) {
         int rc = fast_kernel_setup(pl->ctx);
         if (rc) return rc;
-        const int grid = std::min(pl->n_items, pl->ctx->sm_count * (pl->fast_optional ? pl->ctx->fast_ctas_per_sm_full
-                                                                                       : pl->ctx->fast_ctas_per_sm));
-        if (pl->fast_optional)
-            dswx_fused_fast_kernel<true><<<grid, FtGeom<true>::THREADS, FAST_DYN_SMEM, stream>>>(
-                pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, pl->d_items, pl->n_items, pl->P, pl->F);
-        else if (pl->fast_all_graded)
-            dswx_fused_fast_kernel<false, true><<<grid, FtGeom<false>::THREADS, FAST_DYN_SMEM, stream>>>(
-                pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, pl->d_items, pl->n_items, pl->P, pl->F);
-        else
-            dswx_fused_fast_kernel<false><<<grid, FtGeom<false>::THREADS, FAST_DYN_SMEM, stream>>>(
-                pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, pl->d_items, pl->n_items, pl->P, pl->F);
+        launch_fast(pl, pl->d_items, pl->n_items, stream);
     }
     if (pl->n[G_VEC]) {
         dim3 grid(pl->max_ctas[G_VEC], pl->n[G_VEC]);
@@ -803,19 +858,7 @@ static int plan_launch_tile(pb200_plan *pl, int i, cudaStream_t stream) {
     if (g == G_FAST) {
         int rc = fast_kernel_setup(pl->ctx);
         if (rc) return rc;
-        const int n = pl->item_end[i] - pl->item_start[i];
-        const int grid = std::min(n, pl->ctx->sm_count * (pl->fast_optional ? pl->ctx->fast_ctas_per_sm_full
-                                                                            : pl->ctx->fast_ctas_per_sm));
-        const ItemDesc *it = pl->d_items + pl->item_start[i];
-        if (pl->fast_optional)
-            dswx_fused_fast_kernel<true><<<grid, FtGeom<true>::THREADS, FAST_DYN_SMEM, stream>>>(
-                pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, it, n, pl->P, pl->F);
-        else if (pl->fast_all_graded)
-            dswx_fused_fast_kernel<false, true><<<grid, FtGeom<false>::THREADS, FAST_DYN_SMEM, stream>>>(
-                pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, it, n, pl->P, pl->F);
-        else
-            dswx_fused_fast_kernel<false><<<grid, FtGeom<false>::THREADS, FAST_DYN_SMEM, stream>>>(
-                pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, it, n, pl->P, pl->F);
+        launch_fast(pl, pl->d_items + pl->item_start[i], pl->item_end[i] - pl->item_start[i], stream);
     } else if (g == G_VEC) {
         dswx_fused_kernel<true><<<dim3(pl->tile_ctas[i], 1), NTHREADS, 0, stream>>>(pl->d_tiles[g] + slot,
                                                                                     pl->d_maps[g] + slot, pl->P);

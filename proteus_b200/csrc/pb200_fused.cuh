@@ -117,6 +117,17 @@ struct FastParams {
     float    tan32, e0, cc32;           // float32(tan_thr), 1e-6*|tan_thr| + 1e-30, c*|c| with c = cos_thr
     uint32_t fast_shadow_ok;            // thresholds are finite and |cos_thr| <= 1
     uint32_t any_nofill;                // some band has no fill value (fill_or != 0)
+    // ---- FAST8 variant (parameters shaped like the defaults; build_fast_params decides) --------------------------
+    uint32_t nfill[6];                  // packed -fill: (raw + nfill) half == 0 <=> raw == fill
+    // the rational tests as ONE dp2a each on a per-pixel pack: sign(b0 * lo16 + b1 * hi16) <=> test true
+    uint32_t c_wigt;                    // on (gs, dg), dg = S1 - G: unsigned bytes (wigt > 0: both coefficients positive)
+    uint32_t c_p1, c_p2;                // on (gs, dg): signed bytes
+    uint32_t c_ndvi;                    // on (N, R): signed bytes
+    uint32_t c_aw_gd, c_aw_nr;          // 4*awesh terms on the same packs: -2 gs + 8 dg (= -10 G + 6 S1), 6 N
+    uint32_t c_aw_b, c_aw_s2;           // -4 B and + S2 on the two-pixel registers (byte 0 for .lo, byte 3 for .hi)
+    float    sh_c7;                     // e' = sh_c7 * v + e0 >= 1e-6 (|t1| + |t2|) + e0   (|t1| + |t2| <= v / sqrt 2)
+    float    ncc_hi, ncc_lo;            // -(c|c| + 4e-6), -(c|c| - 4e-6)
+    uint32_t fast8;                     // every FAST8 precondition holds
 };
 
 struct __align__(128) DemHalf { float v[FT_SMH][FT_SMW]; };   // TMA destination: 128-B aligned
@@ -166,6 +177,50 @@ __device__ __forceinline__ uint32_t shadow_fast(float l, float r, float u, float
     const bool not_shadow = (diff > e) || ((D > eg) && (L < 0.99999f * v));
     *undecided = *undecided || !(is_shadow || not_shadow);
     return is_shadow ? BIG_SHADOWED : 0u;
+}
+
+// dp2a with signed 16-bit halves and UNSIGNED bytes (IDP.2A.LO.S16.U8): c + lo16(a) * b.byte0 + hi16(a) * b.byte1
+__device__ __forceinline__ int dp2a_lo_s16_u8(uint32_t a, uint32_t b, int c) {
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// FAST8 flavour of the shortcut for TWO pixels at once on the packed float32 pipe (FFMA2 / FMUL2 / FADD2: one
+// instruction, two pixels; scalar operands are broadcast), with every decision read off SIGN BITS instead of float
+// compares (no FSETP / PLOP3).  Same quantities and the same error budget as shadow_fast, with
+//   * e' = c7 * v + e0 >= e: |t1| + |t2| <= k (|a| + |b|) <= sqrt(2) k sqrt(a^2 + b^2) = sqrt(2 (v - 1)) <= v / sqrt(2);
+//   * dot^2 against (c|c| -+ 4e-6) v instead of dot |dot| - c|c| v against -+ 4e-6 v, the sign of dot taken separately
+//     (FAST8 requires cos_thr > 0.01: when dot^2 > c^2 v, |dot| > 0.01 and its float32 sign is exact);
+//   * no "x <= 1" test: FAST8 requires tan_thr <= -0.005, and a back slope s <= tan_thr < 0 has |n_xy| >= |tan_thr|,
+//     so x = dot / nf <= 1 / sqrt(1 + tan_thr^2) < 0.99999 (dot <= cos(zen) - sin(zen) |tan_thr| <= 1).
+// is / nt: bit 31 set <=> certainly shadow / certainly not shadow; non-finite inputs make v non-finite, which the
+// caller detects on the sum of the four v's.
+__device__ __forceinline__ void shadow_fast2(float2 l, float2 r, float2 u, float2 d, const FastParams &F,
+                                             const float (&K)[SK_N], uint32_t (&is)[2], uint32_t (&nt)[2], float2 *v_out) {
+    const float2 neg1 = make_float2(-1.0f, -1.0f);
+    const float2 a = __ffma2_rn(r, neg1, l), b = __ffma2_rn(d, neg1, u);      // l - r, u - d: exact float32 differences
+    const float2 diff = __ffma2_rn(a, make_float2(K[SK_SA], K[SK_SA]),
+                                   __ffma2_rn(b, make_float2(K[SK_CA], K[SK_CA]), make_float2(-F.tan32, -F.tan32)));
+    const float2 dot = __ffma2_rn(a, make_float2(K[SK_SX], K[SK_SX]),
+                                  __ffma2_rn(b, make_float2(K[SK_SY], K[SK_SY]), make_float2(K[SK_SZ], K[SK_SZ])));
+    const float2 v = __ffma2_rn(__ffma2_rn(a, a, __fmul2_rn(b, b)), make_float2(K[SK_XX], K[SK_XX]), make_float2(1.0f, 1.0f));
+    const float2 e = __ffma2_rn(v, make_float2(F.sh_c7, F.sh_c7), make_float2(F.e0, F.e0));
+    const float2 p1 = __fadd2_rn(diff, e);                                    // < 0 <=> diff < -e   (back slope)
+    const float2 q2 = __ffma2_rn(diff, neg1, e);                              // < 0 <=> diff >  e   (not a back slope)
+    const float2 dd = __fmul2_rn(dot, dot);
+    const float2 qlo = __ffma2_rn(v, make_float2(F.ncc_lo, F.ncc_lo), dd);    // < 0 <=> |x| certainly below cos_thr
+    const float2 qhi = __ffma2_rn(v, make_float2(F.ncc_hi, F.ncc_hi), dd);    // >= 0 <=> |x| certainly above cos_thr
+    const uint32_t p1b[2] = {__float_as_uint(p1.x), __float_as_uint(p1.y)}, q2b[2] = {__float_as_uint(q2.x), __float_as_uint(q2.y)};
+    const uint32_t lob[2] = {__float_as_uint(qlo.x), __float_as_uint(qlo.y)}, hib[2] = {__float_as_uint(qhi.x), __float_as_uint(qhi.y)};
+    const uint32_t dtb[2] = {__float_as_uint(dot.x), __float_as_uint(dot.y)};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        // shadow: back slope and (|x| < thr, or |x| > thr with dot < 0);  lit: no back slope, or |x| > thr with dot > 0
+        is[i] = p1b[i] & (lob[i] | (~hib[i] & dtb[i]));
+        nt[i] = q2b[i] | ~(hib[i] | dtb[i]);
+    }
+    *v_out = v;
 }
 
 // Shared-memory reads through an explicit 32-bit shared address: the base is computed once per thread
@@ -224,7 +279,9 @@ __device__ __noinline__ uint32_t shadow_exact(float l, float r, float u, float d
 // ALL_GRADED: the tile batch writes all four graded layers (the product's configuration): no pointer tests in the row
 // loop.  The lean kernel is also instantiated without it for subsets such as DIAG + WTR (BASELINE configs[0]); a
 // run-time test in the one instantiation measured 2.5 % slower on the full product.
-template <bool OPTIONAL_LAYERS, bool ALL_GRADED = false>
+// FAST8: parameters shaped like the defaults (FastParams::fast8): fill test as one add-min chain, each rational test
+// as one IDP.2A on a per-pixel pack, the terrain-shadow shortcut on the packed float32 pipe with sign-bit decisions.
+template <bool OPTIONAL_LAYERS, bool ALL_GRADED = false, bool FAST8 = false>
 __global__ void __launch_bounds__(FtGeom<OPTIONAL_LAYERS>::THREADS, 1)
 dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__restrict__ tmaps,
                        const FusedTables *__restrict__ tables, const ItemDesc *__restrict__ items, int n_items,
@@ -331,6 +388,14 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                 s.sun32[SK_SX] = (float)(kx * g.sx); s.sun32[SK_SY] = (float)(ky * g.sy); s.sun32[SK_SZ] = (float)g.sz;
                 s.sun32[SK_XX] = (float)(kx * kx);
                 s.sun32[SK_EA] = 1e-6f * fabsf(s.sun32[SK_SA]); s.sun32[SK_EB] = 1e-6f * fabsf(s.sun32[SK_CA]);
+                if (FAST8) {
+                    // "x <= 1 is implied for back slopes" needs a sun whose horizontal component points along
+                    // (sin az, cos az), i.e. sin(zenith) >= 0, and a unit sun vector; any other tile (elevation outside
+                    // 0..90 degrees, hand-made sun_terms) runs the exact sequence on every pixel: NaN makes v NaN
+                    const double hz = g.sx * g.sin_az + g.sy * g.cos_az, n2 = g.sx * g.sx + g.sy * g.sy + g.sz * g.sz;
+                    if (!(hz >= 0.0 && fabs(n2 - 1.0) < 1e-9 && fabs(g.sin_az * g.sin_az + g.cos_az * g.cos_az - 1.0) < 1e-9))
+                        s.sun32[SK_XX] = __int_as_float(0x7fffffff);
+                }
             }
             cur_tile = item.tile;
             ld4 = 0xffffffffu; oc4 = 0x01010101u;         // defaults of a tile without LAND / ocean raster
@@ -400,7 +465,13 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                     const uint32_t selb = p ? 0x4342u : 0x4140u;              // bytes -> 16-bit halves
                     const uint32_t fmh = __byte_perm(fm4, 0u, selb);          // Fmask values as halves
                     uint32_t xm;
-                    {
+                    if constexpr (FAST8) {
+                        // every band has a fill value: (raw - fill) mod 2^16 == 0 <=> raw == fill, min-reduced in one
+                        // VIADDMNMX.U16x2 per band                                                    D:2204-2207
+                        xm = __byte_perm(fm4 ^ F.fmask_xor4, 0u, selb) | F.fmask_or;
+#pragma unroll
+                        for (int k = 5; k >= 0; --k) xm = __viaddmin_u16x2(w[k][p], F.nfill[k], xm);   // half == 0 <=> invalid
+                    } else {
                         uint32_t xf[6];
 #pragma unroll
                         for (int k = 0; k < 6; ++k) xf[k] = (w[k][p] ^ F.fill_xor[k]) | F.fill_or[k];   // D:2204-2207 (one LOP3)
@@ -414,9 +485,12 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                     const uint32_t B = __vmaxs2(w[0][p], 0x00010001u), G = __vmaxs2(w[1][p], 0x00010001u);   // D:2299
                     const uint32_t R = __vmaxs2(w[2][p], 0x00010001u), N = __vmaxs2(w[3][p], 0x00010001u);
                     const uint32_t S1 = __vmaxs2(w[4][p], 0x00010001u), S2 = __vmaxs2(w[5][p], 0x00010001u);
-                    const uint32_t gs = __vadd2(G, S1), gd = __vsub2(G, S1);                                 // D:1872
+                    const uint32_t gs = __vadd2(G, S1);                                                      // D:1872
                     const uint32_t gr = __vadd2(G, R), ns = __vadd2(N, S1);                                  // D:1875-1878
-                    const uint32_t nrs = __vadd2(N, R), nrd = __vsub2(N, R);                                 // D:1884
+                    const uint32_t nrs = __vadd2(N, R);                                                      // D:1884
+                    // numerators: FAST8 needs S1 - G only (NDVI runs on the (N, R) pack)
+                    const uint32_t gd = FAST8 ? __vsub2(S1, G) : __vsub2(G, S1);
+                    const uint32_t nrd = FAST8 ? 0u : __vsub2(N, R);
                     const bool slow = ((gs | gr | ns | nrs) & 0x80008000u) != 0u;      // some int16 sum wrapped
                     const uint32_t T4 = __viaddmax_s16x2(N, F.m_p1nir, __vadd2(S1, F.m_p1swir1));           // < 0 <=> all below
                     const uint32_t T5 = __viaddmax_s16x2(N, F.m_p2nir, __viaddmax_s16x2(S2, F.m_p2swir2,
@@ -444,17 +518,36 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
 #pragma unroll
                         for (int hh = 0; hh < 2; ++hh) {
                             const bool hi = hh;
+                            int x0w, x1w, x2w, x3w, aw = F.awesh_init;
+                            if constexpr (FAST8) {
+                                // per-pixel packs (lo, hi) = (gs, S1 - G) and (N, R); sign set <=> test true
+                                const uint32_t pgd = __byte_perm(gs, gd, hi ? 0x7632 : 0x5410);
+                                const uint32_t pnr = __byte_perm(N, R, hi ? 0x7632 : 0x5410);
+                                x0w = dp2a_lo_s16_u8(pgd, F.c_wigt, 0);
+                                x1w = __dp2a_lo((int)pgd, (int)F.c_p1, 0);
+                                x2w = __dp2a_lo((int)pgd, (int)F.c_p2, 0);
+                                x3w = __dp2a_lo((int)pnr, (int)F.c_ndvi, 0);
+                                // 4*awesh: init - 4B - 10G + 6 N + 6 S1 + S2 < 0 <=> awesh > awgt
+                                aw = __dp2a_lo((int)pgd, (int)F.c_aw_gd, aw);
+                                aw = __dp2a_lo((int)pnr, (int)F.c_aw_nr, aw);
+                                if (hi) {
+                                    aw = __dp2a_hi((int)B, (int)F.c_aw_b, aw);
+                                    aw = __dp2a_hi((int)S2, (int)F.c_aw_s2, aw);
+                                } else {
+                                    aw = __dp2a_lo((int)B, (int)F.c_aw_b, aw);
+                                    aw = __dp2a_lo((int)S2, (int)F.c_aw_s2, aw);
+                                }
+                            } else {
                             const int n1 = hi ? sext_hi(gd) : sext_lo(gd);
                             const int q1 = hi ? (int)(gs >> 16) : (int)(gs & 0xffffu);
                             const int n2 = hi ? sext_hi(nrd) : sext_lo(nrd);
                             const int q2 = hi ? (int)(nrs >> 16) : (int)(nrs & 0xffffu);
                             // sign set <=> test true:  sa*q + p*(-sb) < 0 <=> p/q > sa/sb  (two IMADs)
-                            const int x0w = n1 * F.nsb[RB_WIGT] + F.sa[RB_WIGT] * q1;
-                            const int x1w = n1 * F.nsb[RB_P1_MNDWI] + F.sa[RB_P1_MNDWI] * q1;
-                            const int x2w = n1 * F.nsb[RB_P2_MNDWI] + F.sa[RB_P2_MNDWI] * q1;
-                            const int x3w = n2 * F.nsb[RB_P1_NDVI] + F.sa[RB_P1_NDVI] * q2;       // p/q < sa/sb
+                            x0w = n1 * F.nsb[RB_WIGT] + F.sa[RB_WIGT] * q1;
+                            x1w = n1 * F.nsb[RB_P1_MNDWI] + F.sa[RB_P1_MNDWI] * q1;
+                            x2w = n1 * F.nsb[RB_P2_MNDWI] + F.sa[RB_P2_MNDWI] * q1;
+                            x3w = n2 * F.nsb[RB_P1_NDVI] + F.sa[RB_P1_NDVI] * q2;       // p/q < sa/sb
                             // 4*awesh: init - 4B - 10G + 6*mbsrn + S2 < 0 <=> awesh > awgt
-                            int aw = F.awesh_init;
                             if (hi) {
                                 aw = __dp2a_hi((int)B, (int)0xFC0000FCu, aw);
                                 aw = __dp2a_hi((int)G, (int)0xF60000F6u, aw);
@@ -465,6 +558,7 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                                 aw = __dp2a_lo((int)G, (int)0xF60000F6u, aw);
                                 aw = __dp2a_lo((int)ns, (int)0x06000006u, aw);
                                 aw = __dp2a_lo((int)S2, (int)0x01000001u, aw);
+                            }
                             }
                             const uint32_t sh16 = hi ? 0u : 16u;
                             const uint32_t t2w = (hi ? p2h : p2l) ? 0u : 0x80000000u;
@@ -561,15 +655,41 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
 #pragma unroll
                         for (int j = 0; j < 4; ++j) { u[j] = lds_f32(am - RB + 4 * j); d[j] = lds_f32(am + RB + 4 * j); }
                     }
-                    bool undecided = (F.fast_shadow_ok == 0u);
                     float K[SK_N];
                     {
                         const float4 k0 = lds_f32x4(sb + FS_OFF(sun32)), k1 = lds_f32x4(sb + FS_OFF(sun32) + 16);
                         K[0] = k0.x; K[1] = k0.y; K[2] = k0.z; K[3] = k0.w; K[4] = k1.x; K[5] = k1.y; K[6] = k1.z; K[7] = k1.w;
                         static_assert(SK_N == 8, "two 16-byte loads");
                     }
+                    bool undecided;
+                    if constexpr (FAST8) {
+                        uint32_t is[4], nt[4];
+                        float2 v01, v23;
+                        {
+                            uint32_t i2[2], n2[2];
+                            shadow_fast2(make_float2(m[0], m[1]), make_float2(m[2], m[3]), make_float2(u[0], u[1]),
+                                         make_float2(d[0], d[1]), F, K, i2, n2, &v01);
+                            is[0] = i2[0]; is[1] = i2[1]; nt[0] = n2[0]; nt[1] = n2[1];
+                            shadow_fast2(make_float2(m[2], m[3]), make_float2(m[4], m[5]), make_float2(u[2], u[3]),
+                                         make_float2(d[2], d[3]), F, K, i2, n2, &v23);
+                            is[2] = i2[0]; is[3] = i2[1]; nt[2] = n2[0]; nt[3] = n2[1];
+                        }
+                        // bit 31 of `und`: some pixel neither certainly shadowed nor certainly lit, or a non-finite v
+                        // (v >= 1; exponent 0xff + 1 carries into bit 31; NaNs from float32 arithmetic are 0x7fffffff)
+                        const float2 vs2 = __fadd2_rn(v01, v23);
+                        const uint32_t vsb = __float_as_uint(vs2.x + vs2.y) + 0x00800000u;
+                        uint32_t und = vsb;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) shw[j] = shadow_fast(m[j], m[j + 2], u[j], d[j], F, K, &undecided);
+                        for (int j = 0; j < 4; ++j) {
+                            und |= ~(is[j] | nt[j]);
+                            shw[j] = (uint32_t)((int)is[j] >> 31) & BIG_SHADOWED;
+                        }
+                        undecided = (und >> 31) != 0u;
+                    } else {
+                        undecided = (F.fast_shadow_ok == 0u);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) shw[j] = shadow_fast(m[j], m[j + 2], u[j], d[j], F, K, &undecided);
+                    }
                     if (undecided) {
                         // rare: redo the 4 pixels with the float64 reference sequence
 #pragma unroll
