@@ -57,6 +57,15 @@ namespace pb200 {
 #ifndef PB200_FT_PATCH_SLOW
 #define PB200_FT_PATCH_SLOW 1      // evaluate the packed fast path unconditionally and patch wrapped pairs afterwards
 #endif
+#ifndef PB200_FT_LAND_DP4A
+#define PB200_FT_LAND_DP4A 0       // land_lut address as ONE IDP.4A (byte select + base add) instead of shift, mask, add
+#endif
+#ifndef PB200_FT_SHADOW_ALWAYS
+#define PB200_FT_SHADOW_ALWAYS 0   // FAST8: evaluate the shadow shortcut for every lane of a tile with a DEM
+#endif
+#ifndef PB200_FT_SHADOW_SCALAR
+#define PB200_FT_SHADOW_SCALAR 0   // FAST8 shadow shortcut with scalar FFMA (1) or packed FFMA2 (0)
+#endif
 #ifndef PB200_FT_XITEM_PREFETCH
 #define PB200_FT_XITEM_PREFETCH 1  // request the first row of the next item in the last row of the current one
 #endif
@@ -220,6 +229,24 @@ __device__ __forceinline__ void shadow_fast2(float2 l, float2 r, float2 u, float
         is[i] = p1b[i] & (lob[i] | (~hib[i] & dtb[i]));
         nt[i] = q2b[i] | ~(hib[i] | dtb[i]);
     }
+    *v_out = v;
+}
+
+// The same decision for ONE pixel with scalar FFMA (full rate on B200: two FFMA issue faster than one FFMA2 in a mixed
+// instruction stream, scripts/ubench/pipes2.cu)
+__device__ __forceinline__ void shadow_fast1(float l, float r, float u, float d, const FastParams &F, const float (&K)[SK_N],
+                                             uint32_t *is, uint32_t *nt, float *v_out) {
+    const float a = l - r, b = u - d;
+    const float diff = fmaf(a, K[SK_SA], fmaf(b, K[SK_CA], -F.tan32));
+    const float dot = fmaf(a, K[SK_SX], fmaf(b, K[SK_SY], K[SK_SZ]));
+    const float v = fmaf(fmaf(a, a, b * b), K[SK_XX], 1.0f);
+    const float e = fmaf(v, F.sh_c7, F.e0);
+    const uint32_t p1 = __float_as_uint(diff + e), q2 = __float_as_uint(e - diff);
+    const float dd = dot * dot;
+    const uint32_t lo = __float_as_uint(fmaf(v, F.ncc_lo, dd)), hi = __float_as_uint(fmaf(v, F.ncc_hi, dd));
+    const uint32_t dt = __float_as_uint(dot);
+    *is = p1 & (lo | (~hi & dt));
+    *nt = q2 | ~(hi | dt);
     *v_out = v;
 }
 
@@ -599,7 +626,12 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                         const uint32_t k1s = dl[hh] >> 16;                    // k1 << 8 | k1 << 2 (bank swizzle)
                         const uint32_t fi = hi ? ((fa >> 16) ^ k1s) : ((fa & 0xffffu) ^ k1s);
                         const uint32_t ev = lds_tab8(sb + FS_OFF(fk_lut) + fi);       // D:1237-1246, 1984-1991, 2081
+#if PB200_FT_LAND_DP4A
+                        // byte j of ld4 + table base in one IDP.4A (the FMA-side pipe; shift + mask + add are 2 ALU-pipe ops)
+                        const uint32_t cat = lds_tab8(__dp4a(ld4, 1u << (8 * j), sb + FS_OFF(land_lut)));
+#else
                         const uint32_t cat = lds_tab8(sb + FS_OFF(land_lut) + ((ld4 >> (8 * j)) & 255u));
+#endif
                         const uint32_t bri = hi ? (brp >> 16) : (brp & 0xffffu);
                         idx[j] = ((ev & 0x7Fu) ^ bri) + (cat << 7);          // bits 7-8 are still clear: the sum is an OR
                         water_any |= ev;                                      // bit 7: the pixel holds a water class
@@ -629,7 +661,7 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                 // ---- terrain shadow: only where it can change the result ----------------
                 // (bit 7 of a fk_lut byte = the pixel holds a water class: only those can be masked, D:1340-1343)
                 uint32_t shw[4] = {0u, 0u, 0u, 0u};                           // BIG_SHADOWED = in shadow
-                if (has_dem && (want_shad || (water_any & 0x80u))) {
+                if (has_dem && ((FAST8 && PB200_FT_SHADOW_ALWAYS) || want_shad || (water_any & 0x80u))) {
                     if (!dem_ready) {
                         mbar_wait(&s.full[buf], (fstate >> buf) & 1u);
                         dem_ready = true;
@@ -665,6 +697,13 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                     if constexpr (FAST8) {
                         uint32_t is[4], nt[4];
                         float2 v01, v23;
+#if PB200_FT_SHADOW_SCALAR
+                        shadow_fast1(m[0], m[2], u[0], d[0], F, K, &is[0], &nt[0], &v01.x);
+                        shadow_fast1(m[1], m[3], u[1], d[1], F, K, &is[1], &nt[1], &v01.y);
+                        shadow_fast1(m[2], m[4], u[2], d[2], F, K, &is[2], &nt[2], &v23.x);
+                        shadow_fast1(m[3], m[5], u[3], d[3], F, K, &is[3], &nt[3], &v23.y);
+                        const uint32_t vsb = __float_as_uint((v01.x + v01.y) + (v23.x + v23.y)) + 0x00800000u;
+#else
                         {
                             uint32_t i2[2], n2[2];
                             shadow_fast2(make_float2(m[0], m[1]), make_float2(m[2], m[3]), make_float2(u[0], u[1]),
@@ -678,6 +717,7 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                         // (v >= 1; exponent 0xff + 1 carries into bit 31; NaNs from float32 arithmetic are 0x7fffffff)
                         const float2 vs2 = __fadd2_rn(v01, v23);
                         const uint32_t vsb = __float_as_uint(vs2.x + vs2.y) + 0x00800000u;
+#endif
                         uint32_t und = vsb;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
