@@ -662,6 +662,7 @@ def run_ours(args):
                                     shared_ancillary=(args.workload == 'timeseries'))
     params = pb.make_params(collapse_wtr_classes=True)
     plan = pb.Plan(tiles, params, pb.GRADED_LAYERS)
+    kernel_name = plan.kernel_name
     stream = torch.cuda.current_stream()
 
     # cudaProfilerStart/Stop bracket the timed regions: `ncu --profile-from-start off` then lists exactly the
@@ -807,7 +808,7 @@ def run_ours(args):
                          'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                          'algorithmic_bytes_per_launch': algo_bytes, 'kernel_ms': kernel_ms,
                          'frac_of_nominal_8TBs': achieved / 8000.0,
-                         'kernel': 'pb200::dswx_fused_fast_kernel<false, true>', 'sustained': sustained},
+                         'kernel': kernel_name, 'sustained': sustained},
             'e2e': e2e, 'cpu_baseline': cpu_baseline, 'parity': parity,
             'gpu_launches': args.steps, 'clocks': clocks,
         }

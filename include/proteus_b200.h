@@ -151,6 +151,15 @@ int  pb200_classify(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles,
 int  pb200_plan_create(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles,
                        const pb200_params *params, pb200_plan **out);
 int  pb200_plan_run(pb200_plan *plan, void *stream);
+/* Which kernels the plan launches (tests, benchmarks): bit 0 fused kernel with direct loads, bit 1 fused kernel with
+ * TMA-fed inputs (tile height % 4 == 0, width >= 36, 16-byte aligned planes, the four graded layers + counters), bit 2
+ * the FAST8 flavour of either (parameters shaped like the defaults), bit 3 the generic kernel for some tile (width % 4
+ * != 0, unaligned planes, DEM not TMA-addressable). */
+#define PB200_KERNEL_FAST    1
+#define PB200_KERNEL_STREAM  2
+#define PB200_KERNEL_FAST8   4
+#define PB200_KERNEL_GENERIC 8
+int  pb200_plan_kernels(const pb200_plan *plan, int *mask);
 int  pb200_plan_destroy(pb200_plan *plan);
 /* Same contract as pb200_classify for ONE tile whose pointers are HOST
  * pointers (what generate_dswx_layers holds after gdal.ReadAsArray, D:2192).
@@ -322,6 +331,14 @@ int  pb200_ratio_bound(double t, int is_less, int32_t *a, int32_t *b);
  * pairs (d == 0 included: inf / nan semantics). Synchronous. */
 int  pb200_ratio_sweep(pb200_ctx *ctx, double t, int is_less,
                        uint64_t *mismatches);
+/* The float32 shortcuts of the terrain-shadow test (D:4264-4281) against the exact float64 sequence on n_samples DEM
+ * neighbourhoods generated on the GPU: mode 0 random gradients, 1 on the back-slope boundary (+- a relative 2^-25 ..
+ * 2^-12), 2 on the incidence boundary, 3 special values (zeros, denormals, 1e30, +-inf, NaN).  counts[8] = samples,
+ * exact-shadow samples, then (decided, decided-but-wrong) for the compare shortcut, the sign-bit shortcut (FAST8) and
+ * its packed flavour.  "wrong" must be 0: a decided pixel never differs from the reference sequence.  Synchronous. */
+int  pb200_shadow_sweep(pb200_ctx *ctx, const pb200_params *params, double sun_azimuth, double sun_elevation,
+                        const double *sun_terms /* 5 doubles or NULL */, int mode, uint64_t seed, uint64_t n_samples,
+                        uint64_t counts[8]);
 /* Derived angle thresholds the library would use for these params (libm). */
 int  pb200_angle_thresholds(const pb200_params *params, double *cos_inc,
                             double *tan_slope);

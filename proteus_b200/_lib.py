@@ -17,11 +17,12 @@ ADJ_MODES = {'mask': 0, 'ignore': 1, 'cover': 2}
 N_COUNTERS = 12
 E_INVALID_ARG, E_BAD_MODE, E_UNSUPPORTED, E_NO_DRIVER_API, E_ALIGNMENT, E_NCCL = -1, -2, -3, -4, -5, -6
 COMM_ID_BYTES = 128
+KERNEL_FAST, KERNEL_STREAM, KERNEL_FAST8, KERNEL_GENERIC = 1, 2, 4, 8
 
 EXPORTS = (
     'pb200_version', 'pb200_last_error', 'pb200_ctx_create', 'pb200_ctx_destroy',
     'pb200_params_default', 'pb200_classify', 'pb200_plan_create',
-    'pb200_plan_run', 'pb200_plan_destroy', 'pb200_classify_host', 'pb200_classify_host_ex',
+    'pb200_plan_run', 'pb200_plan_kernels', 'pb200_plan_destroy', 'pb200_classify_host', 'pb200_classify_host_ex',
     'pb200_host_alloc', 'pb200_host_free', 'pb200_invalid_and_clip',
     'pb200_diagnostic_tests', 'pb200_diagnostic_tests_f32', 'pb200_interpreted_layer',
     'pb200_binary_representation', 'pb200_preliminary_cloud',
@@ -30,7 +31,7 @@ EXPORTS = (
     'pb200_confidence', 'pb200_collapse', 'pb200_shadow', 'pb200_landcover_aggregate',
     'pb200_browse_table', 'pb200_byte_table', 'pb200_scale_offset',
     'pb200_histogram_u8', 'pb200_otsu_threshold', 'pb200_greater_than_u8', 'pb200_ratio_bound',
-    'pb200_ratio_sweep', 'pb200_angle_thresholds',
+    'pb200_ratio_sweep', 'pb200_shadow_sweep', 'pb200_angle_thresholds',
     'pb200_comm_unique_id', 'pb200_comm_init', 'pb200_halo_exchange_dem', 'pb200_comm_allreduce_u64',
     'pb200_comm_destroy',
 )
@@ -116,6 +117,8 @@ def load():
         raise ImportError('libproteus_b200.so ABI version mismatch')
     lib.pb200_ratio_bound.argtypes = [C.c_double, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.pb200_ratio_sweep.argtypes = [C.c_void_p, C.c_double, C.c_int, C.POINTER(C.c_uint64)]
+    lib.pb200_shadow_sweep.argtypes = [C.c_void_p, C.POINTER(Params), C.c_double, C.c_double, C.POINTER(C.c_double), C.c_int,
+                                       C.c_uint64, C.c_uint64, C.c_uint64 * 8]
     lib.pb200_angle_thresholds.argtypes = [C.POINTER(Params), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.pb200_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
     lib.pb200_ctx_destroy.argtypes = [C.c_void_p]
@@ -123,6 +126,7 @@ def load():
     lib.pb200_classify.argtypes = [C.c_void_p, C.POINTER(Tile), C.c_int, C.POINTER(Params), C.c_void_p]
     lib.pb200_plan_create.argtypes = [C.c_void_p, C.POINTER(Tile), C.c_int, C.POINTER(Params), C.POINTER(C.c_void_p)]
     lib.pb200_plan_run.argtypes = [C.c_void_p, C.c_void_p]
+    lib.pb200_plan_kernels.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
     lib.pb200_plan_destroy.argtypes = [C.c_void_p]
     lib.pb200_classify_host.argtypes = [C.c_void_p, C.POINTER(Tile), C.POINTER(Params), C.c_int]
     lib.pb200_classify_host_ex.argtypes = [C.c_void_p, C.POINTER(Tile), C.POINTER(Params), C.c_int, C.c_int]

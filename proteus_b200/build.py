@@ -22,6 +22,9 @@ LIB = os.path.join(HERE, 'libproteus_b200.so')
 SOURCES = [os.path.join(CSRC, 'pb200_api.cu')]
 HEADERS = [os.path.join(CSRC, 'pb200_kernels.cuh'),
            os.path.join(CSRC, 'pb200_fused.cuh'),
+           os.path.join(CSRC, 'pb200_fused_row.inc'),
+           os.path.join(CSRC, 'pb200_stream.cuh'),
+           os.path.join(CSRC, 'pb200_sweep.cuh'),
            os.path.join(CSRC, 'pb200_cover.cuh'),
            os.path.join(CSRC, 'pb200_landcover.cuh'),
            os.path.join(CSRC, 'pb200_device.cuh'),

@@ -23,9 +23,11 @@
 #include "../../include/proteus_b200.h"
 #include "pb200_kernels.cuh"
 #include "pb200_fused.cuh"
+#include "pb200_stream.cuh"
 #include "pb200_cover.cuh"
 #include "pb200_landcover.cuh"
 #include "pb200_comm.cuh"
+#include "pb200_sweep.cuh"
 
 using namespace pb200;
 
@@ -536,6 +538,9 @@ struct pb200_plan {
     bool fast_optional = false;                      // some fast tile wants WTR-1 / WTR-2 / CLOUD / SHAD
     bool fast_all_graded = true;                     // every fast tile writes DIAG, WTR, BWTR and CONF
     bool no_fast8 = false;                           // PB200_NO_FAST8=1: run the general variant (A/B, tests)
+    int n_fast_seen = 0;
+    bool stream = false;                             // every fast tile meets the preconditions of dswx_fused_stream_kernel
+    int maps_per_tile = 1;                           // tensor maps per fast tile: 1 (DEM) or ST_MAPS
     bool stream_ordered = false;                     // allocated with cudaMallocAsync
     bool from_arena = false;                         // allocated from a caller-owned arena: nothing to free
     // per input tile: where it went (for launching one tile of the plan on its own)
@@ -711,6 +716,11 @@ static int plan_build(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles, cons
     std::vector<TileDev> td[N_GROUPS];
     std::vector<CUtensorMap> tm[N_GROUPS];
     std::vector<ItemDesc> items;
+    bool stream_ok = true;
+    {
+        const char *e = std::getenv("PB200_NO_STREAM");
+        if (e && *e && *e != '0') stream_ok = false;
+    }
     for (int i = 0; i < n_tiles; ++i) {
         TileDev d;
         alignas(64) CUtensorMap m;
@@ -730,6 +740,10 @@ static int plan_build(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles, cons
         pl->tile_ctas.push_back(d.n_ctas);
         pl->item_start.push_back((int)items.size());
         if (fast) {
+            // TMA-fed variant (pb200_stream.cuh): 4-row super-rows need height % 4 == 0 and 16-byte aligned planes
+            bool st = (d.height % 4) == 0 && d.width >= 36 && aligned(d.fmask, 16) && aligned(d.land, 16) && aligned(d.ocean, 16);
+            for (int k = 0; k < 6; ++k) st = st && aligned(d.band[k], 16);
+            if (!st) stream_ok = false;
             // the fast kernel stages the DEM with its own box shape
             if (d.dem) {
                 const cuuint64_t gdim[2] = {(cuuint64_t)d.dem_pitch, (cuuint64_t)d.dem_rows};
@@ -741,6 +755,7 @@ static int plan_build(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles, cons
                                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
                 if (r != CUDA_SUCCESS) return fail(PB200_E_INVALID_ARG, "tile %d: cuTensorMapEncodeTiled failed (%d)", i, (int)r);
             }
+            pl->n_fast_seen++;
             const int ntx = (d.width + FT_W - 1) / FT_W, nty = (d.height + FT_H - 1) / FT_H;
             const uint32_t slot = (uint32_t)td[G_FAST].size();
             for (int ty = 0; ty < nty; ++ty)
@@ -755,6 +770,38 @@ static int plan_build(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles, cons
         td[g].push_back(d);
         tm[g].push_back(m);
         pl->max_ctas[g] = std::max(pl->max_ctas[g], d.n_ctas);
+    }
+    // TMA-fed variant: lean product configuration only (all four graded layers + counters on every fast tile)
+    pl->stream = stream_ok && pl->n_fast_seen > 0 && !pl->fast_optional && pl->fast_all_graded;
+    if (pl->stream) {
+        // ten tensor maps per fast tile: DEM, six bands, Fmask, LAND, ocean (4-row super-rows, see pb200_stream.cuh)
+        std::vector<CUtensorMap> all(td[G_FAST].size() * ST_MAPS);
+        std::memset(all.data(), 0, all.size() * sizeof(CUtensorMap));
+        for (size_t i = 0; i < td[G_FAST].size(); ++i) {
+            const TileDev &d = td[G_FAST][i];
+            CUtensorMap *m = &all[i * ST_MAPS];
+            m[SM_DEM] = tm[G_FAST][i];
+            const cuuint64_t gdim[2] = {(cuuint64_t)4 * d.width, (cuuint64_t)d.height / 4};
+            const cuuint32_t estr[2] = {1, 1};
+            auto enc = [&](CUtensorMap *dst, CUtensorMapDataType dt, const void *base, size_t esz, int box_w) -> bool {
+                if (!base) return true;
+                const cuuint64_t gstr[1] = {(cuuint64_t)4 * d.width * esz};
+                const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)ST_WARPS};
+                return ctx->encode(dst, dt, 2, const_cast<void *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            };
+            bool ok = true;
+            for (int k = 0; k < 6; ++k) ok = ok && enc(&m[SM_BAND0 + k], CU_TENSOR_MAP_DATA_TYPE_UINT16, d.band[k], 2, ST_BAND_W);
+            ok = ok && enc(&m[SM_FMASK], CU_TENSOR_MAP_DATA_TYPE_UINT8, d.fmask, 1, ST_BYTE_W);
+            ok = ok && enc(&m[SM_LAND], CU_TENSOR_MAP_DATA_TYPE_UINT8, d.land, 1, ST_BYTE_W);
+            ok = ok && enc(&m[SM_OCEAN], CU_TENSOR_MAP_DATA_TYPE_UINT8, d.ocean, 1, ST_BYTE_W);
+            if (!ok) { pl->stream = false; break; }
+        }
+        if (pl->stream) {
+            tm[G_FAST].swap(all);
+            pl->maps_per_tile = ST_MAPS;
+        }
     }
     CK(cudaSetDevice(ctx->device));
     pl->from_arena = arena != nullptr;
@@ -811,6 +858,8 @@ static int fast_kernel_setup(pb200_ctx *ctx) {
         CK(cudaFuncSetAttribute(dswx_fused_fast_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)FAST_DYN_SMEM));
     }
+    CK(cudaFuncSetAttribute(dswx_fused_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamSmem)));
+    CK(cudaFuncSetAttribute(dswx_fused_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamSmem)));
     int nb = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dswx_fused_fast_kernel<false>, FtGeom<false>::THREADS, FAST_DYN_SMEM));
     ctx->fast_ctas_per_sm = nb > 0 ? nb : 1;
@@ -825,6 +874,16 @@ static void launch_fast(pb200_plan *pl, const ItemDesc *it, int n, cudaStream_t 
     const pb200_ctx *ctx = pl->ctx;
     const int grid = std::min(n, ctx->sm_count * (pl->fast_optional ? ctx->fast_ctas_per_sm_full : ctx->fast_ctas_per_sm));
     const bool f8 = pl->F.fast8 != 0u && !pl->no_fast8;
+    if (pl->stream) {
+        const int g1 = std::min(n, ctx->sm_count);            // 219 KB of shared memory: one CTA per SM
+        if (f8)
+            dswx_fused_stream_kernel<true><<<g1, ST_THREADS, sizeof(StreamSmem), stream>>>(
+                pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, it, n, pl->P, pl->F);
+        else
+            dswx_fused_stream_kernel<false><<<g1, ST_THREADS, sizeof(StreamSmem), stream>>>(
+                pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, it, n, pl->P, pl->F);
+        return;
+    }
 #define PB200_LAUNCH_FAST(OPT, GRADED, F8)                                                                         \
     dswx_fused_fast_kernel<OPT, GRADED, F8><<<grid, FtGeom<OPT>::THREADS, FAST_DYN_SMEM, stream>>>(                 \
         pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, it, n, pl->P, pl->F)
@@ -919,6 +978,17 @@ extern "C" int pb200_plan_create(pb200_ctx *ctx, const pb200_tile *tiles, int n_
         return rc;
     }
     *out = pl;
+    return 0;
+}
+// which kernels a plan launches: bit 0 = dswx_fused_fast_kernel, bit 1 = dswx_fused_stream_kernel (TMA-fed), bit 2 =
+// FAST8 flavour of either, bit 3 = dswx_fused_kernel (generic path) for some tile
+extern "C" int pb200_plan_kernels(const pb200_plan *plan, int *mask) {
+    if (!plan || !mask) return fail(PB200_E_INVALID_ARG, "pb200_plan_kernels: null argument");
+    int m = 0;
+    if (plan->n[G_FAST]) m |= plan->stream ? 2 : 1;
+    if (plan->n[G_FAST] && plan->F.fast8 != 0u && !plan->no_fast8) m |= 4;
+    if (plan->n[G_VEC] || plan->n[G_GENERIC]) m |= 8;
+    *mask = m;
     return 0;
 }
 extern "C" int pb200_plan_run(pb200_plan *plan, void *stream) {
@@ -1135,7 +1205,7 @@ extern "C" int pb200_classify_host_ex(pb200_ctx *ctx, const pb200_tile *ht, cons
     // worst case per strip: descriptor + tensor map + one item per FT_W x FT_H pixels
     {
         const size_t items_max = (size_t)((W + FT_W - 1) / FT_W) * (size_t)((H + FT_H - 1) / FT_H + n_strips);
-        const size_t need = (size_t)n_strips * (sizeof(TileDev) + sizeof(CUtensorMap) + 1024) +
+        const size_t need = (size_t)n_strips * (sizeof(TileDev) + ST_MAPS * sizeof(CUtensorMap) + 1024) +
                             items_max * sizeof(ItemDesc) + 8192;
         if (need > p.arena.cap) {
             CKP(cudaStreamSynchronize(p.s_k));
@@ -1631,6 +1701,41 @@ extern "C" int pb200_landcover_aggregate(pb200_ctx *ctx, const uint8_t *worldcov
     if (vec) landcover_aggregate_kernel<true><<<grid, block, 0, st>>>(worldcover, copernicus, land, rows, cols, L);
     else landcover_aggregate_kernel<false><<<grid, block, 0, st>>>(worldcover, copernicus, land, rows, cols, L);
     LEAVE();
+}
+
+extern "C" int pb200_shadow_sweep(pb200_ctx *ctx, const pb200_params *params, double sun_azimuth, double sun_elevation,
+                                  const double *terms, int mode, uint64_t seed, uint64_t n_samples, uint64_t counts[8]) {
+    REQUIRE(ctx && params && counts, "pb200_shadow_sweep: null argument");
+    REQUIRE(mode >= 0 && mode <= 3, "pb200_shadow_sweep: mode 0..3");
+    CK(cudaSetDevice(ctx->device));
+    DevParams P;
+    pb200_params p = *params;
+    if (p.adjacent_mode == PB200_ADJ_COVER) p.adjacent_mode = PB200_ADJ_MASK;
+    int rc = derive_params(&p, &P, true);
+    if (rc) return rc;
+    FastParams F;
+    build_fast_params(&p, P, &F);
+    pb200_tile t;
+    std::memset(&t, 0, sizeof(t));
+    t.sun_azimuth = sun_azimuth;
+    t.sun_elevation = sun_elevation;
+    t.sun_terms[0] = std::numeric_limits<double>::quiet_NaN();
+    if (terms)
+        for (int i = 0; i < 5; ++i) t.sun_terms[i] = terms[i];
+    TileDev d;
+    std::memset(&d, 0, sizeof(d));
+    sun_terms(t, &d);
+    SweepCounts *dc = nullptr;
+    CK(cudaMalloc((void **)&dc, sizeof(SweepCounts)));
+    CK(cudaMemset(dc, 0, sizeof(SweepCounts)));
+    const int blocks = ctx->sm_count * 8, threads = 256;
+    const unsigned long long per_thread = (n_samples + (uint64_t)blocks * threads - 1) / ((uint64_t)blocks * threads);
+    shadow_sweep_kernel<<<blocks, threads>>>(P, F, d, mode, seed, per_thread, dc);
+    static_assert(sizeof(SweepCounts) == 8 * sizeof(uint64_t), "counts[8]");
+    cudaError_t e = cudaMemcpy(counts, dc, sizeof(SweepCounts), cudaMemcpyDeviceToHost);
+    cudaFree(dc);
+    if (e != cudaSuccess) return fail_cuda(e, "pb200_shadow_sweep");
+    return 0;
 }
 
 extern "C" int pb200_ratio_sweep(pb200_ctx *ctx, double t, int is_less, uint64_t *mismatches) {

@@ -485,319 +485,27 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
             for (int rr = 0; rr < nrows; ++rr, pix += (uint32_t)W) {
                 const int ly = rgrp * FT_ROWS_PER_WARP + rr;
 
-                uint32_t idx[4], dgw[2], k1p[2], water_any = 0u;
-#pragma unroll
-                for (int p = 0; p < 2; ++p) {
-                    // ================= packed stage: pixels 2p, 2p+1 =================
-                    const uint32_t selb = p ? 0x4342u : 0x4140u;              // bytes -> 16-bit halves
-                    const uint32_t fmh = __byte_perm(fm4, 0u, selb);          // Fmask values as halves
-                    uint32_t xm;
-                    if constexpr (FAST8) {
-                        // every band has a fill value: (raw - fill) mod 2^16 == 0 <=> raw == fill, min-reduced in one
-                        // VIADDMNMX.U16x2 per band                                                    D:2204-2207
-                        xm = __byte_perm(fm4 ^ F.fmask_xor4, 0u, selb) | F.fmask_or;
-#pragma unroll
-                        for (int k = 5; k >= 0; --k) xm = __viaddmin_u16x2(w[k][p], F.nfill[k], xm);   // half == 0 <=> invalid
-                    } else {
-                        uint32_t xf[6];
-#pragma unroll
-                        for (int k = 0; k < 6; ++k) xf[k] = (w[k][p] ^ F.fill_xor[k]) | F.fill_or[k];   // D:2204-2207 (one LOP3)
-                        const uint32_t xfm = __byte_perm(fm4 ^ F.fmask_xor4, 0u, selb) | F.fmask_or;
-                        xm = __vimin3_u16x2(__vimin3_u16x2(xf[0], xf[1], xf[2]), xf[3], xf[4]);
-                        xm = __vimin3_u16x2(xm, xf[5], xfm);                  // half == 0 <=> pixel invalid
-                    }
-                    const uint32_t nz = __vminu2(xm, 0x00010001u);            // 1 = valid
-                    const uint32_t ob = __vminu2(__byte_perm(oc4, 0u, selb), 0x00010001u);   // D:5245: 0 is masked
-                    const uint32_t comb = ob * 2u + nz;
-                    const uint32_t B = __vmaxs2(w[0][p], 0x00010001u), G = __vmaxs2(w[1][p], 0x00010001u);   // D:2299
-                    const uint32_t R = __vmaxs2(w[2][p], 0x00010001u), N = __vmaxs2(w[3][p], 0x00010001u);
-                    const uint32_t S1 = __vmaxs2(w[4][p], 0x00010001u), S2 = __vmaxs2(w[5][p], 0x00010001u);
-                    const uint32_t gs = __vadd2(G, S1);                                                      // D:1872
-                    const uint32_t gr = __vadd2(G, R), ns = __vadd2(N, S1);                                  // D:1875-1878
-                    const uint32_t nrs = __vadd2(N, R);                                                      // D:1884
-                    // numerators: FAST8 needs S1 - G only (NDVI runs on the (N, R) pack)
-                    const uint32_t gd = FAST8 ? __vsub2(S1, G) : __vsub2(G, S1);
-                    const uint32_t nrd = FAST8 ? 0u : __vsub2(N, R);
-                    const bool slow = ((gs | gr | ns | nrs) & 0x80008000u) != 0u;      // some int16 sum wrapped
-                    const uint32_t T4 = __viaddmax_s16x2(N, F.m_p1nir, __vadd2(S1, F.m_p1swir1));           // < 0 <=> all below
-                    const uint32_t T5 = __viaddmax_s16x2(N, F.m_p2nir, __viaddmax_s16x2(S2, F.m_p2swir2,
-                                        __viaddmax_s16x2(S1, F.m_p2swir1, __vadd2(B, F.m_p2blue))));
-                    const uint32_t tn = __vadd2(N, F.m_nle);                  // sign <=> nir <= 1000      (D:1239)
-                    const uint32_t tb = __vadd2(N, F.m_lc);                   // sign <=> !(nir > lcmask)  (D:1354)
-                    // fmask value | (nir <= 1000) << 11, and bright << 10, per half
-                    const uint32_t fa = fmh | ((tn >> 4) & 0x08000800u);
-#if PB200_FT_SWIZZLE_BRIGHT
-                    const uint32_t brp = ((~tb >> 15) & 0x00010001u) * BIG_BRIGHT;   // per half: index bit 10 and bank bit 4
-#else
-                    const uint32_t brp = (~tb >> 5) & 0x04000400u;
-#endif
-
-                    uint32_t dcode[2];
-#if PB200_FT_PATCH_SLOW
-                    // the packed evaluation runs unconditionally (straight-line code the scheduler can interleave
-                    // with the look-ups of the previous pair); a pair with a wrapped sum is re-evaluated afterwards
-                    {
-#else
-                    if (!slow) {
-#endif
-                        bool p2h, p2l;
-                        (void)__vibmax_s16x2(ns, gr, &p2h, &p2l);             // pred = mbsrn >= mbsrv: test 2 is its negation
-#pragma unroll
-                        for (int hh = 0; hh < 2; ++hh) {
-                            const bool hi = hh;
-                            int x0w, x1w, x2w, x3w, aw = F.awesh_init;
-                            if constexpr (FAST8) {
-                                // per-pixel packs (lo, hi) = (gs, S1 - G) and (N, R); sign set <=> test true
-                                const uint32_t pgd = __byte_perm(gs, gd, hi ? 0x7632 : 0x5410);
-                                const uint32_t pnr = __byte_perm(N, R, hi ? 0x7632 : 0x5410);
-                                x0w = dp2a_lo_s16_u8(pgd, F.c_wigt, 0);
-                                x1w = __dp2a_lo((int)pgd, (int)F.c_p1, 0);
-                                x2w = __dp2a_lo((int)pgd, (int)F.c_p2, 0);
-                                x3w = __dp2a_lo((int)pnr, (int)F.c_ndvi, 0);
-                                // 4*awesh: init - 4B - 10G + 6 N + 6 S1 + S2 < 0 <=> awesh > awgt
-                                aw = __dp2a_lo((int)pgd, (int)F.c_aw_gd, aw);
-                                aw = __dp2a_lo((int)pnr, (int)F.c_aw_nr, aw);
-                                if (hi) {
-                                    aw = __dp2a_hi((int)B, (int)F.c_aw_b, aw);
-                                    aw = __dp2a_hi((int)S2, (int)F.c_aw_s2, aw);
-                                } else {
-                                    aw = __dp2a_lo((int)B, (int)F.c_aw_b, aw);
-                                    aw = __dp2a_lo((int)S2, (int)F.c_aw_s2, aw);
-                                }
-                            } else {
-                            const int n1 = hi ? sext_hi(gd) : sext_lo(gd);
-                            const int q1 = hi ? (int)(gs >> 16) : (int)(gs & 0xffffu);
-                            const int n2 = hi ? sext_hi(nrd) : sext_lo(nrd);
-                            const int q2 = hi ? (int)(nrs >> 16) : (int)(nrs & 0xffffu);
-                            // sign set <=> test true:  sa*q + p*(-sb) < 0 <=> p/q > sa/sb  (two IMADs)
-                            x0w = n1 * F.nsb[RB_WIGT] + F.sa[RB_WIGT] * q1;
-                            x1w = n1 * F.nsb[RB_P1_MNDWI] + F.sa[RB_P1_MNDWI] * q1;
-                            x2w = n1 * F.nsb[RB_P2_MNDWI] + F.sa[RB_P2_MNDWI] * q1;
-                            x3w = n2 * F.nsb[RB_P1_NDVI] + F.sa[RB_P1_NDVI] * q2;       // p/q < sa/sb
-                            // 4*awesh: init - 4B - 10G + 6*mbsrn + S2 < 0 <=> awesh > awgt
-                            if (hi) {
-                                aw = __dp2a_hi((int)B, (int)0xFC0000FCu, aw);
-                                aw = __dp2a_hi((int)G, (int)0xF60000F6u, aw);
-                                aw = __dp2a_hi((int)ns, (int)0x06000006u, aw);
-                                aw = __dp2a_hi((int)S2, (int)0x01000001u, aw);
-                            } else {
-                                aw = __dp2a_lo((int)B, (int)0xFC0000FCu, aw);
-                                aw = __dp2a_lo((int)G, (int)0xF60000F6u, aw);
-                                aw = __dp2a_lo((int)ns, (int)0x06000006u, aw);
-                                aw = __dp2a_lo((int)S2, (int)0x01000001u, aw);
-                            }
-                            }
-                            const uint32_t sh16 = hi ? 0u : 16u;
-                            const uint32_t t2w = (hi ? p2h : p2l) ? 0u : 0x80000000u;
-                            const uint32_t t4w = (uint32_t)x1w & (uint32_t)x3w & (T4 << sh16);
-                            const uint32_t t5w = (uint32_t)x2w & (T5 << sh16);
-                            const uint32_t cpx = hi ? (comb >> 16) : (comb & 3u);   // valid | not_ocean << 1
-                            uint32_t d = __funnelshift_l(t5w, cpx, 1);
-                            d = __funnelshift_l(t4w, d, 1);
-                            d = __funnelshift_l((uint32_t)aw, d, 1);
-                            d = __funnelshift_l(t2w, d, 1);
-                            d = __funnelshift_l((uint32_t)x0w, d, 1);
-                            dcode[hh] = d;
-                        }
-                    }
-#if PB200_FT_PATCH_SLOW
-                    if (slow) {
-#else
-                    else {
-#endif
-#if PB200_FT_PATCH_SLOW
-                        // only the pixel whose sums wrapped (usually one of the two)
-                        const uint32_t wr = (gs | gr | ns | nrs) & 0x80008000u;
-                        if (wr & 0x8000u) dcode[0] = diag_pixel_slow(B, G, R, N, S1, S2, 0u, P) | ((comb & 3u) << 5);
-                        if (wr >> 31) dcode[1] = diag_pixel_slow(B, G, R, N, S1, S2, 1u, P) | ((comb >> 16) << 5);
-#else
-                        dcode[0] = diag_pixel_slow(B, G, R, N, S1, S2, 0u, P) | ((comb & 3u) << 5);
-                        dcode[1] = diag_pixel_slow(B, G, R, N, S1, S2, 1u, P) | ((comb >> 16) << 5);
-#endif
-                    }
-
-                    // ================= per pixel: tables ================================
-                    uint32_t dl[2];
-#pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        const bool hi = hh;
-                        const int j = 2 * p + hh;
-                        dl[hh] = lds_tab32(sb + FS_OFF(diag_lut) + 4u * dcode[hh]);   // D:5227-5231, 5245, 5249
-                        const uint32_t k1s = dl[hh] >> 16;                    // k1 << 8 | k1 << 2 (bank swizzle)
-                        const uint32_t fi = hi ? ((fa >> 16) ^ k1s) : ((fa & 0xffffu) ^ k1s);
-                        const uint32_t ev = lds_tab8(sb + FS_OFF(fk_lut) + fi);       // D:1237-1246, 1984-1991, 2081
-#if PB200_FT_LAND_DP4A
-                        // byte j of ld4 + table base in one IDP.4A (the FMA-side pipe; shift + mask + add are 2 ALU-pipe ops)
-                        const uint32_t cat = lds_tab8(__dp4a(ld4, 1u << (8 * j), sb + FS_OFF(land_lut)));
-#else
-                        const uint32_t cat = lds_tab8(sb + FS_OFF(land_lut) + ((ld4 >> (8 * j)) & 255u));
-#endif
-                        const uint32_t bri = hi ? (brp >> 16) : (brp & 0xffffu);
-                        idx[j] = ((ev & 0x7Fu) ^ bri) + (cat << 7);          // bits 7-8 are still clear: the sum is an OR
-                        water_any |= ev;                                      // bit 7: the pixel holds a water class
-                    }
-                    dgw[p] = __byte_perm(dl[0], dl[1], 0x5410);               // two DIAG values
-                    if (OPTIONAL_LAYERS) k1p[p] = __byte_perm(dl[0], dl[1], 0x4743);   // k1 of the two pixels in bytes 0 and 2
-                }
-
-                if (has_counters) acc_nno = __dp4a(oc4, 0x01010101u, acc_nno);   // D:5105; no shoreline: 1 per pixel (D:5107)
-#if PB200_FT_LATE_REQUEST
-                // DEM tile of the next item: requested after this thread's second row, when the other warps have
-                // normally left item k - 1 (requested at the top of the item, thread 0 spent half its time waiting
-                // for the slowest of them, profiles/)
-                if (tid == 0 && has_dem && rr == min(1, nrows - 1) && next.tile == cur_tile) request_dem(k + 1u, next, padx);
-#endif
-                if (rr + 1 < nrows) {
-                    FT_LOAD_ROW(pix + (uint32_t)W);
-                } else if (PB200_FT_XITEM_PREFETCH && next.tile == cur_tile) {
-                    // last row: first row of this warp in the next item of the CTA (same tile, same planes)
-                    const int xn = next.tx * FT_W + 4 * lane, yn = next.ty * FT_H + rgrp * FT_ROWS_PER_WARP;
-                    if (xn < W && yn < H) {
-                        FT_LOAD_ROW((uint32_t)yn * (uint32_t)W + (uint32_t)xn);
-                        row_loaded = true;
-                    }
-                }
-
-                // ---- terrain shadow: only where it can change the result ----------------
-                // (bit 7 of a fk_lut byte = the pixel holds a water class: only those can be masked, D:1340-1343)
-                uint32_t shw[4] = {0u, 0u, 0u, 0u};                           // BIG_SHADOWED = in shadow
-                if (has_dem && ((FAST8 && PB200_FT_SHADOW_ALWAYS) || want_shad || (water_any & 0x80u))) {
-                    if (!dem_ready) {
-                        mbar_wait(&s.full[buf], (fstate >> buf) & 1u);
-                        dem_ready = true;
-                    }
-                    // shared address of this lane's first pixel in the middle row of the 3-row window
-                    const uint32_t am = sb + FS_OFF(dem) + buf * (uint32_t)sizeof(DemHalf) +
-                                        4u * (uint32_t)((ly + 1) * FT_SMW + 4 * lane + padx);
-                    constexpr uint32_t RB = 4u * FT_SMW;                      // bytes per row of the DEM tile
-                    float m[6], u[4], d[4];
-                    if ((padx & 1) == 0) {
-                        // even DEM margins (production: 50): 8-byte vectors
-                        m[0] = lds_f32(am - 4);
-                        const float2 m1 = lds_f32x2(am), m2 = lds_f32x2(am + 8);
-                        m[1] = m1.x; m[2] = m1.y; m[3] = m2.x; m[4] = m2.y;
-                        const float2 u0 = lds_f32x2(am - RB), d0 = lds_f32x2(am + RB);
-                        u[0] = u0.x; u[1] = u0.y; d[0] = d0.x; d[1] = d0.y;
-                        m[5] = lds_f32(am + 16);
-                        const float2 u1 = lds_f32x2(am - RB + 8), d1 = lds_f32x2(am + RB + 8);
-                        u[2] = u1.x; u[3] = u1.y; d[2] = d1.x; d[3] = d1.y;
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 6; ++j) m[j] = lds_f32(am + 4 * j - 4);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) { u[j] = lds_f32(am - RB + 4 * j); d[j] = lds_f32(am + RB + 4 * j); }
-                    }
-                    float K[SK_N];
-                    {
-                        const float4 k0 = lds_f32x4(sb + FS_OFF(sun32)), k1 = lds_f32x4(sb + FS_OFF(sun32) + 16);
-                        K[0] = k0.x; K[1] = k0.y; K[2] = k0.z; K[3] = k0.w; K[4] = k1.x; K[5] = k1.y; K[6] = k1.z; K[7] = k1.w;
-                        static_assert(SK_N == 8, "two 16-byte loads");
-                    }
-                    bool undecided;
-                    if constexpr (FAST8) {
-                        uint32_t is[4], nt[4];
-                        float2 v01, v23;
-#if PB200_FT_SHADOW_SCALAR
-                        shadow_fast1(m[0], m[2], u[0], d[0], F, K, &is[0], &nt[0], &v01.x);
-                        shadow_fast1(m[1], m[3], u[1], d[1], F, K, &is[1], &nt[1], &v01.y);
-                        shadow_fast1(m[2], m[4], u[2], d[2], F, K, &is[2], &nt[2], &v23.x);
-                        shadow_fast1(m[3], m[5], u[3], d[3], F, K, &is[3], &nt[3], &v23.y);
-                        const uint32_t vsb = __float_as_uint((v01.x + v01.y) + (v23.x + v23.y)) + 0x00800000u;
-#else
-                        {
-                            uint32_t i2[2], n2[2];
-                            shadow_fast2(make_float2(m[0], m[1]), make_float2(m[2], m[3]), make_float2(u[0], u[1]),
-                                         make_float2(d[0], d[1]), F, K, i2, n2, &v01);
-                            is[0] = i2[0]; is[1] = i2[1]; nt[0] = n2[0]; nt[1] = n2[1];
-                            shadow_fast2(make_float2(m[2], m[3]), make_float2(m[4], m[5]), make_float2(u[2], u[3]),
-                                         make_float2(d[2], d[3]), F, K, i2, n2, &v23);
-                            is[2] = i2[0]; is[3] = i2[1]; nt[2] = n2[0]; nt[3] = n2[1];
-                        }
-                        // bit 31 of `und`: some pixel neither certainly shadowed nor certainly lit, or a non-finite v
-                        // (v >= 1; exponent 0xff + 1 carries into bit 31; NaNs from float32 arithmetic are 0x7fffffff)
-                        const float2 vs2 = __fadd2_rn(v01, v23);
-                        const uint32_t vsb = __float_as_uint(vs2.x + vs2.y) + 0x00800000u;
-#endif
-                        uint32_t und = vsb;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            und |= ~(is[j] | nt[j]);
-                            shw[j] = (uint32_t)((int)is[j] >> 31) & BIG_SHADOWED;
-                        }
-                        undecided = (und >> 31) != 0u;
-                    } else {
-                        undecided = (F.fast_shadow_ok == 0u);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) shw[j] = shadow_fast(m[j], m[j + 2], u[j], d[j], F, K, &undecided);
-                    }
-                    if (undecided) {
-                        // rare: redo the 4 pixels with the float64 reference sequence
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) shw[j] = shadow_exact(m[j], m[j + 2], u[j], d[j], P, s.tile);
-                    }
-                }
-                // ---- final look-up (D:1331-1376, 2084-2131, 1727, 1793-1835) ------------------
-                uint32_t o[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) o[j] = lds_tab32(sb + FS_OFF(big_lut) + 4u * (idx[j] ^ shw[j]));
-
-                // ---- pack and store -------------------------------------------------------
-                const uint32_t t01a = __byte_perm(o[0], o[1], 0x5140);
-                const uint32_t t23a = __byte_perm(o[2], o[3], 0x5140);
-                const uint32_t t01b = __byte_perm(o[0], o[1], 0x7362);
-                const uint32_t t23b = __byte_perm(o[2], o[3], 0x7362);
-                const uint32_t wtr4 = __byte_perm(t01a, t23a, 0x5410);
-                const uint32_t bwtr4 = __byte_perm(t01a, t23a, 0x7632);
-                const uint32_t conf4 = __byte_perm(t01b, t23b, 0x5410);
-                const uint32_t flag4 = __byte_perm(t01b, t23b, 0x7632);
-                if (all_graded) {
-                    stg_stream_v2(plane_at(lds_ptr<uint16_t>(sb + FS_TILE(diag)), pix), dgw[0], dgw[1]);
-                    stg_stream_u32(plane_at(lds_ptr<uint8_t>(sb + FS_TILE(wtr)), pix), wtr4);
-                    stg_stream_u32(plane_at(lds_ptr<uint8_t>(sb + FS_TILE(bwtr)), pix), bwtr4);
-                    stg_stream_u32(plane_at(lds_ptr<uint8_t>(sb + FS_TILE(conf)), pix), conf4);
-                } else {
-                    if (s.tile.diag) stg_stream_v2(s.tile.diag + pix, dgw[0], dgw[1]);
-                    if (s.tile.wtr) stg_stream_u32(s.tile.wtr + pix, wtr4);
-                    if (s.tile.bwtr) stg_stream_u32(s.tile.bwtr + pix, bwtr4);
-                    if (s.tile.conf) stg_stream_u32(s.tile.conf + pix, conf4);
-                }
-
-                if (OPTIONAL_LAYERS) {
-                    const uint32_t cls_lo = P.cls_lut[0] | (P.cls_lut[1] << 8) | (P.cls_lut[2] << 16) | (P.cls_lut[3] << 24);
-                    const uint32_t cls_hi = P.cls_lut[4] | (P.cls_lut[5] << 8) | (P.cls_lut[6] << 16) | (P.cls_lut[7] << 24);
-                    uint32_t sel1r = 0, sel2 = 0, c4 = 0, s4 = 0;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        // undo the bank swizzle of "bright" (index bit 10 also flipped bit 4 = bit 1 of c)
-                        const uint32_t kb = idx[j] & 7u,
-                                       c = ((idx[j] >> 3) & 15u) ^ (PB200_FT_SWIZZLE_BRIGHT ? ((idx[j] >> 9) & 2u) : 0u);
-                        const uint32_t shb = shw[j] >> 9;
-                        // kill_lut index: kb | shadowed<<3 | bright<<4 | cat<<5  (bright = idx bit 10, cat = idx bits 7-8)
-                        const uint32_t k2 = s.kill_lut[kb | (shb << 3) | ((idx[j] >> 6) & 0x10u) | ((idx[j] >> 2) & 0x60u)];
-                        sel1r |= kb << (4 * j);
-                        sel2 |= k2 << (4 * j);
-                        c4 |= ((k2 == 7u && !(P.flags & PF_DEFER_SNOW)) ? 255u : c) << (8 * j);    // D:2084 ('cover': after the dilations)
-                        s4 |= (shb ^ 1u) << (8 * j);
-                    }
-                    // k1p[p]: byte 0 = k1 of pixel 2p, byte 2 = k1 of pixel 2p+1
-                    const uint32_t sel1 = (k1p[0] & 7u) | ((k1p[0] >> 12) & 0x70u) | ((k1p[1] & 7u) << 8) |
-                                          ((k1p[1] >> 4) & 0x7000u);
-                    if (s.tile.cloud) stg_stream_u32(s.tile.cloud + pix, c4);
-                    if (s.tile.wtr1) stg_stream_u32(s.tile.wtr1 + pix, __byte_perm(cls_lo, cls_hi, sel1));
-                    if (s.tile.wtr1r) stg_stream_u32(s.tile.wtr1r + pix, __byte_perm(cls_lo, cls_hi, sel1r));
-                    if (s.tile.wtr2) stg_stream_u32(s.tile.wtr2 + pix, __byte_perm(cls_lo, cls_hi, sel2));
-                    if (s.tile.shad) stg_stream_u32(s.tile.shad + pix, s4);
-                }
-
-                // ---- counters (D:5104-5111) from the flag bytes -----------------------------
-                if (has_counters) {
-                    // valid in the low half, cloud-and-valid in the high half (a thread sees < 2^16 pixels per tile)
-                    acc_vc += __popc(flag4 & 0x01010101u) + (__popc(flag4 & 0x02020202u) << 16);
-                    if (histogram) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) acc_hist += 1ull << (7u * ((flag4 >> (8 * j + 4)) & 15u));
-                    }
-                }
+                // hooks of the shared row body (pb200_fused_row.inc).  Mid-row, when the row's input registers are dead:
+                // request the DEM tile of the next item (after this thread's second row, when the other warps have
+                // normally left item k - 1: requested at the top of the item, thread 0 spent half its time waiting for the
+                // slowest of them), then issue the loads of the next row - of the warp's first row in the next item of
+                // the CTA (same tile, same planes) when this is the last one
+#define FT_DEM_WAIT() mbar_wait(&s.full[buf], (fstate >> buf) & 1u)
+#define FT_ROW_MIDPOINT() do { \
+                    if (PB200_FT_LATE_REQUEST && tid == 0 && has_dem && rr == min(1, nrows - 1) && next.tile == cur_tile) request_dem(k + 1u, next, padx); \
+                if (rr + 1 < nrows) { \
+                    FT_LOAD_ROW(pix + (uint32_t)W); \
+                } else if (PB200_FT_XITEM_PREFETCH && next.tile == cur_tile) { \
+                    const int xn = next.tx * FT_W + 4 * lane, yn = next.ty * FT_H + rgrp * FT_ROWS_PER_WARP; \
+                    if (xn < W && yn < H) { \
+                        FT_LOAD_ROW((uint32_t)yn * (uint32_t)W + (uint32_t)xn); \
+                        row_loaded = true; \
+                    } \
+                } \
+                } while (0)
+#include "pb200_fused_row.inc"
+#undef FT_ROW_MIDPOINT
+#undef FT_DEM_WAIT
             }
 #undef FT_LOAD_ROW
         }

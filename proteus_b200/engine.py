@@ -285,6 +285,25 @@ class Plan:
             stream = torch.cuda.current_stream(self.ctx.device)
         _lib.check(self.ctx._lib.pb200_plan_run(self.handle, C.c_void_p(stream.cuda_stream)))
 
+    @property
+    def kernels(self):
+        """Bit mask of the kernels this plan launches (``_lib.KERNEL_*``)."""
+        m = C.c_int()
+        _lib.check(self.ctx._lib.pb200_plan_kernels(self.handle, C.byref(m)))
+        return m.value
+
+    @property
+    def kernel_name(self):
+        m = self.kernels
+        names = []
+        if m & _lib.KERNEL_STREAM:
+            names.append(f'pb200::dswx_fused_stream_kernel<{"true" if m & _lib.KERNEL_FAST8 else "false"}>')
+        if m & _lib.KERNEL_FAST:
+            names.append('pb200::dswx_fused_fast_kernel' + ('<FAST8>' if m & _lib.KERNEL_FAST8 else ''))
+        if m & _lib.KERNEL_GENERIC:
+            names.append('pb200::dswx_fused_kernel')
+        return ' + '.join(names)
+
     def zero_counters(self):
         if self.counters is not None:
             self.counters.zero_()

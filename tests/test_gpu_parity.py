@@ -152,6 +152,34 @@ def test_ratio_test_exhaustive_int16_pairs(pb, t, is_less):
     assert bad.value == 0
 
 
+@pytest.mark.parametrize('az,el', [(150.0, 45.0), (10.0, 5.0), (359.0, 89.0), (200.0, 15.0), (135.0, 30.0)])
+def test_shadow_shortcuts_never_decide_wrongly(pb, az, el):
+    """the float32 shadow shortcuts proved the way the ratio test was - by brute force on the GPU.  For
+    each sun geometry: 2^32 random DEM neighbourhoods + 2^30 / 2^28 planted on the decision boundaries (slope: diff = +-e;
+    incidence: D = +-eg) + special values, through shadow_fast (compares), shadow_fast1 / shadow_fast2 (sign bits,
+    FAST8) and the exact float64 sequence (D:4264-4281).  A decided sample must never differ."""
+    import ctypes as C
+    from proteus_b200 import _lib
+    from proteus_b200.params import sun_terms
+    ctx = pb.get_context()
+    params = pb.make_params()
+    terms = (C.c_double * 5)(*sun_terms(az, el))
+    report = {}
+    for mode, n in ((0, 2 ** 32), (1, 2 ** 30), (2, 2 ** 28), (3, 2 ** 24)):
+        counts = (C.c_uint64 * 8)()
+        _lib.check(ctx._lib.pb200_shadow_sweep(ctx.handle, C.byref(params), az, el, terms, mode, 1234 + mode, n, counts))
+        n_s, shadow, dec_c, bad_c, dec_s, bad_s, dec_s2, bad_s2 = [int(v) for v in counts]
+        assert n_s >= n
+        assert bad_c == 0 and bad_s == 0 and bad_s2 == 0, (mode, bad_c, bad_s, bad_s2)
+        report[mode] = (shadow / n_s, 1 - dec_c / n_s, 1 - dec_s / n_s, 1 - dec_s2 / n_s)
+    # the generators do what they say: random gradients are almost always decided, planted ones often fall in the band
+    assert report[0][1] < 1e-3 and report[0][2] < 1e-3
+    assert 0.02 < report[0][0] < 0.98                      # both outcomes occur
+    assert report[1][2] > 0.01 and report[2][2] > 0.01     # > 1 % of the planted samples are inside a guard band
+    assert report[3][2] > 0.3                              # special values mostly go to the exact sequence
+    print(f'sun ({az}, {el}): mode -> (shadow share, undecided share compare / sign / sign2)', report)
+
+
 def test_device_division_matches_numpy_division():
     """The sweep above trusts __ddiv_rn == numpy true_divide; spot-check that
     link on the host side of the same inputs through the function-level kernel."""
@@ -516,6 +544,63 @@ def test_batch_of_mixed_tiles_through_the_item_pipeline(pb):
                 assert np.array_equal(res['counters'][:3], ref['counters']), (i, launch)
 
 
+def test_tma_fed_stream_kernel_matches_oracle(pb):
+    """The product configuration (four graded layers + counters) on tiles whose planes TMA can address as 4-row
+    super-rows runs dswx_fused_stream_kernel (producer warp + shared-memory ring): tiles smaller than an item, ragged
+    right / bottom edges, with and without DEM / LAND / ocean, adversarial data, several tiles per launch (a CTA changes
+    tile between items), two launches of the same plan - against the oracle; and the same batch through the
+    direct-load kernel (PB200_NO_STREAM) gives the same bits."""
+    import os
+    import torch
+    from proteus_b200 import _lib
+    specs = [(51, 96, 128, {}), (52, 100, 132, dict(with_ocean=False)), (53, 4, 36, dict(adversarial=True)),
+             (54, 700, 128, dict(adversarial=True)), (55, 256, 384, dict(with_dem=False)),
+             (56, 192, 260, dict(with_land=False, with_ocean=False)), (57, 388, 1028, {}), (58, 96, 3660, {}),
+             (59, 8, 40, dict(with_dem=False, with_land=False, with_ocean=False))]
+    tiles, refs = [], []
+    for seed, h, w, kw in specs:
+        t = synth.make_tile(seed, h, w, **kw)
+        refs.append(O.reference_chain(t['bands'], t['fmask'], t['dem'], t['land'], t['ocean'],
+                                      t['sun_azimuth'], t['sun_elevation']))
+        dev = {k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) else v) for k, v in t.items() if k != 'bands'}
+        dev['bands'] = [torch.from_numpy(b).cuda() for b in t['bands']]
+        tiles.append(dev)
+    for params, what in ((pb.make_params(collapse_wtr_classes=False), 'defaults (FAST8)'),
+                         (pb.make_params(pb.HlsThresholds(wigt=0.13, pswt_1_ndvi=0.71), collapse_wtr_classes=False,
+                                         min_slope_angle=3), 'general parameters')):
+        kw = {} if what.startswith('defaults') else dict(thresholds=O.HlsThresholds(wigt=0.13, pswt_1_ndvi=0.71),
+                                                          processing=dict(min_slope_angle=3))
+        if kw:
+            refs_p = []
+            for seed, h, w, tkw in specs:
+                t = synth.make_tile(seed, h, w, **tkw)
+                refs_p.append(O.reference_chain(t['bands'], t['fmask'], t['dem'], t['land'], t['ocean'],
+                                                t['sun_azimuth'], t['sun_elevation'], **kw))
+        else:
+            refs_p = refs
+        plan = pb.Plan(tiles, params, pb.GRADED_LAYERS)
+        assert plan.kernels & _lib.KERNEL_STREAM, 'the batch should qualify for the TMA-fed kernel'
+        assert bool(plan.kernels & _lib.KERNEL_FAST8) == what.startswith('defaults')
+        for launch in range(2):
+            plan.zero_counters()
+            plan.run()
+            for i, ref in enumerate(refs_p):
+                res = plan.results(i)
+                _assert_layers(res, ref, ('DIAG', 'WTR', 'BWTR', 'CONF'), f'{what}: tile {i} launch {launch}')
+                assert np.array_equal(res['counters'][:3], ref['counters']), (what, i, launch)
+        os.environ['PB200_NO_STREAM'] = '1'
+        try:
+            direct = pb.Plan(tiles, params, pb.GRADED_LAYERS)
+        finally:
+            del os.environ['PB200_NO_STREAM']
+        assert not (direct.kernels & _lib.KERNEL_STREAM)
+        direct.run()
+        for i in range(len(tiles)):
+            a, b = plan.results(i), direct.results(i)
+            for name in ('DIAG', 'WTR', 'BWTR', 'CONF'):
+                assert np.array_equal(a[name], b[name]), (what, i, name)
+
+
 def test_otsu_threshold_dropin(pb):
     """SURVEY 8f next #3: _compute_otsu_threshold on uint8 hillshades (GPU histogram + compare, host threshold)."""
     import proteus_b200.dswx_hls as G
@@ -677,3 +762,107 @@ def test_host_path_reuses_resident_ancillary_rasters(pb):
     third = pb.classify_tile(b['bands'], b['fmask'], poisoned['dem'], poisoned['land'], poisoned['ocean'],
                              b['sun_azimuth'], b['sun_elevation'], collapse_wtr_classes=False, reuse_ancillary=True)
     _assert_layers(third, ref_b, FUSED_LAYERS, 'after a refused call')
+
+
+def _stand_in_reference_module():
+    """A module object shaped like proteus.dswx_hls as far as generate_dswx_layers' per-pixel statements go: the
+    constants they use, the one helper that is not replaced, and - for every function install() must rebind - a stub
+    that fails when called."""
+    import types
+    import proteus_b200.dswx_hls as G
+    mod = types.ModuleType('proteus_dswx_hls_stand_in')
+    for name in ('DIAGNOSTIC_LAYER_NO_DATA_DECIMAL', 'WTR_OCEAN_MASKED', 'UINT8_FILL_VALUE'):
+        setattr(mod, name, getattr(G, name))
+    mod._crop_2d_array_all_sides = lambda a, margin: a[margin:-margin, margin:-margin]      # D:4320-4337, not replaced
+
+    def make_stub(name):
+        def stub(*args, **kwargs):
+            raise AssertionError(f'{name}: the CPU function was called - install() did not rebind it')
+        stub.__name__ = name
+        return stub
+    for name in G.REPLACED_FUNCTIONS:
+        setattr(mod, name, make_stub(name))
+    return mod
+
+
+@pytest.mark.parametrize('case', ('full_default', 'ignore_noaerosol', 'cover_mode', 'ragged_adversarial'))
+def test_install_rebinds_the_reference_call_order_onto_the_gpu(pb, case):
+    """INTEGRATION level 2 executed.  install(module) rebinds the 14 per-pixel functions; the statement
+    order of generate_dswx_layers (D:5088-5369, oracle/make_golden.py:reference_chain - the very code that produced
+    the fixtures from the live reference) then runs on the GPU entry points and must reproduce every fixture layer;
+    uninstall() restores the module."""
+    import json
+    import os
+    from conftest import GOLDEN_DIR
+    from oracle import make_golden
+    import proteus_b200.dswx_hls as G
+    mod = _stand_in_reference_module()
+    before = {name: getattr(mod, name) for name in G.REPLACED_FUNCTIONS}
+    assert pb.install(mod) is mod
+    for name in G.REPLACED_FUNCTIONS:
+        assert getattr(mod, name) is getattr(G, name), name
+    with open(os.path.join(GOLDEN_DIR, 'reference_tables.json')) as f:
+        tables = json.load(f)
+    ins, ref = load_golden(case)
+    t = dict(bands=ins['bands'], fmask=ins['fmask'], dem=ins['dem'], land=ins['land'], ocean=ins['ocean'],
+             sun_azimuth=ins['sun_azimuth'], sun_elevation=ins['sun_elevation'], dem_margin=ins['dem_margin'])
+    got = make_golden.reference_chain(mod, t, tables['processing'], pb.HlsThresholds(**tables['hls_thresholds']),
+                                      ins['mode'], ins['aerosol'])
+    for name, r in ref.items():
+        assert name in got, name
+        g = np.asarray(got[name])
+        assert np.array_equal(g.astype(r.dtype) if g.dtype != r.dtype and g.dtype == np.bool_ else g, r), (case, name)
+    pb.uninstall(mod)
+    for name in G.REPLACED_FUNCTIONS:
+        assert getattr(mod, name) is before[name], name
+
+
+def test_one_shot_classify_and_invalid_and_clip_exports(pb):
+    """The two exports nothing else calls: pb200_classify (plan build + launch + release in one asynchronous call on
+    the caller's stream) and pb200_invalid_and_clip (D:2203-2209, D:2298-2299)."""
+    import ctypes as C
+    import torch
+    from proteus_b200 import _lib, engine
+    ctx = pb.get_context()
+    t = synth.make_tile(61, 200, 264)
+    ref = O.reference_chain(t['bands'], t['fmask'], t['dem'], t['land'], t['ocean'], t['sun_azimuth'], t['sun_elevation'])
+    dev = {k: torch.from_numpy(t[k]).cuda() for k in ('fmask', 'dem', 'land', 'ocean')}
+    bands = [torch.from_numpy(b).cuda() for b in t['bands']]
+    outs = {n: torch.empty((200, 264), device='cuda', dtype=torch.int16 if n == 'DIAG' else torch.uint8) for n in FUSED_LAYERS}
+    counters = torch.zeros(12, dtype=torch.int64, device='cuda')
+    tile = _lib.Tile()
+    engine._fill_tile(tile, height=200, width=264, band_ptrs=[b.data_ptr() for b in bands], fmask_ptr=dev['fmask'].data_ptr(),
+                      dem_ptr=dev['dem'].data_ptr(), dem_shape=dev['dem'].shape, dem_off=(50, 50),
+                      land_ptr=dev['land'].data_ptr(), ocean_ptr=dev['ocean'].data_ptr(),
+                      sun=(t['sun_azimuth'], t['sun_elevation']), out_ptrs={k: v.data_ptr() for k, v in outs.items()},
+                      counters_ptr=counters.data_ptr())
+    params = pb.make_params(collapse_wtr_classes=False)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    for _ in range(3):                                   # back-to-back one-shot calls on a non-default stream
+        counters.zero_()
+        side.wait_stream(torch.cuda.current_stream())
+        _lib.check(ctx._lib.pb200_classify(ctx.handle, C.byref(tile), 1, C.byref(params), C.c_void_p(side.cuda_stream)))
+        side.synchronize()
+    for n in FUSED_LAYERS:
+        a = outs[n].cpu().numpy()
+        assert np.array_equal(a.view(np.uint16) if n == 'DIAG' else a, ref[n]), n
+    assert np.array_equal(counters.cpu().numpy()[:3].astype(np.uint64), ref['counters'])
+    # invalid mask + clip, custom fills, with and without the optional outputs
+    n = 200 * 264
+    raw = (C.c_void_p * 6)(*[b.data_ptr() for b in bands])
+    clipped = [torch.empty_like(b) for b in bands]
+    cl = (C.c_void_p * 6)(*[b.data_ptr() for b in clipped])
+    invalid = torch.empty((200, 264), dtype=torch.uint8, device='cuda')
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(ctx._lib.pb200_invalid_and_clip(ctx.handle, raw, dev['fmask'].data_ptr(), C.byref(params), n, cl,
+                                               invalid.data_ptr(), stream))
+    inv_ref, clip_ref = O.invalid_mask_and_clip(t['bands'], t['fmask'])
+    assert np.array_equal(invalid.cpu().numpy().astype(bool), inv_ref)
+    for got, want in zip(clipped, clip_ref):
+        assert np.array_equal(got.cpu().numpy(), want)
+    _lib.check(ctx._lib.pb200_invalid_and_clip(ctx.handle, raw, None, C.byref(params), n, (C.c_void_p * 6)(), invalid.data_ptr(), stream))
+    inv_nofmask = np.zeros_like(inv_ref)
+    for b in t['bands']:
+        inv_nofmask |= b == -9999
+    assert np.array_equal(invalid.cpu().numpy().astype(bool), inv_nofmask)

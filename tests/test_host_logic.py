@@ -225,3 +225,31 @@ def test_product_package_does_not_import_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', text, flags=re.M), f
                 assert 'dswx_oracle' not in text, f
+
+
+def test_install_swaps_exactly_the_replaced_functions_on_the_live_reference():
+    """INTEGRATION level 2 in the build container: install() on the LIVE reference module rebinds exactly the names
+    of REPLACED_FUNCTIONS, every one with the reference's own signature, and uninstall() puts the originals back."""
+    import inspect
+    from oracle import ref_import
+    if not ref_import.available():
+        pytest.skip('needs /root/reference (build container)')
+    import proteus_b200
+    import proteus_b200.dswx_hls as G
+    ref = ref_import.load()
+    originals = {n: getattr(ref, n) for n in G.REPLACED_FUNCTIONS}
+    other = {n: v for n, v in vars(ref).items() if callable(v) and n not in G.REPLACED_FUNCTIONS}
+    for n, fn in originals.items():
+        assert inspect.signature(fn) == inspect.signature(getattr(G, n)), n
+    try:
+        assert proteus_b200.install(ref) is ref
+        for n in G.REPLACED_FUNCTIONS:
+            assert getattr(ref, n) is getattr(G, n), n
+        for n, v in other.items():
+            assert getattr(ref, n) is v, f'{n} must not be touched'
+        # generate_dswx_layers resolves its helpers as module globals at call time (D:5089, 5161, 5225-5368)
+        assert ref.generate_dswx_layers.__globals__['_compute_diagnostic_tests'] is G._compute_diagnostic_tests
+    finally:
+        proteus_b200.uninstall(ref)
+    for n, fn in originals.items():
+        assert getattr(ref, n) is fn, n
