@@ -730,7 +730,7 @@ static int plan_build(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles, cons
         const pb200_tile &t = tiles[i];
         bool fast = (d.flags & TF_VEC) && (d.dem == nullptr || (d.flags & TF_TMA)) &&
                     (uint64_t)d.height * (uint64_t)d.width < 0xfff00000ull && d.width <= 65000 * FT_W &&
-                    d.height <= 65000 * FT_H;
+                    d.height <= 65000 * std::min(FT_H, ST_H);
         (void)t;
         // the first DEM box of a row of items must not start left of the DEM array
         if (d.dem) fast = fast && d.dem_off_x >= DEM_PADX + (d.dem_off_x & 3);
@@ -738,41 +738,50 @@ static int plan_build(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles, cons
         pl->tile_group.push_back(g);
         pl->tile_slot.push_back((int)td[g].size());
         pl->tile_ctas.push_back(d.n_ctas);
-        pl->item_start.push_back((int)items.size());
         if (fast) {
             // TMA-fed variant (pb200_stream.cuh): 4-row super-rows need height % 4 == 0 and 16-byte aligned planes
             bool st = (d.height % 4) == 0 && d.width >= 36 && aligned(d.fmask, 16) && aligned(d.land, 16) && aligned(d.ocean, 16);
             for (int k = 0; k < 6; ++k) st = st && aligned(d.band[k], 16);
             if (!st) stream_ok = false;
-            // the fast kernel stages the DEM with its own box shape
-            if (d.dem) {
-                const cuuint64_t gdim[2] = {(cuuint64_t)d.dem_pitch, (cuuint64_t)d.dem_rows};
-                const cuuint64_t gstr[1] = {(cuuint64_t)d.dem_pitch * sizeof(float)};
-                const cuuint32_t box[2] = {(cuuint32_t)FT_SMW, (cuuint32_t)FT_SMH};
-                const cuuint32_t estr[2] = {1, 1};
-                const CUresult r = ctx->encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)d.dem, gdim, gstr, box,
-                                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-                if (r != CUDA_SUCCESS) return fail(PB200_E_INVALID_ARG, "tile %d: cuTensorMapEncodeTiled failed (%d)", i, (int)r);
-            }
             pl->n_fast_seen++;
-            const int ntx = (d.width + FT_W - 1) / FT_W, nty = (d.height + FT_H - 1) / FT_H;
-            const uint32_t slot = (uint32_t)td[G_FAST].size();
-            for (int ty = 0; ty < nty; ++ty)
-                for (int tx = 0; tx < ntx; ++tx) items.push_back(ItemDesc{slot, (uint16_t)tx, (uint16_t)ty});
             // the lean kernel variant writes any subset of the four graded layers and assumes the counters;
             // anything else -> full variant
             if (d.wtr1 || d.wtr1r || d.wtr2 || d.cloud || d.shad || params->class_histogram || !d.counters)
                 pl->fast_optional = true;
             if (!d.diag || !d.wtr || !d.bwtr || !d.conf) pl->fast_all_graded = false;
         }
-        pl->item_end.push_back((int)items.size());
         td[g].push_back(d);
         tm[g].push_back(m);
         pl->max_ctas[g] = std::max(pl->max_ctas[g], d.n_ctas);
     }
     // TMA-fed variant: lean product configuration only (all four graded layers + counters on every fast tile)
     pl->stream = stream_ok && pl->n_fast_seen > 0 && !pl->fast_optional && pl->fast_all_graded;
+    // items and DEM boxes of the fast tiles, in the geometry of the kernel that will run them
+    {
+        const int item_h = pl->stream ? ST_H : FT_H;
+        for (int i = 0; i < n_tiles; ++i) {
+            pl->item_start.push_back((int)items.size());
+            if (pl->tile_group[i] == G_FAST) {
+                const uint32_t slot = (uint32_t)pl->tile_slot[i];
+                const TileDev &d = td[G_FAST][slot];
+                if (d.dem) {
+                    // the fast kernels stage the DEM with their own box shape: item width + pad, item height + 2 halo rows
+                    const cuuint64_t gdim[2] = {(cuuint64_t)d.dem_pitch, (cuuint64_t)d.dem_rows};
+                    const cuuint64_t gstr[1] = {(cuuint64_t)d.dem_pitch * sizeof(float)};
+                    const cuuint32_t box[2] = {(cuuint32_t)FT_SMW, (cuuint32_t)(item_h + 2)};
+                    const cuuint32_t estr[2] = {1, 1};
+                    const CUresult r = ctx->encode(&tm[G_FAST][slot], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)d.dem, gdim, gstr,
+                                                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    if (r != CUDA_SUCCESS) return fail(PB200_E_INVALID_ARG, "tile %d: cuTensorMapEncodeTiled failed (%d)", i, (int)r);
+                }
+                const int ntx = (d.width + FT_W - 1) / FT_W, nty = (d.height + item_h - 1) / item_h;
+                for (int ty = 0; ty < nty; ++ty)
+                    for (int tx = 0; tx < ntx; ++tx) items.push_back(ItemDesc{slot, (uint16_t)tx, (uint16_t)ty});
+            }
+            pl->item_end.push_back((int)items.size());
+        }
+    }
     if (pl->stream) {
         // ten tensor maps per fast tile: DEM, six bands, Fmask, LAND, ocean (4-row super-rows, see pb200_stream.cuh)
         std::vector<CUtensorMap> all(td[G_FAST].size() * ST_MAPS);
@@ -1204,7 +1213,7 @@ extern "C" int pb200_classify_host_ex(pb200_ctx *ctx, const pb200_tile *ht, cons
     }
     // worst case per strip: descriptor + tensor map + one item per FT_W x FT_H pixels
     {
-        const size_t items_max = (size_t)((W + FT_W - 1) / FT_W) * (size_t)((H + FT_H - 1) / FT_H + n_strips);
+        const size_t items_max = (size_t)((W + FT_W - 1) / FT_W) * (size_t)((H + std::min(FT_H, ST_H) - 1) / std::min(FT_H, ST_H) + n_strips);
         const size_t need = (size_t)n_strips * (sizeof(TileDev) + ST_MAPS * sizeof(CUtensorMap) + 1024) +
                             items_max * sizeof(ItemDesc) + 8192;
         if (need > p.arena.cap) {

@@ -62,6 +62,18 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
         "r"(parity)
         : "memory");
 }
+// the box load alone; the caller has acquired the tensor map (tma_acquire_map) since it was written
+__device__ __forceinline__ void tma_load_2d_acquired(void *dst, const CUtensorMap *map, int c0, int c1,
+                                                     unsigned long long *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+            "r"(smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_acquire_map(const CUtensorMap *map) {
+    asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(map) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1,
                                             unsigned long long *bar) {
     // The tensor maps live in GLOBAL memory (one per tile of the batch, written

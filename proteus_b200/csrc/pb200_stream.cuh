@@ -10,7 +10,7 @@
 //    of an HLS raster, 3660 elements, is not a multiple of 16 bytes, four rows are: 4 W * 2 B and 4 W * 1 B with
 //    W % 4 == 0).  The raster rows r = c (mod 4) of an item are then the CONSECUTIVE super-rows of one 2-D box that
 //    starts at column c W + x0 - a box of 24 rows is "row c of every warp" (a warp owns 4 consecutive rows of the
-//    128 x 96 item);
+//    128 x 92 item);
 //  * a chunk = that box for each of the 9 input planes: 6 x (136 int16 x 24) + 3 x (144 B x 24) = 48.4 KB, 9 TMA
 //    instructions for 3072 pixels.  Boxes start on 16-byte boundaries (measured requirement on B200): the column is
 //    rounded down, a lane adds the remainder (0 / 4 int16 elements, 0 / 4 / 8 / 12 bytes) to its shared-memory address;
@@ -29,10 +29,17 @@
 
 namespace pb200 {
 
-constexpr int ST_WARPS = PB200_FT_WARPS_LEAN;                 // consumer warps; one more warp produces
+// 23 consumer warps + the producer = 24 warps = 6 per SM sub-partition: 80 registers each (a 25th warp would put 7 on
+// one sub-partition and cap every thread at 72 registers: measured 165 instead of 215 Gpixel/s, profiles/)
+#ifndef PB200_ST_WARPS
+#define PB200_ST_WARPS 23
+#endif
+constexpr int ST_WARPS = PB200_ST_WARPS;                      // consumer warps; one more warp produces
 constexpr int ST_THREADS = 32 * (ST_WARPS + 1);
-constexpr int ST_ROWS_PER_WARP = FT_H / ST_WARPS;
-static_assert(ST_ROWS_PER_WARP == 4, "a chunk is one row class modulo 4 of the item");
+constexpr int ST_ROWS_PER_WARP = 4;                           // a chunk is one row class modulo 4 of the item
+constexpr int ST_H = ST_ROWS_PER_WARP * ST_WARPS;             // item height of this kernel (92 rows)
+static_assert(ST_H + 2 <= FT_SMH, "the DEM tile of an item fits the double buffer of FastSmem");
+constexpr uint32_t ST_DEM_BOX_BYTES = (ST_H + 2) * FT_SMW * sizeof(float);
 constexpr int ST_BAND_W = FT_W + 8;                           // int16 elements per staged band row (272 B)
 constexpr int ST_BYTE_W = FT_W + 16;                          // bytes per staged byte-raster row
 constexpr int ST_MAPS = 10;                                   // tensor maps per tile: DEM, 6 bands, Fmask, LAND, ocean
@@ -86,17 +93,24 @@ dswx_fused_stream_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *_
     // =========================== producer warp ==================================
     if (warp == ST_WARPS) {
         if (lane != 0) return;
-        uint32_t k = 0;
+        uint32_t k = 0, acquired_tile = 0xffffffffu;
 #pragma unroll 1
         for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k) {
             const ItemDesc d = items[it];
             const TileDev &g = tiles[d.tile];
             const CUtensorMap *tm = tmaps + (size_t)d.tile * ST_MAPS;
+            if (d.tile != acquired_tile) {
+                // tensor maps live in global memory: one tensormap-proxy acquire per map when the CTA first meets the tile
+                // (a system-scope fence costs microseconds - per box it made the producer the bottleneck, 75 Gpixel/s)
+#pragma unroll 1
+                for (int j = 0; j < ST_MAPS; ++j) tma_acquire_map(&tm[j]);
+                acquired_tile = d.tile;
+            }
             const int W = __ldg(&g.width);
             const bool has_dem = __ldg(reinterpret_cast<const unsigned long long *>(&g.dem)) != 0ull;
             const bool has_land = __ldg(reinterpret_cast<const unsigned long long *>(&g.land)) != 0ull;
             const bool has_ocean = __ldg(reinterpret_cast<const unsigned long long *>(&g.ocean)) != 0ull;
-            const int x0 = d.tx * FT_W, row4 = d.ty * (FT_H / 4);            // item rows start at super-row ty * 24
+            const int x0 = d.tx * FT_W, row4 = d.ty * (ST_H / 4);            // item rows start at super-row ty * ST_WARPS
             {
                 // DEM tile of the item (or a plain arrival: the phases of full[] / empty[] count items)
                 const uint32_t b = k & 1u;
@@ -105,8 +119,8 @@ dswx_fused_stream_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *_
                     const int dox = __ldg(&g.dem_off_x), doy = __ldg(&g.dem_off_y);
                     const int padx = DEM_PADX + (dox & 3);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    mbar_expect_tx(&s.full[b], DEM_BOX_BYTES);
-                    tma_load_2d(&s.dem[b].v[0][0], &tm[SM_DEM], dox + x0 - padx, doy + d.ty * FT_H - 1, &s.full[b]);
+                    mbar_expect_tx(&s.full[b], ST_DEM_BOX_BYTES);
+                    tma_load_2d_acquired(&s.dem[b].v[0][0], &tm[SM_DEM], dox + x0 - padx, doy + d.ty * ST_H - 1, &s.full[b]);
                 } else {
                     mbar_arrive(&s.full[b]);
                 }
@@ -121,10 +135,10 @@ dswx_fused_stream_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *_
                 const int xe = c * W + x0;                                    // column inside the 4-row super-row
                 InSlot &in = S.in[slot];
 #pragma unroll
-                for (int b = 0; b < 6; ++b) tma_load_2d(&in.band[b][0], &tm[SM_BAND0 + b], xe & ~7, row4, &S.full_in[slot]);
-                tma_load_2d(&in.byte[0][0], &tm[SM_FMASK], xe & ~15, row4, &S.full_in[slot]);
-                if (has_land) tma_load_2d(&in.byte[1][0], &tm[SM_LAND], xe & ~15, row4, &S.full_in[slot]);
-                if (has_ocean) tma_load_2d(&in.byte[2][0], &tm[SM_OCEAN], xe & ~15, row4, &S.full_in[slot]);
+                for (int b = 0; b < 6; ++b) tma_load_2d_acquired(&in.band[b][0], &tm[SM_BAND0 + b], xe & ~7, row4, &S.full_in[slot]);
+                tma_load_2d_acquired(&in.byte[0][0], &tm[SM_FMASK], xe & ~15, row4, &S.full_in[slot]);
+                if (has_land) tma_load_2d_acquired(&in.byte[1][0], &tm[SM_LAND], xe & ~15, row4, &S.full_in[slot]);
+                if (has_ocean) tma_load_2d_acquired(&in.byte[2][0], &tm[SM_OCEAN], xe & ~15, row4, &S.full_in[slot]);
             }
         }
         return;
@@ -187,7 +201,7 @@ dswx_fused_stream_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *_
             consumer_sync();
         }
         const int W = s.tile.width, H = s.tile.height;
-        const int x0 = item.tx * FT_W, y0 = item.ty * FT_H;
+        const int x0 = item.tx * FT_W, y0 = item.ty * ST_H;
         const bool has_dem = s.tile.dem != nullptr;
         const bool has_land = s.tile.land != nullptr;
         const bool has_ocean = s.tile.ocean != nullptr;

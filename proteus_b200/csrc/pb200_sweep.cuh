@@ -61,7 +61,8 @@ __global__ void __launch_bounds__(256) shadow_sweep_kernel(const __grid_constant
         } else {
             const double mag = exp(log(1e-4) + sweep_u01(st) * (log(1e5) - log(1e-4)));
             const double phi = sweep_u01(st) * 6.283185307179586;
-            const double cphi = cos(phi), sphi = sin(phi);
+            double cphi = cos(phi), sphi = sin(phi);
+            if (mode == 2 && cphi * kx * T.sin_az + sphi * ky * T.cos_az > 0.0) { cphi = -cphi; sphi = -sphi; }   // a ray of back slopes
             double a = mag * cphi, b = mag * sphi;
             if (mode == 1) {
                 // on the slope boundary: a kx sin_az + b ky cos_az = tan_thr, solved for the component with the larger weight

@@ -152,32 +152,43 @@ def test_ratio_test_exhaustive_int16_pairs(pb, t, is_less):
     assert bad.value == 0
 
 
-@pytest.mark.parametrize('az,el', [(150.0, 45.0), (10.0, 5.0), (359.0, 89.0), (200.0, 15.0), (135.0, 30.0)])
-def test_shadow_shortcuts_never_decide_wrongly(pb, az, el):
+def test_shadow_shortcuts_never_decide_wrongly(pb):
     """the float32 shadow shortcuts proved the way the ratio test was - by brute force on the GPU.  For
-    each sun geometry: 2^32 random DEM neighbourhoods + 2^30 / 2^28 planted on the decision boundaries (slope: diff = +-e;
-    incidence: D = +-eg) + special values, through shadow_fast (compares), shadow_fast1 / shadow_fast2 (sign bits,
-    FAST8) and the exact float64 sequence (D:4264-4281).  A decided sample must never differ."""
+    five sun geometries: 2^32 random DEM neighbourhoods + 2^30 / 2^28 planted on the decision boundaries (slope:
+    diff = +-e; incidence: D = +-eg, on rays that face away from the sun) + special values, through shadow_fast
+    (compares), shadow_fast1 / shadow_fast2 (sign bits, FAST8) and the exact float64 sequence (D:4264-4281).  A decided
+    sample must never differ from the exact one."""
     import ctypes as C
+    import json
+    import os
     from proteus_b200 import _lib
     from proteus_b200.params import sun_terms
     ctx = pb.get_context()
     params = pb.make_params()
-    terms = (C.c_double * 5)(*sun_terms(az, el))
     report = {}
-    for mode, n in ((0, 2 ** 32), (1, 2 ** 30), (2, 2 ** 28), (3, 2 ** 24)):
-        counts = (C.c_uint64 * 8)()
-        _lib.check(ctx._lib.pb200_shadow_sweep(ctx.handle, C.byref(params), az, el, terms, mode, 1234 + mode, n, counts))
-        n_s, shadow, dec_c, bad_c, dec_s, bad_s, dec_s2, bad_s2 = [int(v) for v in counts]
-        assert n_s >= n
-        assert bad_c == 0 and bad_s == 0 and bad_s2 == 0, (mode, bad_c, bad_s, bad_s2)
-        report[mode] = (shadow / n_s, 1 - dec_c / n_s, 1 - dec_s / n_s, 1 - dec_s2 / n_s)
-    # the generators do what they say: random gradients are almost always decided, planted ones often fall in the band
-    assert report[0][1] < 1e-3 and report[0][2] < 1e-3
-    assert 0.02 < report[0][0] < 0.98                      # both outcomes occur
-    assert report[1][2] > 0.01 and report[2][2] > 0.01     # > 1 % of the planted samples are inside a guard band
-    assert report[3][2] > 0.3                              # special values mostly go to the exact sequence
-    print(f'sun ({az}, {el}): mode -> (shadow share, undecided share compare / sign / sign2)', report)
+    for az, el in ((150.0, 45.0), (10.0, 5.0), (359.0, 89.0), (200.0, 15.0), (135.0, 70.0)):
+        terms = (C.c_double * 5)(*sun_terms(az, el))
+        for mode, n in ((0, 2 ** 32), (1, 2 ** 30), (2, 2 ** 28), (3, 2 ** 24)):
+            counts = (C.c_uint64 * 8)()
+            _lib.check(ctx._lib.pb200_shadow_sweep(ctx.handle, C.byref(params), az, el, terms, mode, 1234 + mode, n, counts))
+            n_s, shadow, dec_c, bad_c, dec_s, bad_s, dec_s2, bad_s2 = [int(v) for v in counts]
+            assert n_s >= n
+            assert bad_c == 0 and bad_s == 0 and bad_s2 == 0, (az, el, mode, bad_c, bad_s, bad_s2)
+            report[f'az {az} el {el} mode {mode}'] = dict(samples=n_s, shadow_share=shadow / n_s, undecided_compare=1 - dec_c / n_s,
+                                                         undecided_sign=1 - dec_s / n_s, undecided_sign_packed=1 - dec_s2 / n_s)
+        r0, r1 = report[f'az {az} el {el} mode 0'], report[f'az {az} el {el} mode 1']
+        # the generators do what they say: random gradients are almost always decided, with both outcomes; the ones
+        # planted on the slope boundary often fall inside the guard band; special values mostly go to the exact sequence
+        assert r0['undecided_compare'] < 1e-3 and r0['undecided_sign'] < 1e-3
+        assert 0.02 < r0['shadow_share'] < 0.98
+        assert r1['undecided_sign'] > 0.01 and r1['undecided_compare'] > 0.01
+        assert report[f'az {az} el {el} mode 3']['undecided_sign'] > 0.3
+    # the incidence boundary can only be met by a back slope when the sun stands high (zenith < 40 degrees)
+    assert report['az 359.0 el 89.0 mode 2']['undecided_sign'] > 0.01
+    assert report['az 135.0 el 70.0 mode 2']['undecided_sign'] > 0.01
+    os.makedirs(os.path.join(os.path.dirname(__file__), '..', 'gpurun_out'), exist_ok=True)
+    with open(os.path.join(os.path.dirname(__file__), '..', 'gpurun_out', 'shadow_sweep_report.json'), 'w') as f:
+        json.dump(report, f, indent=1)
 
 
 def test_device_division_matches_numpy_division():
@@ -568,8 +579,9 @@ def test_tma_fed_stream_kernel_matches_oracle(pb):
     for params, what in ((pb.make_params(collapse_wtr_classes=False), 'defaults (FAST8)'),
                          (pb.make_params(pb.HlsThresholds(wigt=0.13, pswt_1_ndvi=0.71), collapse_wtr_classes=False,
                                          min_slope_angle=3), 'general parameters')):
-        kw = {} if what.startswith('defaults') else dict(thresholds=O.HlsThresholds(wigt=0.13, pswt_1_ndvi=0.71),
-                                                          processing=dict(min_slope_angle=3))
+        oth = O.default_thresholds()
+        oth.wigt, oth.pswt_1_ndvi = 0.13, 0.71
+        kw = {} if what.startswith('defaults') else dict(thresholds=oth, processing=dict(min_slope_angle=3))
         if kw:
             refs_p = []
             for seed, h, w, tkw in specs:
