@@ -34,6 +34,9 @@ namespace pb200 {
 #ifndef PB200_ST_WARPS
 #define PB200_ST_WARPS 23
 #endif
+#ifndef PB200_ST_SLEEP_NS
+#define PB200_ST_SLEEP_NS 200      // producer: nanoseconds between polls of an empty barrier
+#endif
 constexpr int ST_WARPS = PB200_ST_WARPS;                      // consumer warps; one more warp produces
 constexpr int ST_THREADS = 32 * (ST_WARPS + 1);
 constexpr int ST_ROWS_PER_WARP = 4;                           // a chunk is one row class modulo 4 of the item
@@ -114,7 +117,7 @@ dswx_fused_stream_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *_
             {
                 // DEM tile of the item (or a plain arrival: the phases of full[] / empty[] count items)
                 const uint32_t b = k & 1u;
-                if (k >= 2u) mbar_wait(&s.empty[b], ((k >> 1) - 1u) & 1u);
+                if (k >= 2u) mbar_wait_sleep(&s.empty[b], ((k >> 1) - 1u) & 1u, PB200_ST_SLEEP_NS);
                 if (has_dem) {
                     const int dox = __ldg(&g.dem_off_x), doy = __ldg(&g.dem_off_y);
                     const int padx = DEM_PADX + (dox & 3);
@@ -128,7 +131,7 @@ dswx_fused_stream_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *_
 #pragma unroll 1
             for (int c = 0; c < ST_ROWS_PER_WARP; ++c) {
                 const uint32_t q = 4u * k + (uint32_t)c, slot = q & 1u;
-                if (q >= 2u) mbar_wait(&S.empty_in[slot], ((q >> 1) - 1u) & 1u);
+                if (q >= 2u) mbar_wait_sleep(&S.empty_in[slot], ((q >> 1) - 1u) & 1u, PB200_ST_SLEEP_NS);
                 // generic-proxy reads of the slot (ordered by the empty barrier) before the async-proxy writes
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_expect_tx(&S.full_in[slot], 6u * ST_BAND_TX + ST_BYTE_TX * (1u + (has_land ? 1u : 0u) + (has_ocean ? 1u : 0u)));

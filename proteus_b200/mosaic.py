@@ -23,6 +23,9 @@ import numpy as np
 from .params import DEM_MARGIN_IN_PIXELS
 
 
+EDGE_ROWS = 4        # rows at either end of a strip that wait for the halo exchange (overlap mode)
+
+
 def shard_tiles(n_tiles, rank, world):
     """Indices of the tiles rank ``rank`` processes (round robin)."""
     return list(range(int(rank), int(n_tiles), int(world)))
@@ -101,7 +104,7 @@ class MosaicStrip:
     ``exchange``: 'torch' - ``torch.distributed`` P2P batch (NCCL on GPUs, gloo in the CPU tests); 'library' - the C
     ABI's own exchange (``pb200_halo_exchange_dem`` on the communicator of ``init_library_comm``), what a non-Python
     host uses.  ``overlap``: True - exchange on a side stream while the interior rows are classified, the two
-    boundary rows afterwards (two launches); False - exchange first, then ONE launch over the whole strip.
+    boundary bands (4 rows each) afterwards (two launches); False - exchange first, then ONE launch over the whole strip.
 
     Parameters
     ----------
@@ -160,9 +163,12 @@ class MosaicStrip:
 
         self._interior = self._edges = self._whole = None
         if self.overlap:
-            edge_rows = [(0, 1)] + ([(n - 1, n)] if n > 1 else [])
-            if n > 2:
-                t, o = sub((1, n - 1))
+            # the rows whose stencil reaches a halo row are the first and the last one; they are classified as 4-row bands
+            # so that every piece keeps a height that is a multiple of 4 and 16-byte aligned planes (the TMA-fed kernel)
+            e = EDGE_ROWS if n >= 3 * EDGE_ROWS else 1
+            edge_rows = [(0, min(e, n))] + ([(max(e, n - e), n)] if n > e else [])
+            if n > 2 * e:
+                t, o = sub((e, n - e))
                 self._interior = Plan([t], self.params, self.layers, ctx=ctx, outputs_into=[o],
                                       counters_into=self.counters)
             tiles, outs = zip(*[sub(r) for r in edge_rows])
