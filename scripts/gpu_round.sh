@@ -29,7 +29,7 @@ PY
 if [ "$2" != "quick" ]; then
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 400 --csv --log-file gpurun_out/launches_$tag.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras --sustained-s 0 > gpurun_out/launches_$tag.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:dswx_fused_fast -s 3 -c 1 -f -o gpurun_out/prof_$tag \
+ncu --set full --clock-control none --import-source on -k regex:dswx_fused_stream -s 3 -c 1 -f -o gpurun_out/prof_$tag \
     python bench.py --steps 3 --warmup 3 --tiles 4 --no-cpu-baseline --no-e2e --no-extras --sustained-s 0 > gpurun_out/ncu_$tag.log 2>&1
 fi
 ls -la gpurun_out | tail -8
