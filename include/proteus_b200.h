@@ -290,6 +290,14 @@ int  pb200_scale_offset(pb200_ctx *ctx, const int16_t *band, int64_t n, double s
  * accumulated into - zero it first; ranks of a mosaic all-reduce these).  pb200_otsu_threshold (host only): numpy's
  * np.histogram(image, bins=256) binning of those counts and the float64 Otsu arithmetic in numpy's operation order ->
  * the threshold the reference compares with.  pb200_greater_than_u8: out = image > threshold (bool as uint8). */
+/* The hillshade of the 'otsu' algorithm (D:4177-4212: gdal.DEMProcessing(..., "hillshade", azimuth, altitude)) over a
+ * float32 DEM (rows x cols, pitch = cols; ewres / nsres = pixel spacing of the geotransform, nsres < 0 for a north-up
+ * raster), Byte output with 0 on the first / last row and column (gdaldem without -compute_edges), fused with the
+ * 256-bin count of its own output (counts may be NULL; accumulated into, DEVICE memory).  PARITY UNPINNED: GDAL's
+ * arithmetic is not part of the reference tree; this is the published gdaldem Horn formula (z = 1, scale = 1), pinned
+ * to oracle/dswx_oracle.py:compute_hillshade_gdal. */
+int  pb200_hillshade(pb200_ctx *ctx, const float *dem, int rows, int cols, double sun_azimuth, double sun_elevation,
+                     double ewres, double nsres, uint8_t *out, unsigned long long *counts, void *stream);
 int  pb200_histogram_u8(pb200_ctx *ctx, const uint8_t *image, int64_t n, unsigned long long *counts, void *stream);
 int  pb200_otsu_threshold(const unsigned long long counts[256], int is_normalized, double *threshold);
 int  pb200_greater_than_u8(pb200_ctx *ctx, const uint8_t *image, int64_t n, double threshold, uint8_t *out,

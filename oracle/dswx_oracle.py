@@ -461,6 +461,53 @@ def compute_otsu_threshold(image, is_normalized=True):
     return image > otsu_threshold(image, is_normalized)
 
 
+def compute_hillshade_gdal(dem, sun_azimuth_angle, sun_elevation_angle, ewres=30.0, nsres=-30.0):
+    """PARITY UNPINNED restatement of what ``_compute_hillshade`` (D:4177-4212) gets back from
+    ``gdal.DEMProcessing(..., "hillshade", azimuth, altitude)``: GDAL 3.6.2 is not vendored in the reference tree and is
+    absent from this image, so neither its output nor a reference-owned vector can pin these numbers.  This is the
+    published gdaldem algorithm (gdaldem_lib.cpp: GDALCreateHillshadeData + GDALHillshadeAlg, Horn gradient, defaults
+    z = 1, scale = 1, no -compute_edges, Byte output) for a float32 band:
+
+        x = ((w0 + w3 + w3 + w6) - (w2 + w5 + w5 + w8)) / ewres      (window sums in float32, left to right)
+        y = ((w6 + w7 + w7 + w8) - (w0 + w1 + w1 + w2)) / nsres      (w0..w2 = northern row)
+        c = (254 sin(alt) - (y * 254 cos(az) cos(alt) z/8 - x * 254 sin(az) cos(alt) z/8)) / sqrt(1 + (z/8)^2 (x^2 + y^2))
+        shade = 1 if c <= 0 else 1 + c;  Byte = trunc(float32(shade) + 0.5);  border rows / columns = 0 (no data)
+
+    SSE2 builds of GDAL approximate the division with rsqrt + one Newton step: a shade within ~1e-6 of a rounding
+    boundary may differ there by one grey level."""
+    d = np.asarray(dem)
+    if d.dtype != np.float32 or d.ndim != 2:
+        raise TypeError('compute_hillshade_gdal: a 2-D float32 DEM')
+    rows, cols = d.shape
+    out = np.zeros((rows, cols), np.uint8)
+    if rows < 3 or cols < 3:
+        return out
+    w = [[d[i:rows - 2 + i, j:cols - 2 + j] for j in range(3)] for i in range(3)]      # w[row][col], float32 views
+    xs = (((w[0][0] + w[1][0]) + w[1][0]) + w[2][0]) - (((w[0][2] + w[1][2]) + w[1][2]) + w[2][2])
+    ys = (((w[2][0] + w[2][1]) + w[2][1]) + w[2][2]) - (((w[0][0] + w[0][1]) + w[0][1]) + w[0][2])
+    assert xs.dtype == np.float32 and ys.dtype == np.float32
+    deg2rad = 3.14159265358979323846 / 180.0
+    z_scaled = 1.0 / 8.0
+    cos_alt_z = np.cos(sun_elevation_angle * deg2rad) * z_scaled
+    sin_alt_254 = 254.0 * np.sin(sun_elevation_angle * deg2rad)
+    cos_az_254 = 254.0 * (np.cos(sun_azimuth_angle * deg2rad) * cos_alt_z)
+    sin_az_254 = 254.0 * (np.sin(sun_azimuth_angle * deg2rad) * cos_alt_z)
+    x = xs.astype(np.float64) * (1.0 / ewres)
+    y = ys.astype(np.float64) * (1.0 / nsres)
+    with np.errstate(all='ignore'):
+        c254 = (sin_alt_254 - (y * cos_az_254 - x * sin_az_254)) / np.sqrt(1.0 + (z_scaled * z_scaled) * (x * x + y * y))
+        cang = np.where(c254 <= 0.0, 1.0, 1.0 + c254)
+        f = cang.astype(np.float32) + np.float32(0.5)
+        b = np.where(f > 0, np.minimum(f, np.float32(255.0)), np.float32(0.0))      # NaN -> 0
+        out[1:-1, 1:-1] = np.trunc(b).astype(np.uint8)
+    return out
+
+
+def compute_otsu_shadow_layer(dem, sun_azimuth_angle, sun_elevation_angle, ewres=30.0, nsres=-30.0):
+    """The 'otsu' branch of D:5152-5157: hillshade (above, parity unpinned) -> _compute_otsu_threshold(normalized)."""
+    return compute_otsu_threshold(compute_hillshade_gdal(dem, sun_azimuth_angle, sun_elevation_angle, ewres, nsres), True)
+
+
 def reference_chain(raw_bands, fmask, dem_with_margin=None, landcover=None,
                     ocean_mask=None, sun_azimuth_angle=150.0,
                     sun_elevation_angle=45.0, thresholds=None,

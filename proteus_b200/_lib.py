@@ -30,7 +30,7 @@ EXPORTS = (
     'pb200_snow_to_cloud', 'pb200_snow_to_cloud_cover', 'pb200_masked_dilation', 'pb200_cover_tail', 'pb200_cloud_masking', 'pb200_binary_water',
     'pb200_confidence', 'pb200_collapse', 'pb200_shadow', 'pb200_landcover_aggregate',
     'pb200_browse_table', 'pb200_byte_table', 'pb200_scale_offset',
-    'pb200_histogram_u8', 'pb200_otsu_threshold', 'pb200_greater_than_u8', 'pb200_ratio_bound',
+    'pb200_hillshade', 'pb200_histogram_u8', 'pb200_otsu_threshold', 'pb200_greater_than_u8', 'pb200_ratio_bound',
     'pb200_ratio_sweep', 'pb200_shadow_sweep', 'pb200_angle_thresholds',
     'pb200_comm_unique_id', 'pb200_comm_init', 'pb200_halo_exchange_dem', 'pb200_comm_allreduce_u64',
     'pb200_comm_destroy',
@@ -154,6 +154,7 @@ def load():
     lib.pb200_browse_table.argtypes = [C.c_int] * 6 + [C.c_uint8 * 256]
     lib.pb200_byte_table.argtypes = [vp, vp, i64, C.c_uint8 * 256, vp, vp]
     lib.pb200_scale_offset.argtypes = [vp, vp, i64, C.c_double, C.c_double, vp, vp, vp]
+    lib.pb200_hillshade.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, vp, vp, vp]
     lib.pb200_histogram_u8.argtypes = [vp, vp, i64, vp, vp]
     lib.pb200_otsu_threshold.argtypes = [C.c_uint64 * 256, C.c_int, C.POINTER(C.c_double)]
     lib.pb200_greater_than_u8.argtypes = [vp, vp, i64, C.c_double, vp, vp]

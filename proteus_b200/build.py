@@ -25,6 +25,7 @@ HEADERS = [os.path.join(CSRC, 'pb200_kernels.cuh'),
            os.path.join(CSRC, 'pb200_fused_row.inc'),
            os.path.join(CSRC, 'pb200_stream.cuh'),
            os.path.join(CSRC, 'pb200_sweep.cuh'),
+           os.path.join(CSRC, 'pb200_hillshade.cuh'),
            os.path.join(CSRC, 'pb200_cover.cuh'),
            os.path.join(CSRC, 'pb200_landcover.cuh'),
            os.path.join(CSRC, 'pb200_device.cuh'),

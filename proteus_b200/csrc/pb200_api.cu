@@ -27,6 +27,7 @@
 #include "pb200_cover.cuh"
 #include "pb200_landcover.cuh"
 #include "pb200_comm.cuh"
+#include "pb200_hillshade.cuh"
 #include "pb200_sweep.cuh"
 
 using namespace pb200;
@@ -1709,6 +1710,42 @@ extern "C" int pb200_landcover_aggregate(pb200_ctx *ctx, const uint8_t *worldcov
     dim3 block(32, 8), grid(((cols + 3) / 4 + 31) / 32, (rows + 7) / 8);
     if (vec) landcover_aggregate_kernel<true><<<grid, block, 0, st>>>(worldcover, copernicus, land, rows, cols, L);
     else landcover_aggregate_kernel<false><<<grid, block, 0, st>>>(worldcover, copernicus, land, rows, cols, L);
+    LEAVE();
+}
+
+extern "C" int pb200_hillshade(pb200_ctx *ctx, const float *dem, int rows, int cols, double sun_azimuth, double sun_elevation,
+                               double ewres, double nsres, uint8_t *out, unsigned long long *counts, void *stream) {
+    ENTER(ctx);
+    REQUIRE(rows >= 0 && cols >= 0, "pb200_hillshade: bad size");
+    if ((long long)rows * cols == 0) return 0;
+    REQUIRE(dem && out, "pb200_hillshade: null argument");
+    REQUIRE(ewres != 0.0 && nsres != 0.0, "pb200_hillshade: zero pixel spacing");
+    // GDALCreateHillshadeData with gdaldem's defaults: z = 1, scale = 1, Horn (divisor 8)
+    const double deg2rad = 3.14159265358979323846 / 180.0;
+    const double z_scaled = 1.0 / 8.0;
+    HillParams H;
+    H.inv_ewres = 1.0 / ewres;
+    H.inv_nsres = 1.0 / nsres;
+    const double cos_alt_z = std::cos(sun_elevation * deg2rad) * z_scaled;
+    H.sin_alt_254 = 254.0 * std::sin(sun_elevation * deg2rad);
+    H.cos_az_cos_alt_z_254 = 254.0 * (std::cos(sun_azimuth * deg2rad) * cos_alt_z);
+    H.sin_az_cos_alt_z_254 = 254.0 * (std::sin(sun_azimuth * deg2rad) * cos_alt_z);
+    H.square_z = z_scaled * z_scaled;
+    dim3 grid((cols + TW - 1) / TW, (rows + TH - 1) / TH);
+    alignas(64) CUtensorMap map;
+    std::memset(&map, 0, sizeof(map));
+    bool tma = aligned(dem, 16) && (cols % 4) == 0 && cols >= SMW && rows >= SMH;
+    if (tma) {
+        const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+        const cuuint64_t gstr[1] = {(cuuint64_t)cols * sizeof(float)};
+        const cuuint32_t box[2] = {(cuuint32_t)SMW, (cuuint32_t)SMH};
+        const cuuint32_t estr[2] = {1, 1};
+        tma = ctx->encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)dem, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    if (tma) hillshade_hist_kernel<true><<<grid, NTHREADS, 0, st>>>(dem, map, rows, cols, out, counts, H);
+    else hillshade_hist_kernel<false><<<grid, NTHREADS, 0, st>>>(dem, map, rows, cols, out, counts, H);
     LEAVE();
 }
 

@@ -444,6 +444,44 @@ def _compute_otsu_threshold(image, is_normalized=True):
     return _to_host(out, np.uint8).astype(bool)
 
 
+def compute_hillshade(dem, sun_azimuth_angle, sun_elevation_angle, pixel_spacing_x=30.0, pixel_spacing_y=-30.0,
+                      return_counts=False):
+    """What ``_compute_hillshade`` (D:4177-4212) reads back from ``gdal.DEMProcessing(..., "hillshade", azimuth,
+    altitude)``, computed on the GPU from the DEM ARRAY (the reference's function takes the DEM *file*; see
+    INTEGRATION.md): uint8, 0 on the border.  PARITY UNPINNED - GDAL's arithmetic is not part of the reference tree; this
+    is the published gdaldem Horn formula (``oracle/dswx_oracle.py:compute_hillshade_gdal``).  With ``return_counts``
+    also the exact 256-bin histogram of the result (device tensor), counted in the same pass."""
+    torch = _torch()
+    ctx = get_context()
+    d = np.asarray(dem)
+    if d.dtype != np.float32 or d.ndim != 2:
+        raise NotImplementedError(f'compute_hillshade: DEM dtype {d.dtype}; a 2-D float32 array')
+    x = _to_device(d, np.float32, 'dem')
+    out = _empty_like_device(d.shape, np.uint8)
+    counts = torch.zeros(256, dtype=torch.int64, device='cuda') if return_counts else None
+    _lib.check(ctx._lib.pb200_hillshade(
+        ctx.handle, x.data_ptr(), int(d.shape[0]), int(d.shape[1]), float(sun_azimuth_angle), float(sun_elevation_angle),
+        float(pixel_spacing_x), float(pixel_spacing_y), out.data_ptr(),
+        counts.data_ptr() if counts is not None else None, _stream()))
+    if return_counts:
+        return out, counts
+    return _to_host(out, np.uint8)
+
+
+def compute_otsu_shadow_layer(dem, sun_azimuth_angle, sun_elevation_angle, pixel_spacing_x=30.0, pixel_spacing_y=-30.0):
+    """The 'otsu' branch of D:5152-5157 on the device: hillshade + its histogram in one pass over the DEM, the Otsu
+    threshold from the 256 counts on the host, one compare pass.  Bool array, True = not shadow."""
+    ctx = get_context()
+    hill, counts = compute_hillshade(dem, sun_azimuth_angle, sun_elevation_angle, pixel_spacing_x, pixel_spacing_y,
+                                     return_counts=True)
+    if hill.numel() == 0:
+        raise ValueError('attempt to get argmax of an empty sequence')
+    thr = otsu_threshold_from_counts(counts.cpu().numpy(), True)
+    out = _empty_like_device(tuple(hill.shape), np.uint8)
+    _lib.check(ctx._lib.pb200_greater_than_u8(ctx.handle, hill.data_ptr(), int(hill.numel()), thr, out.data_ptr(), _stream()))
+    return _to_host(out, np.uint8).astype(bool)
+
+
 def _crop_2d_array_all_sides(input_2d_array, margin):
     return input_2d_array[margin:-margin, margin:-margin]
 

@@ -200,3 +200,23 @@ def test_otsu_threshold_host_function_equals_the_numpy_restatement():
             t_c = otsu_threshold_from_counts(np.bincount(img.ravel(), minlength=256), norm)
             t_np = O.otsu_threshold(img, norm)
             assert t_c == t_np, (img.min(), img.max(), norm, t_c, t_np)
+
+
+def test_hillshade_restatement_known_answers():
+    """The gdaldem Horn hillshade restatement (PARITY UNPINNED, see its docstring) on cases with a closed form: a flat
+    DEM shades 1 + 254 sin(alt) everywhere but the border; a plane tilted towards the sun is brighter than one tilted
+    away; the border is 0 (no data)."""
+    flat = np.full((8, 9), 500.0, np.float32)
+    h = O.compute_hillshade_gdal(flat, 315.0, 45.0)
+    assert h.dtype == np.uint8 and h.shape == flat.shape
+    assert (h[1:-1, 1:-1] == int(np.float32(1.0 + 254.0 * np.sin(np.radians(45.0))) + np.float32(0.5))).all()
+    assert (h[0] == 0).all() and (h[-1] == 0).all() and (h[:, 0] == 0).all() and (h[:, -1] == 0).all()
+    yy, xx = np.mgrid[0:32, 0:32].astype(np.float32)
+    east_up = (xx * 10.0).astype(np.float32)            # rises towards the east: faces west
+    h_w = O.compute_hillshade_gdal(east_up, 270.0, 30.0)[5, 5]       # sun in the west: lit
+    h_e = O.compute_hillshade_gdal(east_up, 90.0, 30.0)[5, 5]        # sun in the east: darker than flat ground
+    h_flat = int(np.float32(1.0 + 254.0 * 0.5) + np.float32(0.5))          # flat ground under a sun at 30 degrees
+    assert h_w > h_flat > h_e >= 1, (h_w, h_flat, h_e)
+    north_up = ((31 - yy) * 10.0).astype(np.float32)    # rises towards the north (row 0): faces south
+    assert O.compute_hillshade_gdal(north_up, 180.0, 30.0)[5, 5] > h_flat > O.compute_hillshade_gdal(north_up, 0.0, 30.0)[5, 5]
+    assert O.compute_hillshade_gdal(np.zeros((2, 5), np.float32), 150.0, 45.0).sum() == 0
