@@ -449,7 +449,7 @@ def compute_hillshade(dem, sun_azimuth_angle, sun_elevation_angle, pixel_spacing
     """What ``_compute_hillshade`` (D:4177-4212) reads back from ``gdal.DEMProcessing(..., "hillshade", azimuth,
     altitude)``, computed on the GPU from the DEM ARRAY (the reference's function takes the DEM *file*; see
     INTEGRATION.md): uint8, 0 on the border.  PARITY UNPINNED - GDAL's arithmetic is not part of the reference tree; this
-    is the published gdaldem Horn formula (``oracle/dswx_oracle.py:compute_hillshade_gdal``).  With ``return_counts``
+    is the published gdaldem Horn formula (the test oracle's ``compute_hillshade_gdal``).  With ``return_counts``
     also the exact 256-bin histogram of the result (device tensor), counted in the same pass."""
     torch = _torch()
     ctx = get_context()
