@@ -3,7 +3,7 @@
 //
 // PARITY UNPINNED.  The reference obtains the hillshade from GDAL (gdal.DEMProcessing(..., "hillshade", azimuth,
 // altitude), GDAL 3.6.2, un-vendored: its arithmetic is not under /root/reference and GDAL is absent from the build and
-// GPU images).  What is restated here - and in oracle/dswx_oracle.py:compute_hillshade_gdal, which this kernel matches
+// GPU images).  What is restated here - and in the test oracle's compute_hillshade_gdal (oracle/), which this kernel matches
 // bit for bit - is the published gdaldem algorithm with gdaldem's defaults (Horn gradient, z = 1, scale = 1, no
 // -compute_edges, Byte output):
 //     x = ((w0 + w3 + w3 + w6) - (w2 + w5 + w5 + w8)) / ewres        window sums in float32 (the band's type),
