@@ -175,8 +175,18 @@ int  pb200_classify_host(pb200_ctx *ctx, const pb200_tile *host_tile,
  * (PB200_E_INVALID_ARG otherwise); that their CONTENT is unchanged is the caller's statement.  flags = 0 is
  * pb200_classify_host. */
 #define PB200_HOST_REUSE_ANCILLARY 1
+/* Two tiles in flight.  The context holds two independent host pipelines ("slots": device mirror, streams, arena);
+ * PB200_HOST_SLOT1 selects the second.  With PB200_HOST_ASYNC the call returns as soon as the tile's copies and
+ * kernels are enqueued; pb200_host_wait(ctx, slot) returns when its outputs are in host memory (the next call on the
+ * same slot waits implicitly).  A caller that alternates the slots - enqueue tile k + 1, then wait for tile k - keeps
+ * the host-to-device engine busy during the kernel / device-to-host tail of the previous tile.  Every buffer of a
+ * tile must stay untouched until its wait has returned.  PB200_HOST_REUSE_ANCILLARY refers to the rasters resident in
+ * the SAME slot. */
+#define PB200_HOST_ASYNC 2
+#define PB200_HOST_SLOT1 4
 int  pb200_classify_host_ex(pb200_ctx *ctx, const pb200_tile *host_tile,
                             const pb200_params *params, int strip_rows, int flags);
+int  pb200_host_wait(pb200_ctx *ctx, int slot);
 int  pb200_host_alloc(size_t bytes, void **out);
 int  pb200_host_free(void *p);
 

@@ -17,15 +17,15 @@ from .params import (DEFAULT_PROCESSING, DEM_MARGIN_IN_PIXELS, HlsThresholds,
 
 _lib_module.load()              # fail loudly if the CUDA library is missing
 
-from .engine import (ALL_LAYERS, GRADED_LAYERS, Context, Plan,  # noqa: E402
+from .engine import (ALL_LAYERS, GRADED_LAYERS, Context, Plan, TilePipeline,  # noqa: E402
                      classify_device, classify_tile, counters_to_dict,
-                     get_context, pinned_copy, pinned_empty)
+                     get_context, pinned_copy, pinned_empty, wait_tile)
 from .dswx_hls import REPLACED_FUNCTIONS, install, uninstall  # noqa: E402
 from . import dswx_hls  # noqa: E402
 
 __version__ = '0.1.0'
 __all__ = ['ALL_LAYERS', 'GRADED_LAYERS', 'Context', 'Plan', 'classify_device',
-           'classify_tile', 'counters_to_dict', 'get_context', 'pinned_copy',
+           'classify_tile', 'wait_tile', 'TilePipeline', 'counters_to_dict', 'get_context', 'pinned_copy',
            'pinned_empty', 'HlsThresholds', 'make_params', 'install',
            'uninstall', 'dswx_hls', 'REPLACED_FUNCTIONS', 'DEFAULT_PROCESSING',
            'DEM_MARGIN_IN_PIXELS']

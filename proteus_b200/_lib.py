@@ -17,12 +17,13 @@ ADJ_MODES = {'mask': 0, 'ignore': 1, 'cover': 2}
 N_COUNTERS = 12
 E_INVALID_ARG, E_BAD_MODE, E_UNSUPPORTED, E_NO_DRIVER_API, E_ALIGNMENT, E_NCCL = -1, -2, -3, -4, -5, -6
 COMM_ID_BYTES = 128
+HOST_REUSE_ANCILLARY, HOST_ASYNC, HOST_SLOT1 = 1, 2, 4
 KERNEL_FAST, KERNEL_STREAM, KERNEL_FAST8, KERNEL_GENERIC = 1, 2, 4, 8
 
 EXPORTS = (
     'pb200_version', 'pb200_last_error', 'pb200_ctx_create', 'pb200_ctx_destroy',
     'pb200_params_default', 'pb200_classify', 'pb200_plan_create',
-    'pb200_plan_run', 'pb200_plan_kernels', 'pb200_plan_destroy', 'pb200_classify_host', 'pb200_classify_host_ex',
+    'pb200_plan_run', 'pb200_plan_kernels', 'pb200_plan_destroy', 'pb200_classify_host', 'pb200_classify_host_ex', 'pb200_host_wait',
     'pb200_host_alloc', 'pb200_host_free', 'pb200_invalid_and_clip',
     'pb200_diagnostic_tests', 'pb200_diagnostic_tests_f32', 'pb200_interpreted_layer',
     'pb200_binary_representation', 'pb200_preliminary_cloud',
@@ -130,6 +131,7 @@ def load():
     lib.pb200_plan_destroy.argtypes = [C.c_void_p]
     lib.pb200_classify_host.argtypes = [C.c_void_p, C.POINTER(Tile), C.POINTER(Params), C.c_int]
     lib.pb200_classify_host_ex.argtypes = [C.c_void_p, C.POINTER(Tile), C.POINTER(Params), C.c_int, C.c_int]
+    lib.pb200_host_wait.argtypes = [C.c_void_p, C.c_int]
     lib.pb200_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
     lib.pb200_host_free.argtypes = [C.c_void_p]
     P6 = C.c_void_p * 6

@@ -503,6 +503,8 @@ struct HostPipe {               // device mirror of one host tile (pb200_classif
     cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_k;
     // ancillary rasters left on the device by the last successful call (PB200_HOST_REUSE_ANCILLARY)
+    bool pending = false;               // enqueued with PB200_HOST_ASYNC and not yet waited for
+    pb200_tile pending_geom = {};       // what pb200_host_wait records as resident once the work has completed
     bool anc_valid = false, anc_dem = false, anc_land = false, anc_ocean = false;
     int anc_h = 0, anc_w = 0, anc_dem_rows = 0, anc_dem_pitch = 0, anc_dem_off_y = 0, anc_dem_off_x = 0;
 };
@@ -517,7 +519,7 @@ struct pb200_ctx {
     cudaMemPool_t pool = nullptr;    // private stream-ordered pool: plan descriptors, tensor maps, item lists
     cudaStream_t s_plan = nullptr;   // private non-blocking stream: uploads of pb200_plan_create
     Comm comm;                       // NCCL communicator of a row-stripped raster (pb200_comm_init), else empty
-    HostPipe pipe;
+    HostPipe pipe[2];                // two host tiles in flight (PB200_HOST_SLOT1)
     std::mutex mu;
 };
 
@@ -609,16 +611,19 @@ static void pipe_free(HostPipe &p) {
 extern "C" int pb200_ctx_destroy(pb200_ctx *ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
-    HostPipe &p = ctx->pipe;
-    pipe_free(p);
-    cudaFree(p.counters);
-    cudaFree(p.tables);
-    cudaFree(p.arena.base);
-    if (p.s_in) cudaStreamDestroy(p.s_in);
-    if (p.s_k) cudaStreamDestroy(p.s_k);
-    if (p.s_out) cudaStreamDestroy(p.s_out);
-    for (auto e : p.ev_in) cudaEventDestroy(e);
-    for (auto e : p.ev_k) cudaEventDestroy(e);
+    for (HostPipe &p : ctx->pipe) {
+        if (p.s_out) cudaStreamSynchronize(p.s_out);
+        if (p.s_k) cudaStreamSynchronize(p.s_k);
+        pipe_free(p);
+        cudaFree(p.counters);
+        cudaFree(p.tables);
+        cudaFree(p.arena.base);
+        if (p.s_in) cudaStreamDestroy(p.s_in);
+        if (p.s_k) cudaStreamDestroy(p.s_k);
+        if (p.s_out) cudaStreamDestroy(p.s_out);
+        for (auto e : p.ev_in) cudaEventDestroy(e);
+        for (auto e : p.ev_k) cudaEventDestroy(e);
+    }
     if (ctx->comm.comm) pb200_comm_destroy(ctx);
     if (ctx->s_plan) cudaStreamDestroy(ctx->s_plan);
     if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
@@ -1081,6 +1086,28 @@ static void pipe_drain(HostPipe &p) {
         }                                                     \
     } while (0)
 
+// complete the tile enqueued on pipe `p` (outputs in host memory) and record its ancillary rasters as resident
+static int host_wait_locked(pb200_ctx *ctx, HostPipe &p) {
+    if (!p.pending) return 0;
+    p.pending = false;
+    CK(cudaSetDevice(ctx->device));
+    CKP(cudaStreamSynchronize(p.s_out));
+    CKP(cudaStreamSynchronize(p.s_k));
+    const pb200_tile *ht = &p.pending_geom;
+    p.anc_valid = true;
+    p.anc_h = ht->height; p.anc_w = ht->width;
+    p.anc_dem = ht->dem != nullptr; p.anc_land = ht->land != nullptr; p.anc_ocean = ht->ocean != nullptr;
+    p.anc_dem_rows = ht->dem_rows; p.anc_dem_pitch = ht->dem_pitch;
+    p.anc_dem_off_y = ht->dem_off_y; p.anc_dem_off_x = ht->dem_off_x;
+    return 0;
+}
+
+extern "C" int pb200_host_wait(pb200_ctx *ctx, int slot) {
+    if (!ctx || slot < 0 || slot > 1) return fail(PB200_E_INVALID_ARG, "pb200_host_wait: bad argument");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    return host_wait_locked(ctx, ctx->pipe[slot]);
+}
+
 extern "C" int pb200_classify_host(pb200_ctx *ctx, const pb200_tile *ht, const pb200_params *params,
                                    int strip_rows) {
     return pb200_classify_host_ex(ctx, ht, params, strip_rows, 0);
@@ -1089,8 +1116,9 @@ extern "C" int pb200_classify_host(pb200_ctx *ctx, const pb200_tile *ht, const p
 extern "C" int pb200_classify_host_ex(pb200_ctx *ctx, const pb200_tile *ht, const pb200_params *params,
                                       int strip_rows, int flags) {
     if (!ctx || !ht || !params) return fail(PB200_E_INVALID_ARG, "pb200_classify_host: null argument");
-    if (flags & ~PB200_HOST_REUSE_ANCILLARY) return fail(PB200_E_INVALID_ARG, "pb200_classify_host_ex: unknown flag");
-    const bool reuse = (flags & PB200_HOST_REUSE_ANCILLARY) != 0;
+    if (flags & ~(PB200_HOST_REUSE_ANCILLARY | PB200_HOST_ASYNC | PB200_HOST_SLOT1))
+        return fail(PB200_E_INVALID_ARG, "pb200_classify_host_ex: unknown flag");
+    const bool reuse = (flags & PB200_HOST_REUSE_ANCILLARY) != 0, async = (flags & PB200_HOST_ASYNC) != 0;
     std::lock_guard<std::mutex> lock(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     const int H = ht->height, W = ht->width;
@@ -1099,7 +1127,11 @@ extern "C" int pb200_classify_host_ex(pb200_ctx *ctx, const pb200_tile *ht, cons
     strip_rows = ((strip_rows + TH - 1) / TH) * TH;
     const size_t px = (size_t)H * W;
     const size_t dem_elems = ht->dem ? (size_t)ht->dem_rows * ht->dem_pitch : 0;
-    HostPipe &p = ctx->pipe;
+    HostPipe &p = ctx->pipe[(flags & PB200_HOST_SLOT1) ? 1 : 0];
+    if (p.pending) {                                      // the slot's previous tile: complete it first
+        int rcw = host_wait_locked(ctx, p);
+        if (rcw) return rcw;
+    }
     if (reuse) {
         const bool same = p.anc_valid && p.anc_h == H && p.anc_w == W && p.anc_dem == (ht->dem != nullptr) &&
                           p.anc_land == (ht->land != nullptr) && p.anc_ocean == (ht->ocean != nullptr) &&
@@ -1258,13 +1290,16 @@ extern "C" int pb200_classify_host_ex(pb200_ctx *ctx, const pb200_tile *ht, cons
         CKP(cudaMemcpyAsync(ht->counters, p.counters, PB200_N_COUNTERS * sizeof(unsigned long long),
                            cudaMemcpyDeviceToHost, p.s_out));
     if (trace) { CKP(cudaEventRecord(tr[3], p.s_out)); }
-    CKP(cudaStreamSynchronize(p.s_out));
-    CKP(cudaStreamSynchronize(p.s_k));
-    p.anc_valid = true;
-    p.anc_h = H; p.anc_w = W;
-    p.anc_dem = ht->dem != nullptr; p.anc_land = ht->land != nullptr; p.anc_ocean = ht->ocean != nullptr;
-    p.anc_dem_rows = ht->dem_rows; p.anc_dem_pitch = ht->dem_pitch;
-    p.anc_dem_off_y = ht->dem_off_y; p.anc_dem_off_x = ht->dem_off_x;
+    p.pending_geom = *ht;
+    p.pending = true;
+    if (async) {
+        // two tiles in flight: the caller enqueues the next tile on the other slot before it waits for this one
+        if (trace)
+            for (auto &e : tr) cudaEventDestroy(e);
+        return 0;
+    }
+    rc = host_wait_locked(ctx, p);
+    if (rc) return rc;
     if (trace) {
         float h2d = 0, k_end = 0, out_end = 0;
         cudaEventElapsedTime(&h2d, tr[0], tr[1]);

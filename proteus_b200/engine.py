@@ -339,6 +339,32 @@ class Plan:
             pass
 
 
+_cover_staging = {}                # (context, raster shape, DEM shape) -> {name: device tensor}
+_cover_plans = {}                  # (context, raster pointers, shapes, parameter bytes) -> Plan of the first phase
+
+
+def _cached_cover_plan(ctx, tile, params, layers):
+    """Plan of the 'cover' flow's first phase, kept between calls on the same device rasters (a time series re-runs it
+    after overwriting the bands in place): building a plan - descriptors, tensor maps, item list, output rasters - was
+    0.6 of the 1.08 ms the whole flow took (profiles/).  A handful of plans is kept; the outputs of a cached plan are
+    overwritten by the next call that hits it."""
+    def ptr(x):
+        return (int(x.data_ptr()), tuple(x.shape)) if x is not None else None
+    key = (id(ctx), tuple(ptr(b) for b in tile['bands']), ptr(tile['fmask']), ptr(tile.get('dem')), ptr(tile.get('land')),
+           ptr(tile.get('ocean')), float(tile.get('sun_azimuth', 0.0)), float(tile.get('sun_elevation', 90.0)),
+           tile.get('dem_margin'), tuple(tile['dem_off']) if tile.get('dem_off') is not None else None,
+           bytes(params), layers)
+    plan = _cover_plans.pop(key, None)
+    if plan is None:
+        plan = Plan([tile], params, layers, ctx=ctx)
+        while len(_cover_plans) >= 8:
+            _cover_plans.pop(next(iter(_cover_plans))).close()
+    else:
+        plan.zero_counters()
+    _cover_plans[key] = plan           # most recently used last
+    return plan
+
+
 def classify_device_cover(tile, hls_thresholds=None, outputs=ALL_LAYERS, *, collapse_wtr_classes=True,
                           class_histogram=False, ctx=None, **processing):
     """``mask_adjacent_to_cloud_mode='cover'`` for one device-resident tile.
@@ -357,7 +383,7 @@ def classify_device_cover(tile, hls_thresholds=None, outputs=ALL_LAYERS, *, coll
                          collapse_wtr_classes=False, **processing)
     has_dem = tile.get('dem') is not None
     phase1 = ['DIAG', 'WTR1', 'WTR1_REMAPPED', 'WTR2', 'CLOUD'] + (['SHAD'] if has_dem else [])
-    plan = Plan([tile], params, phase1, ctx=ctx)
+    plan = _cached_cover_plan(ctx, tile, params, tuple(phase1))
     plan.run()
     o = plan.outputs[0]
     fmask = tile['fmask']
@@ -405,7 +431,7 @@ def classify_tile(bands, fmask, dem_with_margin=None, landcover_mask=None,
                   sun_elevation_angle=90.0, hls_thresholds=None, *,
                   outputs=ALL_LAYERS, params=None, dem_margin=DEM_MARGIN_IN_PIXELS,
                   dem_off=None, out=None, strip_rows=0, ctx=None, reuse_ancillary=False,
-                  **processing):
+                  slot=0, wait=True, **processing):
     """Classify one tile held in host memory.
 
     Parameters mirror what ``generate_dswx_layers`` has in hand at
@@ -421,6 +447,10 @@ def classify_tile(bands, fmask, dem_with_margin=None, landcover_mask=None,
     ``reuse_ancillary=True`` (time series: the next acquisition of the same MGRS tile): the DEM, LAND and ocean
     rasters the previous call on this context uploaded are used again, only bands and Fmask are copied; the arrays
     must still be passed (same shapes) and be unchanged.
+
+    ``slot`` (0 / 1) selects one of the context's two host pipelines; ``wait=False`` returns as soon as the tile is
+    enqueued - the arrays of the returned dict are complete only after ``wait_tile(result)`` (``TilePipeline`` does
+    this bookkeeping for a stream of tiles: two tiles in flight hide the un-overlapped head and tail of each).
 
     Returns a dict: requested layers (numpy, pinned), 'counters' (uint64[12])
     and 'coverage' (the three percentages of D:5115-5124)."""
@@ -486,11 +516,64 @@ def classify_tile(bands, fmask, dem_with_margin=None, landcover_mask=None,
                sun=(sun_azimuth_angle, sun_elevation_angle),
                out_ptrs={k: v.ctypes.data for k, v in res.items()},
                counters_ptr=counters.ctypes.data)
-    _lib.check(ctx._lib.pb200_classify_host_ex(ctx.handle, C.byref(tile), C.byref(params), int(strip_rows),
-                                               1 if reuse_ancillary else 0))
+    if slot not in (0, 1):
+        raise ValueError('slot: 0 or 1')
+    flags = ((_lib.HOST_REUSE_ANCILLARY if reuse_ancillary else 0) | (_lib.HOST_SLOT1 if slot else 0) |
+             (0 if wait else _lib.HOST_ASYNC))
+    _lib.check(ctx._lib.pb200_classify_host_ex(ctx.handle, C.byref(tile), C.byref(params), int(strip_rows), flags))
     res['counters'] = counters
-    res['coverage'] = counters_to_dict(counters, h * w, ocean_mask is not None)
+    if wait:
+        res['coverage'] = counters_to_dict(counters, h * w, ocean_mask is not None)
+    else:
+        # keep every input alive (and unmodified) until the wait; 'coverage' is filled in by wait_tile
+        res['_pending'] = dict(ctx=ctx, slot=slot, total=h * w, has_ocean=ocean_mask is not None,
+                               keep=(bands, fmask, dem_with_margin, landcover_mask, ocean_mask, tile))
     return res
+
+
+def wait_tile(res):
+    """Complete a tile enqueued with ``classify_tile(..., wait=False)``; returns the same dict, now final."""
+    pend = res.pop('_pending', None)
+    if pend is not None:
+        _lib.check(pend['ctx']._lib.pb200_host_wait(pend['ctx'].handle, pend['slot']))
+        res['coverage'] = counters_to_dict(res['counters'], pend['total'], pend['has_ocean'])
+    return res
+
+
+class TilePipeline:
+    """A stream of host tiles with TWO in flight (the context's two host pipelines): while tile k is classified and
+    its layers travel back, the rasters of tile k + 1 already cross PCIe.
+
+        pipe = TilePipeline()
+        for args in tiles:                      # args / kwargs of classify_tile
+            done = pipe.submit(*args, out=...)  # -> the result of the tile submitted two calls ago, or None
+        last = pipe.flush()                     # -> the results still in flight, oldest first
+
+    Every tile in flight needs its own output buffers (``out=``), inputs may be shared."""
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx or get_context()
+        self._inflight = [None, None]
+        self._n = 0
+
+    def submit(self, *args, **kwargs):
+        slot = self._n & 1
+        self._n += 1
+        done = self._inflight[slot]
+        if done is not None:
+            wait_tile(done)
+        self._inflight[slot] = classify_tile(*args, ctx=self.ctx, slot=slot, wait=False, **kwargs)
+        return done
+
+    def flush(self):
+        order = [(self._n - 2) & 1, (self._n - 1) & 1] if self._n >= 2 else [0]
+        out = []
+        for slot in order:
+            r = self._inflight[slot]
+            if r is not None:
+                out.append(wait_tile(r))
+                self._inflight[slot] = None
+        return out
 
 
 def _classify_tile_cover(bands, fmask, dem_with_margin, landcover_mask, ocean_mask, sun_azimuth_angle,
@@ -501,16 +584,26 @@ def _classify_tile_cover(bands, fmask, dem_with_margin, landcover_mask, ocean_ma
     import torch
     dev = torch.device('cuda', ctx.device)
 
-    def up(a, dtype):
+    # persistent device staging rasters per (context, shape): the same pointers on every call, so that the cached plan
+    # of the first phase is found again (_cached_cover_plan)
+    stage = _cover_staging.setdefault((id(ctx), tuple(np.shape(fmask)),
+                                       tuple(np.shape(dem_with_margin)) if dem_with_margin is not None else None), {})
+
+    def up(a, dtype, name=None):
         if a is None:
             return None
         a = np.ascontiguousarray(a)
         if a.dtype != dtype:
             raise TypeError(f'expected {np.dtype(dtype).name}, got {a.dtype}')
-        return torch.from_numpy(a).to(dev)
-    tile = dict(bands=[up(b, np.int16) for b in bands], fmask=up(fmask, np.uint8),
-                dem=up(dem_with_margin, np.float32), land=up(landcover_mask, np.uint8),
-                ocean=up(ocean_mask, np.uint8), sun_azimuth=sun_azimuth_angle,
+        src = torch.from_numpy(a)
+        dst = stage.get(name)
+        if dst is None or tuple(dst.shape) != tuple(src.shape):
+            dst = stage[name] = torch.empty(src.shape, dtype=src.dtype, device=dev)
+        dst.copy_(src, non_blocking=False)
+        return dst
+    tile = dict(bands=[up(b, np.int16, f'band{k}') for k, b in enumerate(bands)], fmask=up(fmask, np.uint8, 'fmask'),
+                dem=up(dem_with_margin, np.float32, 'dem'), land=up(landcover_mask, np.uint8, 'land'),
+                ocean=up(ocean_mask, np.uint8, 'ocean'), sun_azimuth=sun_azimuth_angle,
                 sun_elevation=sun_elevation_angle, dem_margin=dem_margin, dem_off=dem_off)
     collapse = processing.pop('collapse_wtr_classes', True)
     hist = processing.pop('class_histogram', False)

@@ -901,3 +901,40 @@ def test_hillshade_of_the_otsu_algorithm_matches_the_gdaldem_restatement(pb):
     flat[10, 10] = np.nan
     with np.errstate(all='ignore'):
         assert np.array_equal(G.compute_hillshade(flat, 150.0, 45.0), O.compute_hillshade_gdal(flat, 150.0, 45.0))
+
+
+def test_two_host_tiles_in_flight_give_the_same_layers(pb):
+    """TilePipeline (two alternating host pipelines, pb200_classify_host_ex with PB200_HOST_ASYNC + pb200_host_wait):
+    a stream of different tiles, some sharing their ancillary rasters with reuse_ancillary, equals the oracle tile by
+    tile; results come back in submission order."""
+    tiles = [synth.make_tile(70 + i, 200 + 32 * (i % 3), 264) for i in range(7)]
+    refs = [O.reference_chain(t['bands'], t['fmask'], t['dem'], t['land'], t['ocean'], t['sun_azimuth'], t['sun_elevation'])
+            for t in tiles]
+    pipe = pb.TilePipeline()
+    got = []
+    for t in tiles:
+        r = pipe.submit(t['bands'], t['fmask'], t['dem'], t['land'], t['ocean'], t['sun_azimuth'], t['sun_elevation'],
+                        collapse_wtr_classes=False)
+        if r is not None:
+            got.append(r)
+    got += pipe.flush()
+    assert len(got) == len(tiles)
+    for i, (g, ref) in enumerate(zip(got, refs)):
+        assert '_pending' not in g
+        _assert_layers(g, ref, FUSED_LAYERS, f'tile {i} of the pipeline')
+        assert np.array_equal(g['counters'][:3], ref['counters']), i
+        assert g['coverage']['n_valid'] == int(ref['counters'][0])
+    # time series on both slots: every slot keeps its own resident ancillary rasters
+    a = tiles[0]
+    series = [synth.make_tile(90 + i, 200, 264) for i in range(5)]
+    pipe = pb.TilePipeline()
+    out = []
+    for i, t in enumerate(series):
+        r = pipe.submit(t['bands'], t['fmask'], a['dem'], a['land'], a['ocean'], t['sun_azimuth'], t['sun_elevation'],
+                        collapse_wtr_classes=False, reuse_ancillary=i >= 2)
+        if r is not None:
+            out.append(r)
+    out += pipe.flush()
+    for t, g in zip(series, out):
+        ref = O.reference_chain(t['bands'], t['fmask'], a['dem'], a['land'], a['ocean'], t['sun_azimuth'], t['sun_elevation'])
+        _assert_layers(g, ref, FUSED_LAYERS, 'series')
