@@ -267,6 +267,12 @@ int  pb200_shadow(pb200_ctx *ctx, const float *dem, int rows, int cols,
                   const double *sun_terms /* 5 doubles as in pb200_tile, or NULL */,
                   const pb200_params *params, uint8_t *out, void *stream);
 
+/* The same for a float64 DEM; an integer-typed DEM is converted to float64 by the caller, which is what np.gradient
+ * does with it (D:4255): every operation of D:4255-4281 in float64. */
+int  pb200_shadow_f64(pb200_ctx *ctx, const double *dem, int rows, int cols,
+                      double sun_azimuth, double sun_elevation, const double *sun_terms,
+                      const pb200_params *params, uint8_t *out, void *stream);
+
 /* SURVEY 8f next #1 - the numpy tail of create_landcover_mask (D:1003-1115): 3x3 block counts of the
  * 10 m ESA WorldCover raster [3*rows, 3*cols] (water {80,90,95}, urban 50, tree 10), tree count kept
  * on CGLS forest classes only (forest_class_table[v] != 0), threshold hierarchy thresholds[4] =

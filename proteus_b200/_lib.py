@@ -29,7 +29,7 @@ EXPORTS = (
     'pb200_binary_representation', 'pb200_preliminary_cloud',
     'pb200_aerosol_remap', 'pb200_landcover_shadow_masks',
     'pb200_snow_to_cloud', 'pb200_snow_to_cloud_cover', 'pb200_masked_dilation', 'pb200_cover_tail', 'pb200_cloud_masking', 'pb200_binary_water',
-    'pb200_confidence', 'pb200_collapse', 'pb200_shadow', 'pb200_landcover_aggregate',
+    'pb200_confidence', 'pb200_collapse', 'pb200_shadow', 'pb200_shadow_f64', 'pb200_landcover_aggregate',
     'pb200_browse_table', 'pb200_byte_table', 'pb200_scale_offset',
     'pb200_hillshade', 'pb200_histogram_u8', 'pb200_otsu_threshold', 'pb200_greater_than_u8', 'pb200_ratio_bound',
     'pb200_ratio_sweep', 'pb200_shadow_sweep', 'pb200_angle_thresholds',
@@ -166,6 +166,7 @@ def load():
     lib.pb200_halo_exchange_dem.argtypes = [vp, vp, C.c_int, C.c_int, vp]
     lib.pb200_comm_allreduce_u64.argtypes = [vp, vp, C.c_int, vp]
     lib.pb200_comm_destroy.argtypes = [vp]
+    lib.pb200_shadow_f64.argtypes = lib.pb200_shadow.argtypes
     _lib = lib
     return lib
 

@@ -1726,6 +1726,30 @@ extern "C" int pb200_shadow(pb200_ctx *ctx, const float *dem, int rows, int cols
     LEAVE();
 }
 
+extern "C" int pb200_shadow_f64(pb200_ctx *ctx, const double *dem, int rows, int cols, double sun_azimuth,
+                                double sun_elevation, const double *terms, const pb200_params *params, uint8_t *out,
+                                void *stream) {
+    ENTER(ctx);
+    REQUIRE(dem && out && params, "pb200_shadow_f64: null argument");
+    REQUIRE(rows >= 2 && cols >= 2, "pb200_shadow_f64: the DEM must be at least 2 x 2 (np.gradient, D:4255)");
+    double cos_thr, tan_thr;
+    pb200_angle_thresholds(params, &cos_thr, &tan_thr);
+    pb200_tile t;
+    std::memset(&t, 0, sizeof(t));
+    t.sun_azimuth = sun_azimuth;
+    t.sun_elevation = sun_elevation;
+    t.sun_terms[0] = std::numeric_limits<double>::quiet_NaN();
+    if (terms)
+        for (int i = 0; i < 5; ++i) t.sun_terms[i] = terms[i];
+    TileDev d;
+    sun_terms(t, &d);
+    SunTerms S{d.sx, d.sy, d.sz, d.sin_az, d.cos_az};
+    dim3 block(64, 4), grid((cols + 63) / 64, (rows + 3) / 4);
+    shadow_f64_kernel<<<grid, block, 0, st>>>(dem, rows, cols, out, S, params->pixel_spacing_x, -std::fabs(params->pixel_spacing_y),
+                                              cos_thr, tan_thr);
+    LEAVE();
+}
+
 extern "C" int pb200_landcover_aggregate(pb200_ctx *ctx, const uint8_t *worldcover, const uint8_t *copernicus, int rows,
                                          int cols, const uint8_t forest[256], int year_offset,
                                          const int32_t thresholds[4], uint8_t *land, void *stream) {

@@ -627,6 +627,32 @@ __global__ void shadow_kernel(const float *__restrict__ dem, int rows, int cols,
     out[i] = (uint8_t)shadow_from_gradient(g_col, g_row, P.dxf, P.dyf, S, P.cos_thr, P.tan_thr);
 }
 
+// The same for a float64 DEM - what np.gradient makes of an integer-typed DEM too (D:4255: integer input is converted
+// to float64 first): every operation of D:4255-4281 in float64.
+__global__ void shadow_f64_kernel(const double *__restrict__ dem, int rows, int cols, uint8_t *__restrict__ out,
+                                  SunTerms S, double dx, double dy_neg, double cos_thr, double tan_thr) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= cols || y >= rows) return;
+    const size_t i = (size_t)y * cols + x;
+    double g_col, g_row;
+    if (x == 0) g_col = __dsub_rn(dem[i + 1], dem[i]);
+    else if (x == cols - 1) g_col = __dsub_rn(dem[i], dem[i - 1]);
+    else g_col = __dmul_rn(__dsub_rn(dem[i + 1], dem[i - 1]), 0.5);
+    if (y == 0) g_row = __dsub_rn(dem[i + cols], dem[i]);
+    else if (y == rows - 1) g_row = __dsub_rn(dem[i], dem[i - cols]);
+    else g_row = __dmul_rn(__dsub_rn(dem[i + cols], dem[i - cols]), 0.5);
+    const double nx = __ddiv_rn(-g_col, dx), ny = __ddiv_rn(-g_row, dy_neg);                          // D:4260-4261
+    const double nf = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(nx, nx), __dmul_rn(ny, ny)), 1.0));    // D:4264
+    const double s = __dadd_rn(__dmul_rn(nx, S.sin_az), __dmul_rn(ny, S.cos_az));                     // D:4275-4277
+    uint32_t lit = 1u;
+    if (s <= tan_thr) {                                                                               // back slope
+        const double xc = __ddiv_rn(__dadd_rn(__dadd_rn(__dmul_rn(nx, S.sx), __dmul_rn(ny, S.sy)), S.sz), nf);
+        lit = (xc >= cos_thr && xc <= 1.0) ? 1u : 0u;                                                 // D:4267-4280
+    }
+    out[i] = (uint8_t)lit;
+}
+
 // exhaustive (n, d) in int16^2 check of the integer ratio test against IEEE
 // float64 division (numpy's int16 / int16 -> float64 true_divide)
 __global__ void ratio_sweep_kernel(int a, int b, double t, int is_less, unsigned long long *mismatches) {

@@ -11,7 +11,8 @@ unchanged; the one-pass fused path is ``proteus_b200.classify_tile``.
 Scope notes (explicit errors, no silent fallback):
   * reflectance bands are int16 (the default, D:4640) or, for ``_compute_diagnostic_tests`` only, all
     float32 (``--offset-and-scale-inputs``); the fused path is int16 only;
-  * the DEM must be float32 (what the cubic warp of D:5145 produces).
+  * the DEM of the FUSED path must be float32 (what the cubic warp of D:5145 produces); the function-level
+    ``_compute_opera_shadow_layer`` also takes float64 and integer DEMs (np.gradient's float64 promotion).
 """
 from __future__ import annotations
 
@@ -309,19 +310,23 @@ def _compute_opera_shadow_layer(dem, sun_azimuth_angle, sun_elevation_angle,
     """Bool mask (True = not shadow) over the whole DEM incl. its margin."""
     ctx = get_context()
     d = np.asarray(dem)
-    if d.dtype != np.float32:
-        raise NotImplementedError(
-            f'DEM dtype {d.dtype}: only float32 (the cubic-warped DEM, D:5145-5150)')
     if d.ndim != 2:
         raise ValueError('dem must be 2-D')
     params = make_params(min_slope_angle=min_slope_angle,
                          max_sun_local_inc_angle=max_sun_local_inc_angle,
                          pixel_spacing=(pixel_spacing_x, pixel_spacing_y))
-    dev = _to_device(d, np.float32, 'dem')
-    out = _empty_like_device(d.shape, np.uint8)
     # the five float64 sun scalars come from numpy, like the reference's (D:4245-4252)
     terms = (C.c_double * 5)(*sun_terms(sun_azimuth_angle, sun_elevation_angle))
-    _lib.check(ctx._lib.pb200_shadow(
+    if d.dtype == np.float32:                     # the cubic-warped DEM (D:5145-5150): float32 up to the normalisation
+        entry, dev = ctx._lib.pb200_shadow, _to_device(d, np.float32, 'dem')
+    elif d.dtype == np.float64 or np.issubdtype(d.dtype, np.integer):
+        # np.gradient converts an integer DEM to float64 first; from there on everything is float64
+        entry = ctx._lib.pb200_shadow_f64
+        dev = _torch().from_numpy(np.ascontiguousarray(d, dtype=np.float64)).cuda()
+    else:
+        raise NotImplementedError(f'DEM dtype {d.dtype}: float32, float64 or an integer type')
+    out = _empty_like_device(d.shape, np.uint8)
+    _lib.check(entry(
         ctx.handle, dev.data_ptr(), d.shape[0], d.shape[1], float(sun_azimuth_angle),
         float(sun_elevation_angle), terms, C.byref(params), out.data_ptr(), _stream()))
     return _to_host(out, np.uint8).astype(bool)

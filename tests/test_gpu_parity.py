@@ -292,8 +292,16 @@ def test_shadow_function_matches_oracle_including_borders(pb):
     with np.errstate(all='ignore'):
         ref = O.compute_opera_shadow_layer(dem, 150.0, 45.0, -5, 40)
     assert np.array_equal(G._compute_opera_shadow_layer(dem, 150.0, 45.0, -5, 40), ref)
+    # float64 and integer DEMs: np.gradient promotes an integer DEM to float64, everything then runs in float64
+    rng = np.random.default_rng(8)
+    d64 = (synth._smooth_field(rng, 120, 150, 10.0) * 300.0 + 500.0).astype(np.float64)
+    for az, el in ((150.0, 45.0), (300.0, 80.0)):
+        assert np.array_equal(G._compute_opera_shadow_layer(d64, az, el, -5, 40), O.compute_opera_shadow_layer(d64, az, el, -5, 40))
+        for dt in (np.int16, np.int32, np.uint16):
+            di = d64.astype(dt)
+            assert np.array_equal(G._compute_opera_shadow_layer(di, az, el, -5, 40), O.compute_opera_shadow_layer(di, az, el, -5, 40)), dt
     with pytest.raises(NotImplementedError):
-        G._compute_opera_shadow_layer(dem.astype(np.float64), 150.0, 45.0, -5, 40)
+        G._compute_opera_shadow_layer(dem.astype(np.float16), 150.0, 45.0, -5, 40)
 
 
 def test_error_paths(pb):

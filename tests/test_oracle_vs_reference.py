@@ -114,3 +114,14 @@ def test_otsu_threshold_against_live_reference(ref):
                 live = ref._compute_otsu_threshold(img, norm)
             assert np.array_equal(live, O.compute_otsu_threshold(img, norm))
             assert np.array_equal(live, img > otsu_threshold_from_counts(np.bincount(img.ravel(), minlength=256), norm))
+
+
+@pytest.mark.parametrize('dtype', [np.float64, np.int16, np.int32, np.uint16])
+def test_shadow_layer_on_float64_and_integer_dems_against_live_reference(ref, dtype):
+    """np.gradient promotes an integer DEM to float64 (D:4255); the oracle follows the live reference there too."""
+    from proteus_b200 import synth
+    rng = np.random.default_rng(8)
+    dem = (synth._smooth_field(rng, 90, 110, 9.0) * 300.0 + 500.0).astype(dtype)
+    for az, el in ((150.0, 45.0), (300.0, 80.0), (20.0, 8.0)):
+        assert np.array_equal(O.compute_opera_shadow_layer(dem, az, el, -5, 40),
+                              ref._compute_opera_shadow_layer(dem, az, el, -5, 40))
