@@ -58,7 +58,7 @@ namespace pb200 {
 #define PB200_FT_PATCH_SLOW 1      // evaluate the packed fast path unconditionally and patch wrapped pairs afterwards
 #endif
 #ifndef PB200_FT_LAND_DP4A
-#define PB200_FT_LAND_DP4A 0       // land_lut address as ONE IDP.4A (byte select + base add) instead of shift, mask, add
+#define PB200_FT_LAND_DP4A 1       // land_lut address as ONE IDP.4A (byte select + base add) instead of shift, mask, add
 #endif
 #ifndef PB200_FT_SHADOW_ALWAYS
 #define PB200_FT_SHADOW_ALWAYS 0   // FAST8: evaluate the shadow shortcut for every lane of a tile with a DEM

@@ -34,6 +34,9 @@ namespace pb200 {
 #ifndef PB200_ST_WARPS
 #define PB200_ST_WARPS 23
 #endif
+#ifndef PB200_ST_CONTIGUOUS
+#define PB200_ST_CONTIGUOUS 0      // a CTA takes a contiguous range of the item list (1) or every gridDim-th item (0)
+#endif
 #ifndef PB200_ST_SLEEP_NS
 #define PB200_ST_SLEEP_NS 200      // producer: nanoseconds between polls of an empty barrier
 #endif
@@ -63,6 +66,20 @@ struct __align__(128) StreamSmem {
 };
 
 #define SS_OFF(member) ((uint32_t)offsetof(StreamSmem, member))
+
+// Which items a CTA classifies: every gridDim-th item of the (tile-major, row-major) list, so that at any moment the
+// 148 CTAs read 148 NEIGHBOURING items - the same DRAM pages of every plane, the halo rows and the over-fetched box
+// edges of one CTA are the neighbour's payload.  Contiguous ranges per CTA (a CTA then stays inside one or two tiles
+// and never re-synchronises for a tile change) measured 207 instead of 221 Gpixel/s (profiles/README.md).
+#if PB200_ST_CONTIGUOUS
+#define ST_ITEM_FIRST ((int)(((long long)blockIdx.x * n_items) / gridDim.x))
+#define ST_ITEM_END ((int)(((long long)(blockIdx.x + 1) * n_items) / gridDim.x))
+#define ST_ITEM_STEP 1
+#else
+#define ST_ITEM_FIRST ((int)blockIdx.x)
+#define ST_ITEM_END n_items
+#define ST_ITEM_STEP ((int)gridDim.x)
+#endif
 
 // Registers are allocated per SM sub-partition (16 384 each): 25 warps put 7 on one of them -> at most 72 registers per
 // thread; 21 warps (20 consumers) put 6 -> 80.
@@ -98,7 +115,7 @@ dswx_fused_stream_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *_
         if (lane != 0) return;
         uint32_t k = 0, acquired_tile = 0xffffffffu;
 #pragma unroll 1
-        for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k) {
+        for (int it = ST_ITEM_FIRST; it < ST_ITEM_END; it += ST_ITEM_STEP, ++k) {
             const ItemDesc d = items[it];
             const TileDev &g = tiles[d.tile];
             const CUtensorMap *tm = tmaps + (size_t)d.tile * ST_MAPS;
@@ -175,7 +192,7 @@ dswx_fused_stream_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *_
 
     uint32_t k = 0;
 #pragma unroll 1
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k) {
+    for (int it = ST_ITEM_FIRST; it < ST_ITEM_END; it += ST_ITEM_STEP, ++k) {
         const ItemDesc item = items[it];
         if (item.tile != cur_tile) {
             // tile change: the only synchronisation among all consumer warps (the producer runs ahead on its own)
