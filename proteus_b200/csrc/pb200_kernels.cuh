@@ -49,7 +49,26 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+// Polls of a waiting warp take issue slots from the working warps of its SM sub-partition (profiles/: 12 of 125
+// executed thread-instructions per pixel were YIELD / TRYWAIT / BRA of waiting consumers): the optional
+// suspend-time hint lets the hardware park the thread until the phase completes or the time is over.
+#ifndef PB200_MBAR_HINT_NS
+#define PB200_MBAR_HINT_NS 0
+#endif
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar_addr, uint32_t parity) {
+#if PB200_MBAR_HINT_NS > 0
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar_addr),
+        "r"(parity), "r"((uint32_t)PB200_MBAR_HINT_NS)
+        : "memory");
+#else
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -58,10 +77,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
+        "}\n" ::"r"(bar_addr),
         "r"(parity)
         : "memory");
+#endif
 }
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) { mbar_wait_addr(smem_u32(bar), parity); }
 // the box load alone; the caller has acquired the tensor map (tma_acquire_map) since it was written
 __device__ __forceinline__ void tma_load_2d_acquired(void *dst, const CUtensorMap *map, int c0, int c1,
                                                      unsigned long long *bar) {

@@ -40,6 +40,14 @@ namespace pb200 {
 #ifndef PB200_ST_SLEEP_NS
 #define PB200_ST_SLEEP_NS 200      // producer: nanoseconds between polls of an empty barrier
 #endif
+#ifndef PB200_ST_PRODUCER_HWWAIT
+#define PB200_ST_PRODUCER_HWWAIT 0  // producer waits with the (hinted) hardware try_wait instead of nanosleep polling
+#endif
+#if PB200_ST_PRODUCER_HWWAIT
+#define ST_PRODUCER_WAIT(bar, parity) mbar_wait(bar, parity)
+#else
+#define ST_PRODUCER_WAIT(bar, parity) mbar_wait_sleep(bar, parity, PB200_ST_SLEEP_NS)
+#endif
 constexpr int ST_WARPS = PB200_ST_WARPS;                      // consumer warps; one more warp produces
 constexpr int ST_THREADS = 32 * (ST_WARPS + 1);
 constexpr int ST_ROWS_PER_WARP = 4;                           // a chunk is one row class modulo 4 of the item
@@ -134,7 +142,7 @@ dswx_fused_stream_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *_
             {
                 // DEM tile of the item (or a plain arrival: the phases of full[] / empty[] count items)
                 const uint32_t b = k & 1u;
-                if (k >= 2u) mbar_wait_sleep(&s.empty[b], ((k >> 1) - 1u) & 1u, PB200_ST_SLEEP_NS);
+                if (k >= 2u) ST_PRODUCER_WAIT(&s.empty[b], ((k >> 1) - 1u) & 1u);
                 if (has_dem) {
                     const int dox = __ldg(&g.dem_off_x), doy = __ldg(&g.dem_off_y);
                     const int padx = DEM_PADX + (dox & 3);
@@ -148,7 +156,7 @@ dswx_fused_stream_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *_
 #pragma unroll 1
             for (int c = 0; c < ST_ROWS_PER_WARP; ++c) {
                 const uint32_t q = 4u * k + (uint32_t)c, slot = q & 1u;
-                if (q >= 2u) mbar_wait_sleep(&S.empty_in[slot], ((q >> 1) - 1u) & 1u, PB200_ST_SLEEP_NS);
+                if (q >= 2u) ST_PRODUCER_WAIT(&S.empty_in[slot], ((q >> 1) - 1u) & 1u);
                 // generic-proxy reads of the slot (ordered by the empty barrier) before the async-proxy writes
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_expect_tx(&S.full_in[slot], 6u * ST_BAND_TX + ST_BYTE_TX * (1u + (has_land ? 1u : 0u) + (has_ocean ? 1u : 0u)));
@@ -237,7 +245,7 @@ dswx_fused_stream_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *_
         for (int rr = 0; rr < ST_ROWS_PER_WARP; ++rr, pix += (uint32_t)W) {
             // ---- this warp's row of chunk q: shared memory -> registers, then the slot is free again -------------
             const uint32_t q = 4u * k + (uint32_t)rr, slot = q & 1u;
-            mbar_wait(&S.full_in[slot], (q >> 1) & 1u);
+            mbar_wait_addr(sb + SS_OFF(full_in) + 8u * slot, (q >> 1) & 1u);
             const bool active = rr < nrows && x < W;
             if (active) {
                 const uint32_t xe = (uint32_t)rr * (uint32_t)W + (uint32_t)x0;
@@ -257,10 +265,10 @@ dswx_fused_stream_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *_
                 asm volatile("" ::"r"(w[5][1]), "r"(fm4), "r"(ld4), "r"(oc4) : "memory");
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&S.empty_in[slot]);
+            if (lane == 0) mbar_arrive_addr(sb + SS_OFF(empty_in) + 8u * slot);
             if (!active) continue;
             const int ly = rgrp * ST_ROWS_PER_WARP + rr;
-#define FT_DEM_WAIT() mbar_wait(&s.full[buf], (k >> 1) & 1u)
+#define FT_DEM_WAIT() mbar_wait_addr(sb + FS_OFF(full) + 8u * buf, (k >> 1) & 1u)
 #define FT_ROW_MIDPOINT() do { } while (0)
 #include "pb200_fused_row.inc"
 #undef FT_ROW_MIDPOINT
@@ -269,9 +277,9 @@ dswx_fused_stream_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *_
         // every warp sees the item's DEM phase complete before it arrives on empty[]: the producer's request for item
         // k + 2 waits for all arrivals of item k, so no warp can run two items ahead and arrive twice in one phase
         __syncwarp();
-        if (!dem_ready) mbar_wait(&s.full[buf], (k >> 1) & 1u);
+        if (!dem_ready) mbar_wait_addr(sb + FS_OFF(full) + 8u * buf, (k >> 1) & 1u);
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s.empty[buf]);
+        if (lane == 0) mbar_arrive_addr(sb + FS_OFF(empty) + 8u * buf);
     }
     flush_counters();
 }
