@@ -94,7 +94,11 @@ typedef struct pb200_params {
     /* 1: leave the Fmask snow bit out of CLOUD (and of WTR / CONF): first phase of the 'cover' mode,
      * where the snow mask is dilated (pb200_snow_to_cloud_cover) before it is added (D:2055-2081). */
     int32_t defer_snow;
-    int32_t reserved_;
+    /* 1: the terrain-shadow test (D:4264-4281) with numpy 1.x value-based casting - the reference pins numpy 1.23.5
+     * (setup.py:78), where float32_array * float64_scalar stays float32: sun terms rounded to float32, dot product,
+     * division, arccos / arctan / degrees in float32; the two thresholds above then hold float32 values.
+     * 0: numpy >= 2 promotion (float64 from the dot product on).  Only float32 DEMs are affected. */
+    int32_t numpy1_promotion;
 } pb200_params;
 
 /* One raster tile (an MGRS tile, one acquisition of a time series, or one row

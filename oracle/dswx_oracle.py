@@ -342,14 +342,23 @@ def _central_differences(f, axis):
 
 def compute_opera_shadow_layer(dem, sun_azimuth_angle, sun_elevation_angle,
                                min_slope_angle, max_sun_local_inc_angle,
-                               pixel_spacing_x=30, pixel_spacing_y=30):
+                               pixel_spacing_x=30, pixel_spacing_y=30, numpy1_promotion=False):
     """Bool mask, True = NOT shadow.  Array arithmetic stays in the DEM's
     dtype (float32 for the warped DEM) up to the normalisation factor; the
     products with the float64 sun-vector scalars are float64 under numpy >= 2
-    (NEP 50), which is the semantics the parity target uses."""
+    (NEP 50), which is the semantics the parity target uses.
+
+    ``numpy1_promotion``: numpy 1.x value-based casting instead (the reference
+    pins numpy 1.23.5, setup.py:78): `float32_array * float64_scalar` stays
+    float32 - the scalar is rounded to float32 first - so the dot product, the
+    division, arccos / arctan and degrees all run in float32."""
     az = np.radians(sun_azimuth_angle)                         # D:4245
     zen = np.radians(90 - sun_elevation_angle)                 # D:4246-4247
     sun = (np.sin(az) * np.sin(zen), np.cos(az) * np.sin(zen), np.cos(zen))
+    sin_az, cos_az = np.sin(az), np.cos(az)
+    if numpy1_promotion and np.asarray(dem).dtype == np.float32:
+        sun = tuple(np.float32(v) for v in sun)                # the cast value-based promotion applies to the scalar
+        sin_az, cos_az = np.float32(sin_az), np.float32(cos_az)
     g_row = _central_differences(dem, 0)                       # D:4255
     g_col = _central_differences(dem, 1)
     nx = -g_col / pixel_spacing_x                              # D:4260
@@ -359,7 +368,7 @@ def compute_opera_shadow_layer(dem, sun_azimuth_angle, sun_elevation_angle,
         inc_deg = np.degrees(np.arccos(
             (nx * sun[0] + ny * sun[1] + 1 * sun[2]) / norm))  # D:4267-4273
         dir_deg = np.degrees(np.arctan(
-            nx * np.sin(az) + ny * np.cos(az)))                # D:4275-4277
+            nx * sin_az + ny * cos_az))                        # D:4275-4277
         backslope = dir_deg <= min_slope_angle                 # D:4279
         low_inc = inc_deg <= max_sun_local_inc_angle           # D:4280
     return low_inc | ~backslope                                # D:4281
@@ -512,7 +521,7 @@ def reference_chain(raw_bands, fmask, dem_with_margin=None, landcover=None,
                     ocean_mask=None, sun_azimuth_angle=150.0,
                     sun_elevation_angle=45.0, thresholds=None,
                     processing=None, band_fill=-9999, fmask_fill=255,
-                    dem_margin=DEM_MARGIN_IN_PIXELS):
+                    dem_margin=DEM_MARGIN_IN_PIXELS, numpy1_promotion=False):
     """All layers of the hot path for one tile.  ``raw_bands`` = 6 int16
     arrays in BAND_NAMES order, straight from the file (before clipping)."""
     th = thresholds or default_thresholds()
@@ -529,7 +538,7 @@ def reference_chain(raw_bands, fmask, dem_with_margin=None, landcover=None,
     if dem_with_margin is not None:                            # D:5161-5167
         shad_m = compute_opera_shadow_layer(
             dem_with_margin, sun_azimuth_angle, sun_elevation_angle,
-            pr['min_slope_angle'], pr['max_sun_local_inc_angle'])
+            pr['min_slope_angle'], pr['max_sun_local_inc_angle'], numpy1_promotion=numpy1_promotion)
         shad = (crop_2d_array_all_sides(shad_m, dem_margin)
                 if dem_margin else shad_m)
 

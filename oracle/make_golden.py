@@ -35,11 +35,17 @@ CASES = {
     'ragged_adversarial': (7, 97, 131, dict(adversarial=True, with_ocean=False), 'mask', True, (121.0, 21.0)),
     'shadow_only':      (8, 130, 150, dict(with_land=False, with_ocean=False), 'ignore', True, (200.0, 15.0)),
     'cover_mode':       (5, 160, 192, {}, 'cover', True, None),
+    # DEM on the two decision boundaries of the terrain-shadow test (synth.make_guard_band_dem): about half of the
+    # pixels inside the guard bands of the float32 shortcut; also stored under numpy 1.x promotion (out_*_NUMPY1)
+    'guard_band':       (11, 128, 160, dict(guard_band_dem=True), 'mask', True, (150.0, 56.0)),
 }
 
 
-def reference_chain(ref, t, processing, thresholds, mode, aerosol):
-    """generate_dswx_layers' per-pixel statements, calling the reference."""
+def reference_chain(ref, t, processing, thresholds, mode, aerosol, shadow_fn=None):
+    """generate_dswx_layers' per-pixel statements, calling the reference.  ``shadow_fn`` replaces
+    ref._compute_opera_shadow_layer (ref_import.live_shadow_layer_numpy1: the same code object under numpy 1.x
+    promotion rules)."""
+    shadow_fn = shadow_fn or ref._compute_opera_shadow_layer
     fmask = t['fmask']
     invalid = fmask == 255                                     # D:2204 (Fmask first in v2? order is irrelevant: OR)
     clipped = []
@@ -64,7 +70,7 @@ def reference_chain(ref, t, processing, thresholds, mode, aerosol):
     spatial_no = 0 if n_not_ocean == 0 else int(100 * float(n_valid) / n_not_ocean)
     shad = None
     if t['dem'] is not None:
-        shad_m = ref._compute_opera_shadow_layer(              # D:5161
+        shad_m = shadow_fn(                                    # D:5161
             t['dem'], t['sun_azimuth'], t['sun_elevation'],
             processing['min_slope_angle'], processing['max_sun_local_inc_angle'])
         shad = ref._crop_2d_array_all_sides(shad_m, t['dem_margin'])   # D:5166
@@ -136,8 +142,20 @@ def main():
             numpy_version=np.__version__), f, indent=1, sort_keys=True)
 
     for name, (tid, h, w, kw, mode, aerosol, sun) in CASES.items():
+        kw = dict(kw)
+        guard_band = kw.pop('guard_band_dem', False)
         t = synth.make_tile(tid, h, w, sun=sun, **kw)
+        if guard_band:
+            t['dem'] = synth.make_guard_band_dem(h, w, *sun, min_slope_angle=processing['min_slope_angle'],
+                                                 max_sun_local_inc_angle=processing['max_sun_local_inc_angle'])
         out = reference_chain(ref, t, processing, thresholds, mode, aerosol)
+        if guard_band:
+            np1 = reference_chain(ref, t, processing, thresholds, mode, aerosol,
+                                  shadow_fn=ref_import.live_shadow_layer_numpy1)
+            for key in ('SHAD', 'SHAD_WITH_MARGIN', 'WTR2', 'CLOUD', 'WTR', 'BWTR', 'CONF', 'WTR_COLLAPSED'):
+                out[key + '_NUMPY1'] = np1[key]
+            print(f'{name}: numpy 1.x promotion changes SHAD on {int((np1["SHAD"] != out["SHAD"]).sum())} px, '
+                  f'WTR on {int((np1["WTR"] != out["WTR"]).sum())} px')
         arrays = {f'in_band{k}': b for k, b in enumerate(t['bands'])}
         arrays['in_fmask'] = t['fmask']
         for key in ('dem', 'land', 'ocean'):

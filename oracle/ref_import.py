@@ -71,6 +71,48 @@ def default_runconfig_groups():
         return yaml.safe_load(f)['runconfig']['groups']
 
 
+class _Numpy1ScalarShim:
+    """numpy 1.x value-based casting for the scalar x array expressions of _compute_opera_shadow_layer, obtained from
+    the installed numpy >= 2: sin / cos / radians of a SCALAR return a Python float (same float64 value).  Under NEP 50
+    a Python float is a weak scalar, so `float32_array * python_float` stays float32 with the scalar rounded to float32
+    first - exactly what numpy 1.23.5 (the reference's pin, setup.py:78) does with a float64 scalar.  Scalar x scalar
+    products stay float64 in both.  Everything else is numpy itself."""
+
+    def __getattr__(self, name):
+        import numpy
+        return getattr(numpy, name)
+
+    @staticmethod
+    def _scalar(fn):
+        import numpy
+
+        def wrapped(x):
+            r = fn(x)
+            return float(r) if numpy.ndim(r) == 0 else r
+        return wrapped
+
+    def __init__(self):
+        import numpy
+        self.sin, self.cos, self.radians = (self._scalar(numpy.sin), self._scalar(numpy.cos),
+                                            self._scalar(numpy.radians))
+
+
+def live_shadow_layer_numpy1(dem, sun_azimuth_angle, sun_elevation_angle, min_slope_angle, max_sun_local_inc_angle,
+                             **kw):
+    """The UNMODIFIED code object of ``_compute_opera_shadow_layer`` (dswx_hls.py:4215-4283) executed with the module
+    global ``np`` bound to the shim above: the reference under its own pinned numpy promotion rules."""
+    ref = load()
+    import numpy
+    if numpy.lib.NumpyVersion(numpy.__version__) < '2.0.0':
+        return ref._compute_opera_shadow_layer(dem, sun_azimuth_angle, sun_elevation_angle, min_slope_angle,
+                                               max_sun_local_inc_angle, **kw)
+    fn = ref._compute_opera_shadow_layer
+    g = dict(fn.__globals__)
+    g['np'] = _Numpy1ScalarShim()
+    legacy = types.FunctionType(fn.__code__, g, fn.__name__, fn.__defaults__, fn.__closure__)
+    return legacy(dem, sun_azimuth_angle, sun_elevation_angle, min_slope_angle, max_sun_local_inc_angle, **kw)
+
+
 def live_create_landcover_mask(worldcover_up_3, copernicus, forest_classes, year, mask_type='standard'):
     """Run the UNMODIFIED ``create_landcover_mask`` (dswx_hls.py:911-1130) on in-memory rasters: its two
     ``_warp`` calls (GDAL) return the given arrays and the WorldCover metadata read returns ``year``;

@@ -64,7 +64,7 @@ class Params(C.Structure):
         ('collapse_wtr_classes', C.c_int32),
         ('class_histogram', C.c_int32),
         ('defer_snow', C.c_int32),
-        ('reserved_', C.c_int32),
+        ('numpy1_promotion', C.c_int32),
     ]
 
 

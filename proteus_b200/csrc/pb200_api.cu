@@ -203,13 +203,42 @@ static double derive_tan_threshold(double min_slope) {
     return dunkey(lo);
 }
 
+// float32 flavours (numpy 1.x promotion: arccos / arctan / degrees of float32 arrays, degrees = x * (180 / pi) in float32)
+static uint32_t fkey(float x) { uint32_t b; std::memcpy(&b, &x, 4); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
+static float funkey(uint32_t k) { const uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k; float x; std::memcpy(&x, &b, 4); return x; }
+static const float RAD2DEG_F = (float)RAD2DEG;
+static double derive_cos_threshold_f32(double max_inc) {
+    const float lim = (float)max_inc;
+    auto pred = [&](float x) { return std::acos(x) * RAD2DEG_F <= lim; };
+    if (!pred(1.0f)) return 2.0;
+    if (pred(-1.0f)) return -1.0;
+    uint32_t lo = fkey(-1.0f), hi = fkey(1.0f);
+    while (lo + 1 < hi) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if (pred(funkey(mid))) hi = mid; else lo = mid;
+    }
+    return (double)funkey(hi);
+}
+static double derive_tan_threshold_f32(double min_slope) {
+    const float lim = (float)min_slope;
+    auto pred = [&](float s) { return std::atan(s) * RAD2DEG_F <= lim; };
+    if (pred(INFINITY)) return INFINITY;
+    if (!pred(-INFINITY)) return std::numeric_limits<double>::quiet_NaN();
+    uint32_t lo = fkey(-INFINITY), hi = fkey(INFINITY);
+    while (lo + 1 < hi) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if (pred(funkey(mid))) lo = mid; else hi = mid;
+    }
+    return (double)funkey(lo);
+}
+
 extern "C" int pb200_angle_thresholds(const pb200_params *p, double *cos_inc, double *tan_slope) {
     if (!p || !cos_inc || !tan_slope) return fail(PB200_E_INVALID_ARG, "pb200_angle_thresholds: null argument");
     // NaN in cos_inc_threshold = "derive both"; otherwise both are taken as given
     // (NaN is a legitimate tan_slope_threshold: "no pixel is a back slope").
     if (std::isnan(p->cos_inc_threshold)) {
-        *cos_inc = derive_cos_threshold(p->max_sun_local_inc_angle);
-        *tan_slope = derive_tan_threshold(p->min_slope_angle);
+        *cos_inc = p->numpy1_promotion ? derive_cos_threshold_f32(p->max_sun_local_inc_angle) : derive_cos_threshold(p->max_sun_local_inc_angle);
+        *tan_slope = p->numpy1_promotion ? derive_tan_threshold_f32(p->min_slope_angle) : derive_tan_threshold(p->min_slope_angle);
     } else {
         *cos_inc = p->cos_inc_threshold;
         *tan_slope = p->tan_slope_threshold;
@@ -281,7 +310,8 @@ static int derive_params(const pb200_params *p, DevParams *D, bool fused) {
     for (int k = 0; k < 6; ++k) D->band_fill[k] = p->band_fill[k];
     D->fmask_fill = p->fmask_fill;
     D->flags = (p->apply_aerosol_class_remapping ? PF_AEROSOL : 0u) | (p->collapse_wtr_classes ? PF_COLLAPSE : 0u) |
-               (p->class_histogram ? PF_HISTOGRAM : 0u) | (p->defer_snow ? PF_DEFER_SNOW : 0u);
+               (p->class_histogram ? PF_HISTOGRAM : 0u) | (p->defer_snow ? PF_DEFER_SNOW : 0u) |
+               (p->numpy1_promotion ? PF_NUMPY1 : 0u);
     D->dxf = (float)p->pixel_spacing_x;
     D->dyf = -std::fabs((float)p->pixel_spacing_y);
     double c, t;
@@ -1710,6 +1740,7 @@ extern "C" int pb200_shadow(pb200_ctx *ctx, const float *dem, int rows, int cols
     std::memset(&P, 0, sizeof(P));
     P.dxf = (float)params->pixel_spacing_x;
     P.dyf = -std::fabs((float)params->pixel_spacing_y);
+    P.flags = params->numpy1_promotion ? PF_NUMPY1 : 0u;
     pb200_angle_thresholds(params, &P.cos_thr, &P.tan_thr);
     pb200_tile t;
     std::memset(&t, 0, sizeof(t));

@@ -26,7 +26,8 @@ __device__ __forceinline__ uint32_t expand_class(uint32_t k) {
 
 enum : int { RB_WIGT = 0, RB_P1_MNDWI = 1, RB_P2_MNDWI = 2, RB_P1_NDVI = 3 };
 enum : uint32_t { PF_AEROSOL = 1u, PF_COLLAPSE = 2u, PF_HISTOGRAM = 4u,
-                  PF_DEFER_SNOW = 8u };   // 'cover' flow, phase 1: CLOUD stays the preliminary layer (+ aerosol bit), also on fill pixels
+                  PF_DEFER_SNOW = 8u,     // 'cover' flow, phase 1: CLOUD stays the preliminary layer (+ aerosol bit), also on fill pixels
+                  PF_NUMPY1 = 16u };      // terrain shadow with numpy 1.x promotion: float32 dot product / division (setup.py:78)
 
 // fmask_lut entry layout
 //   bits 0-2 : preliminary CLOUD value (0, 1, 4, 5)          D:1984-1991
@@ -210,11 +211,23 @@ __device__ __forceinline__ uint32_t landcover_shadow(uint32_t w1, int nir, bool 
 // ---------------------------------------------------------------------------
 struct SunTerms { double sx, sy, sz, sin_az, cos_az; };
 
+// np1: numpy 1.x value-based casting (the reference pins numpy 1.23.5, setup.py:78): `float32_array * float64_scalar`
+// stays float32, so the sun terms are rounded to float32 and every product, sum, the division, arccos / arctan and
+// degrees run in float32 (cos_thr / tan_thr then hold the float32 decision boundaries).  Under numpy >= 2 (NEP 50) the
+// same expressions promote to float64.
 __device__ __forceinline__ uint32_t shadow_from_gradient(float g_col, float g_row, float dxf, float dyf,
-                                                         const SunTerms &S, double cos_thr, double tan_thr) {
+                                                         const SunTerms &S, double cos_thr, double tan_thr,
+                                                         bool np1 = false) {
     const float nx = __fdiv_rn(-g_col, dxf);                          // D:4260
     const float ny = __fdiv_rn(-g_row, dyf);                          // D:4261
     const float nf = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(ny, ny)), 1.0f));  // D:4264
+    if (np1) {
+        const float s = __fadd_rn(__fmul_rn(nx, (float)S.sin_az), __fmul_rn(ny, (float)S.cos_az));     // D:4275-4277
+        if (!(s <= (float)tan_thr)) return 1u;
+        const float dot = __fadd_rn(__fadd_rn(__fmul_rn(nx, (float)S.sx), __fmul_rn(ny, (float)S.sy)), (float)S.sz);
+        const float x = __fdiv_rn(dot, nf);                                                            // D:4267-4271
+        return (x >= (float)cos_thr && x <= 1.0f) ? 1u : 0u;
+    }
     const double nxd = (double)nx, nyd = (double)ny, nfd = (double)nf;
     // directional slope: degrees(arctan(s)) <= min_slope  <=>  s <= tan_thr   D:4275-4279
     const double s = __dadd_rn(__dmul_rn(nxd, S.sin_az), __dmul_rn(nyd, S.cos_az));

@@ -302,7 +302,7 @@ __device__ __noinline__ uint32_t shadow_exact(float l, float r, float u, float d
     S.sx = T.sx; S.sy = T.sy; S.sz = T.sz; S.sin_az = T.sin_az; S.cos_az = T.cos_az;
     const float g_col = __fmul_rn(__fsub_rn(r, l), 0.5f);                     // D:4255
     const float g_row = __fmul_rn(__fsub_rn(d, u), 0.5f);
-    return shadow_from_gradient(g_col, g_row, P.dxf, P.dyf, S, P.cos_thr, P.tan_thr) ? 0u : BIG_SHADOWED;
+    return shadow_from_gradient(g_col, g_row, P.dxf, P.dyf, S, P.cos_thr, P.tan_thr, (P.flags & PF_NUMPY1) != 0u) ? 0u : BIG_SHADOWED;
 }
 
 // ---------------------------------------------------------------------------

@@ -267,7 +267,7 @@ dswx_fused_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__restri
                 // np.gradient interior: (f[i+1] - f[i-1]) / 2.0 in float32 (D:4255)
                 const float g_col = __fmul_rn(__fsub_rn(m[j + 2], m[j]), 0.5f);
                 const float g_row = __fmul_rn(__fsub_rn(d[j], u[j]), 0.5f);
-                sh[j] = shadow_from_gradient(g_col, g_row, P.dxf, P.dyf, S, P.cos_thr, P.tan_thr);
+                sh[j] = shadow_from_gradient(g_col, g_row, P.dxf, P.dyf, S, P.cos_thr, P.tan_thr, (P.flags & PF_NUMPY1) != 0u);
             }
         }
 
@@ -645,7 +645,7 @@ __global__ void shadow_kernel(const float *__restrict__ dem, int rows, int cols,
     if (y == 0) g_row = __fsub_rn(dem[i + cols], dem[i]);
     else if (y == rows - 1) g_row = __fsub_rn(dem[i], dem[i - cols]);
     else g_row = __fmul_rn(__fsub_rn(dem[i + cols], dem[i - cols]), 0.5f);
-    out[i] = (uint8_t)shadow_from_gradient(g_col, g_row, P.dxf, P.dyf, S, P.cos_thr, P.tan_thr);
+    out[i] = (uint8_t)shadow_from_gradient(g_col, g_row, P.dxf, P.dyf, S, P.cos_thr, P.tan_thr, (P.flags & PF_NUMPY1) != 0u);
 }
 
 // The same for a float64 DEM - what np.gradient makes of an integer-typed DEM too (D:4255: integer input is converted

@@ -98,50 +98,86 @@ def _f64_unkey(k):
     return float(np.array([b], dtype=np.int64).view(np.float64)[0])
 
 
+def _f32_key(x):
+    k = np.array([x], dtype=np.float32).view(np.int32)[0]
+    return int(k) if k >= 0 else -(2 ** 31) - int(k)
+
+
+def _f32_unkey(k):
+    b = k if k >= 0 else -(2 ** 31) - k
+    return float(np.array([b], dtype=np.int32).view(np.float32)[0])
+
+
+_NUMPY1_PROMOTION_OVERRIDE = None
+
+
+def set_numpy1_promotion(value):
+    """Force the promotion rules of the terrain-shadow test for every parameter set built from now on: True = numpy 1.x
+    (float32), False = numpy >= 2 (float64), None = follow the installed numpy.  Returns the previous setting."""
+    global _NUMPY1_PROMOTION_OVERRIDE
+    previous, _NUMPY1_PROMOTION_OVERRIDE = _NUMPY1_PROMOTION_OVERRIDE, (None if value is None else bool(value))
+    return previous
+
+
+def numpy1_promotion_default():
+    """True when the installed numpy promotes ``float32_array * float64_scalar`` to float32 (numpy 1.x value-based
+    casting; the reference pins numpy 1.23.5, setup.py:78), False under NEP 50 (numpy >= 2): the drop-in follows the
+    numpy it replaces.  ``set_numpy1_promotion`` overrides."""
+    if _NUMPY1_PROMOTION_OVERRIDE is not None:
+        return _NUMPY1_PROMOTION_OVERRIDE
+    return bool((np.ones(1, np.float32) * np.float64(0.1)).dtype == np.float32)
+
+
 @functools.lru_cache(maxsize=64)
-def angle_thresholds(min_slope_angle, max_sun_local_inc_angle):
+def angle_thresholds(min_slope_angle, max_sun_local_inc_angle, numpy1_promotion=False):
     """(cos_thr, tan_thr) such that, with numpy's own arccos / arctan /
     degrees (the functions the reference calls at dswx_hls.py:4267-4277),
 
         degrees(arccos(x)) <= max_inc   <=>  cos_thr <= x <= 1
         degrees(arctan(s)) <= min_slope <=>  s <= tan_thr
 
-    Found by bisection over the ordered float64 values, so the GPU compares
-    against the reference's decision boundary to the last bit without
-    evaluating a transcendental per pixel."""
+    Found by bisection over the ordered float64 values (float32 values with
+    ``numpy1_promotion``: under numpy 1.x the reference evaluates both on
+    float32 arrays), so the GPU compares against the reference's decision
+    boundary to the last bit without evaluating a transcendental per pixel."""
+    if numpy1_promotion:
+        ftype, key, unkey = np.float32, _f32_key, _f32_unkey
+    else:
+        ftype, key, unkey = np.float64, _f64_key, _f64_unkey
     with np.errstate(invalid='ignore'):
+        # one-element ARRAYS and the Python threshold, exactly the operand kinds of D:4279-4280
         def inc_ok(x):
-            return bool(np.degrees(np.arccos(np.float64(x))) <= max_sun_local_inc_angle)
+            return bool((np.degrees(np.arccos(np.array([x], dtype=ftype))) <= max_sun_local_inc_angle)[0])
 
         def slope_ok(s):
-            return bool(np.degrees(np.arctan(np.float64(s))) <= min_slope_angle)
+            return bool((np.degrees(np.arctan(np.array([s], dtype=ftype))) <= min_slope_angle)[0])
 
         if not inc_ok(1.0):
             cos_thr = 2.0
         elif inc_ok(-1.0):
             cos_thr = -1.0
         else:
-            lo, hi = _f64_key(-1.0), _f64_key(1.0)
+            lo, hi = key(-1.0), key(1.0)
             while hi - lo > 1:
                 mid = (lo + hi) // 2
-                if inc_ok(_f64_unkey(mid)):
+                if inc_ok(unkey(mid)):
                     hi = mid
                 else:
                     lo = mid
-            cos_thr = _f64_unkey(hi)
+            cos_thr = unkey(hi)
         if slope_ok(np.inf):
             tan_thr = float('inf')
         elif not slope_ok(-np.inf):
             tan_thr = float('nan')
         else:
-            lo, hi = _f64_key(-np.inf), _f64_key(np.inf)
+            lo, hi = key(-np.inf), key(np.inf)
             while hi - lo > 1:
                 mid = (lo + hi) // 2
-                if slope_ok(_f64_unkey(mid)):
+                if slope_ok(unkey(mid)):
                     lo = mid
                 else:
                     hi = mid
-            tan_thr = _f64_unkey(lo)
+            tan_thr = unkey(lo)
     return cos_thr, tan_thr
 
 
@@ -158,8 +194,12 @@ def make_params(hls_thresholds=None, *, mask_adjacent_to_cloud_mode='mask',
                 apply_aerosol_class_remapping=True, aerosol_fmask_values=None,
                 min_slope_angle=-5, max_sun_local_inc_angle=40,
                 band_fill=-9999, fmask_fill=255, collapse_wtr_classes=True,
-                class_histogram=False, pixel_spacing=(30, 30), defer_snow=False):
-    """Build a ``pb200_params`` structure."""
+                class_histogram=False, pixel_spacing=(30, 30), defer_snow=False,
+                numpy1_promotion=None):
+    """Build a ``pb200_params`` structure.  ``numpy1_promotion``: evaluate the terrain-shadow test as numpy 1.x does
+    (float32 from the dot product on) instead of numpy >= 2 (float64); None = what the installed numpy does."""
+    if numpy1_promotion is None:
+        numpy1_promotion = numpy1_promotion_default()
     th = hls_thresholds or HlsThresholds()
     p = _lib.Params()
     for name in THRESHOLD_FIELDS:
@@ -185,8 +225,9 @@ def make_params(hls_thresholds=None, *, mask_adjacent_to_cloud_mode='mask',
         p.aerosol_class_bits[v] = int(bits[v])
     p.min_slope_angle = float(min_slope_angle)
     p.max_sun_local_inc_angle = float(max_sun_local_inc_angle)
+    p.numpy1_promotion = int(bool(numpy1_promotion))
     p.cos_inc_threshold, p.tan_slope_threshold = angle_thresholds(
-        min_slope_angle, max_sun_local_inc_angle)
+        min_slope_angle, max_sun_local_inc_angle, bool(numpy1_promotion))
     p.pixel_spacing_x, p.pixel_spacing_y = float(pixel_spacing[0]), float(pixel_spacing[1])
     p.collapse_wtr_classes = int(bool(collapse_wtr_classes))
     p.class_histogram = int(bool(class_histogram))

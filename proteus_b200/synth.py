@@ -273,3 +273,37 @@ def make_device_batch(n_tiles, height=HLS_TILE, width=HLS_TILE, *,
         t['sun_azimuth'], t['sun_elevation'] = (150.0, 45.0) if i == 0 else (az, el)
         tiles.append(t)
     return tiles
+
+
+def make_guard_band_dem(height, width, sun_azimuth=150.0, sun_elevation=56.0, *, min_slope_angle=-5.0,
+                        max_sun_local_inc_angle=40.0, margin=DEM_MARGIN, period=16, seed=0):
+    """A float32 DEM (with margin) whose pixels sit ON the two decision boundaries of the terrain-shadow test
+    (dswx_hls.py:4264-4281) - the worst case for a float32 shortcut with guard bands, and the place where numpy 1.x
+    (float32) and numpy >= 2 (float64) promotion can decide differently.
+
+    Rows of the upper half: directional slope = min_slope (1 + delta) with a cross-slope that keeps the incidence angle
+    above max_inc (so the slope test alone decides); lower half: a back slope whose incidence angle is
+    max_inc (1 + delta) (needs 90 - sun_elevation + |slope| == max_inc: the defaults with elevation 56 and a 6 degree
+    slope).  delta is constant per 16 x 16 block, drawn from {0, +-1e-7 ... +-1e-3}; the surface is a sawtooth of
+    planes (period `period` pixels) so that heights stay small and float32 rounding of the heights - about one quantum of
+    the gradient - scatters the pixels across the boundary.  Values at the sawtooth jumps are arbitrary slopes."""
+    rng = np.random.default_rng(7000 + seed)
+    h, w = height + 2 * margin, width + 2 * margin
+    az = np.radians(sun_azimuth)
+    zen = 90.0 - sun_elevation
+    deltas = np.array([0.0, 0.0, 1e-7, -1e-7, 3e-7, -3e-7, 1e-6, -1e-6, 1e-5, -1e-5, 1e-3, -1e-3])
+    by, bx = -(-h // period), -(-w // period)
+    delta = np.kron(deltas[rng.integers(0, len(deltas), (by, bx))], np.ones((period, period)))[:h, :w]
+    yy, xx = np.mgrid[0:h, 0:w]
+    upper = yy < h // 2
+    # slope along the sun azimuth (nx, ny) = t (sin az, cos az) + c (cos az, -sin az)
+    t_upper = np.tan(np.radians(min_slope_angle)) * (1.0 + delta)
+    theta = -(max_sun_local_inc_angle * (1.0 + delta) - zen)          # incidence = zen - theta for a slope along the azimuth
+    t_lower = np.tan(np.radians(theta))
+    t = np.where(upper, t_upper, t_lower)
+    c = np.where(upper, 0.5, 0.0)
+    nx = t * np.sin(az) + c * np.cos(az)
+    ny = t * np.cos(az) - c * np.sin(az)
+    g_col, g_row = -30.0 * nx, 30.0 * ny                              # nx = -g_col / 30, ny = -g_row / -30 (D:4260-4261)
+    dem = g_col * (xx % period) + g_row * (yy % period)
+    return dem.astype(np.float32)

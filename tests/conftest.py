@@ -11,7 +11,7 @@ if ROOT not in sys.path:
 GOLDEN_DIR = os.path.join(ROOT, 'tests', 'golden')
 GOLDEN_CASES = ('full_default', 'full_adversarial', 'ignore_noaerosol',
                 'l30_minimal', 'ragged_adversarial', 'shadow_only',
-                'cover_mode')
+                'cover_mode', 'guard_band')
 
 
 def pytest_configure(config):

@@ -14,7 +14,7 @@ from proteus_b200 import synth
 pytestmark = pytest.mark.gpu
 
 GPU_CASES = ('full_default', 'full_adversarial', 'ignore_noaerosol',
-             'l30_minimal', 'ragged_adversarial', 'shadow_only')
+             'l30_minimal', 'ragged_adversarial', 'shadow_only', 'guard_band')
 FUSED_LAYERS = ('DIAG', 'WTR1', 'WTR1_REMAPPED', 'WTR2', 'CLOUD', 'SHAD', 'WTR',
                 'BWTR', 'CONF')
 
@@ -189,6 +189,62 @@ def test_shadow_shortcuts_never_decide_wrongly(pb):
     os.makedirs(os.path.join(os.path.dirname(__file__), '..', 'gpurun_out'), exist_ok=True)
     with open(os.path.join(os.path.dirname(__file__), '..', 'gpurun_out', 'shadow_sweep_report.json'), 'w') as f:
         json.dump(report, f, indent=1)
+
+
+def test_guard_band_fixture_under_both_numpy_promotions(pb):
+    """VERDICT r1 #3 + ADVICE (numpy 1.23.5 pin): a DEM whose pixels sit ON the two decision boundaries of the
+    terrain-shadow test (about half of them inside the guard bands of the float32 shortcut, so the exact sequence runs
+    there) against the live reference's layers - under numpy >= 2 promotion (float64 dot product, the fixture's out_*)
+    and under numpy 1.x promotion (float32, out_*_NUMPY1: the same reference code object with numpy-1 scalar casting)."""
+    import torch
+    ins, ref = load_golden('guard_band')
+    assert int((ref['SHAD'] != ref['SHAD_NUMPY1']).sum()) > 500          # the two modes really differ on this DEM
+    for np1, sfx in ((False, ''), (True, '_NUMPY1')):
+        got = _classify_host(pb, ins, collapse=False, numpy1_promotion=np1)           # fast kernel, all layers
+        for name in ('SHAD', 'WTR2', 'CLOUD', 'WTR', 'BWTR', 'CONF'):
+            assert np.array_equal(got[name], ref[name + sfx]), (name, np1, int((got[name] != ref[name + sfx]).sum()))
+        assert np.array_equal(got['DIAG'], ref['DIAG']) and np.array_equal(got['WTR1'], ref['WTR1'])
+        # graded layers through the TMA-fed stream kernel (device-resident plan)
+        tile = dict(bands=[torch.from_numpy(b).cuda() for b in ins['bands']], fmask=torch.from_numpy(ins['fmask']).cuda(),
+                    dem=torch.from_numpy(ins['dem']).cuda(), land=torch.from_numpy(ins['land']).cuda(),
+                    ocean=torch.from_numpy(ins['ocean']).cuda(), sun_azimuth=ins['sun_azimuth'],
+                    sun_elevation=ins['sun_elevation'], dem_margin=ins['dem_margin'])
+        params = pb.make_params(mask_adjacent_to_cloud_mode=ins['mode'], apply_aerosol_class_remapping=ins['aerosol'],
+                                collapse_wtr_classes=False, numpy1_promotion=np1)
+        plan = pb.Plan([tile], params, pb.GRADED_LAYERS)
+        assert 'stream' in plan.kernel_name
+        plan.run()
+        res = plan.results(0)
+        for name in ('WTR', 'BWTR', 'CONF'):
+            assert np.array_equal(res[name], ref[name + sfx]), (name, np1)
+        # the function-level drop-in follows the override
+        import proteus_b200.dswx_hls as G
+        from proteus_b200 import params as PP
+        prev = PP.set_numpy1_promotion(np1)
+        try:
+            shad_m = G._compute_opera_shadow_layer(ins['dem'], ins['sun_azimuth'], ins['sun_elevation'], -5, 40)
+        finally:
+            PP.set_numpy1_promotion(prev)
+        assert shad_m.dtype == np.bool_ and np.array_equal(shad_m.astype(np.uint8), ref['SHAD_WITH_MARGIN' + sfx])
+
+
+def test_shadow_shortcuts_never_decide_wrongly_under_numpy1_promotion(pb):
+    """The sweep of test_shadow_shortcuts_never_decide_wrongly with the float32 (numpy 1.x) sequence as the exact side:
+    the guard bands of the shortcuts also cover the reference's own float32 rounding."""
+    import ctypes as C
+    from proteus_b200 import _lib
+    from proteus_b200.params import sun_terms
+    ctx = pb.get_context()
+    params = pb.make_params(numpy1_promotion=True)
+    for az, el in ((150.0, 45.0), (10.0, 5.0), (359.0, 89.0), (135.0, 70.0)):
+        terms = (C.c_double * 5)(*sun_terms(az, el))
+        for mode, n in ((0, 2 ** 30), (1, 2 ** 28), (2, 2 ** 28), (3, 2 ** 22)):
+            counts = (C.c_uint64 * 8)()
+            _lib.check(ctx._lib.pb200_shadow_sweep(ctx.handle, C.byref(params), az, el, terms, mode, 4321 + mode, n, counts))
+            n_s, shadow, dec_c, bad_c, dec_s, bad_s, dec_s2, bad_s2 = [int(v) for v in counts]
+            assert n_s >= n and bad_c == 0 and bad_s == 0 and bad_s2 == 0, (az, el, mode, bad_c, bad_s, bad_s2)
+            if mode == 0:
+                assert dec_s / n_s > 0.999 and 0.02 < shadow / n_s < 0.98
 
 
 def test_device_division_matches_numpy_division():

@@ -141,6 +141,44 @@ def test_angle_thresholds_are_numpy_decision_boundaries():
     assert c == 2.0 and t == float('inf')
 
 
+def test_float32_angle_thresholds_for_numpy1_promotion():
+    """numpy 1.x promotion: the angle tests run on float32 arrays; the thresholds are float32 decision boundaries."""
+    from proteus_b200 import _lib
+    from proteus_b200.params import angle_thresholds, make_params, numpy1_promotion_default, set_numpy1_promotion
+    f32 = np.float32
+    for min_slope, max_inc in ((-5, 40), (-12.5, 33.3), (0, 90)):
+        c, t = angle_thresholds(min_slope, max_inc, True)
+        assert f32(c) == c and f32(t) == t
+        with np.errstate(invalid='ignore'):
+            arr = lambda x: np.array([x], dtype=f32)
+            assert (np.degrees(np.arccos(arr(c))) <= max_inc)[0]
+            assert not (np.degrees(np.arccos(arr(np.nextafter(f32(c), f32(-np.inf))))) <= max_inc)[0]
+            assert (np.degrees(np.arctan(arr(t))) <= min_slope)[0]
+            assert not (np.degrees(np.arctan(arr(np.nextafter(f32(t), f32(np.inf))))) <= min_slope)[0]
+    c64, t64 = angle_thresholds(-5, 40)
+    c32, t32 = angle_thresholds(-5, 40, True)
+    assert abs(c32 - c64) < 1e-6 and abs(t32 - t64) < 1e-7
+    # default follows the installed numpy (>= 2 here: float64), the override and the explicit argument win
+    assert numpy1_promotion_default() == (np.lib.NumpyVersion(np.__version__) < '2.0.0')
+    assert make_params().numpy1_promotion == int(numpy1_promotion_default())
+    prev = set_numpy1_promotion(True)
+    try:
+        p = make_params()
+        assert p.numpy1_promotion == 1 and (p.cos_inc_threshold, p.tan_slope_threshold) == (c32, t32)
+        assert make_params(numpy1_promotion=False).numpy1_promotion == 0
+    finally:
+        set_numpy1_promotion(prev)
+    # the library's own (libm float32) derivation lands within 2 float32 ulps of numpy's
+    lib = _lib.load()
+    q = _lib.Params()
+    lib.pb200_params_default(C.byref(q))
+    q.numpy1_promotion = 1
+    c, t = C.c_double(), C.c_double()
+    assert lib.pb200_angle_thresholds(C.byref(q), C.byref(c), C.byref(t)) == 0
+    assert f32(c.value) == c.value and f32(t.value) == t.value
+    assert abs(c.value - c32) <= 2 * np.spacing(f32(c32)) and abs(t.value - t32) <= 2 * np.spacing(f32(abs(t32)))
+
+
 def test_library_libm_thresholds_agree_with_numpy_ones_here():
     """Not required for parity (Python always passes numpy's), but the libm
     derivation inside the library should land on the same float64."""

@@ -70,6 +70,26 @@ def test_chain_matches_reference_fixture(case):
     assert np.array_equal(got['percentages'], ref['percentages'])
 
 
+def test_guard_band_fixture_under_numpy1_promotion():
+    """The reference pins numpy 1.23.5 (setup.py:78), where the terrain-shadow test runs in float32 from the dot product
+    on.  The guard_band fixture holds the live reference's layers under both promotion rules (oracle/make_golden.py);
+    on its DEM - every pixel on a decision boundary - the two differ, and the oracle follows either."""
+    ins, ref = load_golden('guard_band')
+    assert int((ref['SHAD'] != ref['SHAD_NUMPY1']).sum()) > 500 and int((ref['WTR'] != ref['WTR_NUMPY1']).sum()) > 100
+    got = O.reference_chain(ins['bands'], ins['fmask'], ins['dem'], ins['land'], ins['ocean'], ins['sun_azimuth'],
+                            ins['sun_elevation'], processing=dict(mask_adjacent_to_cloud_mode=ins['mode'],
+                                                                  apply_aerosol_class_remapping=ins['aerosol']),
+                            dem_margin=ins['dem_margin'], numpy1_promotion=True)
+    for name in ('SHAD', 'WTR2', 'CLOUD', 'WTR', 'BWTR', 'CONF', 'WTR_COLLAPSED'):
+        assert np.array_equal(got[name], ref[name + '_NUMPY1']), name
+    shad_m = O.compute_opera_shadow_layer(ins['dem'], ins['sun_azimuth'], ins['sun_elevation'], -5, 40, numpy1_promotion=True)
+    assert np.array_equal(shad_m.astype(np.uint8), ref['SHAD_WITH_MARGIN_NUMPY1'])
+    # a float64 DEM is float64 throughout under both rules
+    d64 = ins['dem'].astype(np.float64)
+    assert np.array_equal(O.compute_opera_shadow_layer(d64, 150.0, 56.0, -5, 40, numpy1_promotion=True),
+                          O.compute_opera_shadow_layer(d64, 150.0, 56.0, -5, 40))
+
+
 @pytest.mark.parametrize('case', ('full_default', 'full_adversarial', 'shadow_only'))
 def test_functions_match_reference_fixture(case):
     """Function-granular: feed each oracle function the reference's

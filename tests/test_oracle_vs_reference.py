@@ -125,3 +125,26 @@ def test_shadow_layer_on_float64_and_integer_dems_against_live_reference(ref, dt
     for az, el in ((150.0, 45.0), (300.0, 80.0), (20.0, 8.0)):
         assert np.array_equal(O.compute_opera_shadow_layer(dem, az, el, -5, 40),
                               ref._compute_opera_shadow_layer(dem, az, el, -5, 40))
+
+
+@pytest.mark.parametrize('az,el,seed', [(150.0, 56.0, 1), (150.0, 45.0, 2), (10.0, 70.0, 3), (220.0, 58.5, 4)])
+def test_shadow_layer_under_numpy1_promotion_against_the_live_code_object(ref, az, el, seed):
+    """The reference pins numpy 1.23.5 (setup.py:78).  ref_import.live_shadow_layer_numpy1 runs the UNMODIFIED code
+    object of _compute_opera_shadow_layer with numpy-1 scalar casting (float32_array * float64_scalar stays float32);
+    the oracle's numpy1_promotion flag follows it - on DEMs built to sit on the decision boundaries, where the two
+    promotion rules decide differently, and on a smooth one, where they agree."""
+    from oracle import ref_import
+    from proteus_b200 import synth
+    dem = synth.make_guard_band_dem(96, 120, az, el, seed=seed)
+    live1 = ref_import.live_shadow_layer_numpy1(dem, az, el, -5, 40)
+    live2 = ref._compute_opera_shadow_layer(dem, az, el, -5, 40)
+    assert live1.dtype == np.bool_
+    assert np.array_equal(O.compute_opera_shadow_layer(dem, az, el, -5, 40, numpy1_promotion=True), live1)
+    assert np.array_equal(O.compute_opera_shadow_layer(dem, az, el, -5, 40), live2)
+    if el == 56.0:
+        assert int((live1 != live2).sum()) > 100
+    rng = np.random.default_rng(seed)
+    smooth = (synth._smooth_field(rng, 90, 110, 9.0) * 300.0 + 500.0).astype(np.float32)
+    smooth[3, 4], smooth[10, 10], smooth[20, 5] = np.nan, np.inf, -np.inf
+    assert np.array_equal(O.compute_opera_shadow_layer(smooth, az, el, -5, 40, numpy1_promotion=True),
+                          ref_import.live_shadow_layer_numpy1(smooth, az, el, -5, 40))
