@@ -1645,8 +1645,11 @@ extern "C" int pb200_histogram_u8(pb200_ctx *ctx, const uint8_t *image, int64_t 
     EMPTY_OK(n);
     REQUIRE(image && counts && n >= 0, "pb200_histogram_u8: bad argument");
     if (n == 0) return 0;
-    // a block counts at most 2^32 - 1 pixels per bin: grid-stride over >= 1 block per SM keeps that far away
-    histogram_u8_kernel<<<grid_for(ctx, (n + 3) / 4, 256), 256, 0, st>>>(image, n, counts);
+    // one CTA per SM (128 KB of lane-private counters each); a CTA counts at most 2^32 - 1 pixels per bin
+    CK(cudaFuncSetAttribute(histogram_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HIST_SMEM_BYTES));
+    const long long work = (n + 16 * 32 * HIST_WARPS - 1) / (16 * 32 * HIST_WARPS);
+    const int grid = (int)std::max<long long>(1, std::min<long long>(work, ctx->sm_count));
+    histogram_u8_kernel<<<grid, 32 * HIST_WARPS, HIST_SMEM_BYTES, st>>>(image, n, counts);
     LEAVE();
 }
 
