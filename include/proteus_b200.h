@@ -359,6 +359,12 @@ int  pb200_ratio_bound(double t, int is_less, int32_t *a, int32_t *b);
  * pairs (d == 0 included: inf / nan semantics). Synchronous. */
 int  pb200_ratio_sweep(pb200_ctx *ctx, double t, int is_less,
                        uint64_t *mismatches);
+/* The FAST8 kernel variant's integer forms of the rational tests (one IDP.2A each on per-pixel packs, sign bookkeeping for
+ * int16 sums that wrapped) and of 4*awesh against numpy's arithmetic (D:1872-1914), over EVERY clipped (green, swir1)
+ * and (nir, red) pair in [1, 32767]^2.  counts[0..4] = mismatches of mndwi > wigt, > pswt_1_mndwi, > pswt_2_mndwi,
+ * ndvi < pswt_1_ndvi, awesh > awgt (must all be 0); counts[5] = visited pairs whose int16 sum wrapped.
+ * PB200_E_UNSUPPORTED when the parameters do not select FAST8.  Synchronous. */
+int  pb200_fast8_sweep(pb200_ctx *ctx, const pb200_params *params, uint64_t counts[6]);
 /* The float32 shortcuts of the terrain-shadow test (D:4264-4281) against the exact float64 sequence on n_samples DEM
  * neighbourhoods generated on the GPU: mode 0 random gradients, 1 on the back-slope boundary (+- a relative 2^-25 ..
  * 2^-12), 2 on the incidence boundary, 3 special values (zeros, denormals, 1e30, +-inf, NaN).  counts[8] = samples,

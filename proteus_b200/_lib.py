@@ -32,7 +32,7 @@ EXPORTS = (
     'pb200_confidence', 'pb200_collapse', 'pb200_shadow', 'pb200_shadow_f64', 'pb200_landcover_aggregate',
     'pb200_browse_table', 'pb200_byte_table', 'pb200_scale_offset',
     'pb200_hillshade', 'pb200_histogram_u8', 'pb200_otsu_threshold', 'pb200_greater_than_u8', 'pb200_ratio_bound',
-    'pb200_ratio_sweep', 'pb200_shadow_sweep', 'pb200_angle_thresholds',
+    'pb200_ratio_sweep', 'pb200_fast8_sweep', 'pb200_shadow_sweep', 'pb200_angle_thresholds',
     'pb200_comm_unique_id', 'pb200_comm_init', 'pb200_halo_exchange_dem', 'pb200_comm_allreduce_u64',
     'pb200_comm_destroy',
 )
@@ -120,6 +120,7 @@ def load():
     lib.pb200_ratio_sweep.argtypes = [C.c_void_p, C.c_double, C.c_int, C.POINTER(C.c_uint64)]
     lib.pb200_shadow_sweep.argtypes = [C.c_void_p, C.POINTER(Params), C.c_double, C.c_double, C.POINTER(C.c_double), C.c_int,
                                        C.c_uint64, C.c_uint64, C.c_uint64 * 8]
+    lib.pb200_fast8_sweep.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(C.c_uint64)]
     lib.pb200_angle_thresholds.argtypes = [C.POINTER(Params), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.pb200_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
     lib.pb200_ctx_destroy.argtypes = [C.c_void_p]

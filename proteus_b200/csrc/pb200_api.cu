@@ -1877,6 +1877,28 @@ extern "C" int pb200_shadow_sweep(pb200_ctx *ctx, const pb200_params *params, do
     return 0;
 }
 
+extern "C" int pb200_fast8_sweep(pb200_ctx *ctx, const pb200_params *params, uint64_t counts[6]) {
+    REQUIRE(ctx && params && counts, "pb200_fast8_sweep: null argument");
+    CK(cudaSetDevice(ctx->device));
+    DevParams P;
+    pb200_params p = *params;
+    if (p.adjacent_mode == PB200_ADJ_COVER) p.adjacent_mode = PB200_ADJ_MASK;
+    int rc = derive_params(&p, &P, true);
+    if (rc) return rc;
+    FastParams F;
+    build_fast_params(&p, P, &F);
+    if (!F.fast8)
+        return fail(PB200_E_UNSUPPORTED, "pb200_fast8_sweep: these parameters do not select the FAST8 kernel variant");
+    unsigned long long *d = nullptr;
+    CK(cudaMalloc((void **)&d, 6 * 8));
+    CK(cudaMemset(d, 0, 6 * 8));
+    fast8_sweep_kernel<<<32767, 256>>>(F, p.th.wigt, p.th.pswt_1_mndwi, p.th.pswt_2_mndwi, p.th.pswt_1_ndvi, p.th.awgt, d);
+    cudaError_t e = cudaMemcpy(counts, d, 6 * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail_cuda(e, "pb200_fast8_sweep");
+    return 0;
+}
+
 extern "C" int pb200_ratio_sweep(pb200_ctx *ctx, double t, int is_less, uint64_t *mismatches) {
     REQUIRE(ctx && mismatches, "pb200_ratio_sweep: null argument");
     CK(cudaSetDevice(ctx->device));

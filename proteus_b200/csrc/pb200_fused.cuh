@@ -60,6 +60,12 @@ namespace pb200 {
 #ifndef PB200_FT_LAND_DP4A
 #define PB200_FT_LAND_DP4A 1       // land_lut address as ONE IDP.4A (byte select + base add) instead of shift, mask, add
 #endif
+#ifndef PB200_FT_FAST8_WRAPFIX
+#define PB200_FT_FAST8_WRAPFIX 1   // FAST8: pixels whose int16 sums wrapped are patched with the IDP.2A forms + sign bookkeeping
+#endif
+#ifndef PB200_FT_NUMPY1
+#define PB200_FT_NUMPY1 1          // the exact shadow sequence honours PF_NUMPY1 (0: A/B builds only)
+#endif
 #ifndef PB200_FT_SHADOW_ALWAYS
 #define PB200_FT_SHADOW_ALWAYS 0   // FAST8: evaluate the shadow shortcut for every lane of a tile with a DEM
 #endif
@@ -296,13 +302,100 @@ __device__ __noinline__ uint32_t diag_pixel_slow(uint32_t B, uint32_t G, uint32_
     return diagnostic_tests<false>((int)(short)(B >> sh), (int)(short)(G >> sh), (int)(short)(R >> sh),
                                    (int)(short)(N >> sh), (int)(short)(S1 >> sh), (int)(short)(S2 >> sh), P);
 }
+// FAST8: the four rational tests and 4*awesh of ONE pixel whose int16 sums wrapped (D:1872-1884: numpy adds int16 arrays
+// modulo 2^16), from the same IDP.2A forms as the fast path plus sign bookkeeping - no division, no scalar re-evaluation:
+//   * a denominator q16 = wrap16(G + S1) < 0: p / q16 > a / b  <=>  (-p) / (-q16) > a / b with -q16 in [2, 32768], the
+//     range the bound a / b was derived for, so the test is the sign of -X instead of X (X = 0 stays false);
+//   * NDVI is evaluated on the pack (N, R), i.e. with the unwrapped N + R: X(q16) = X(N + R) - sa * 65536, then the same
+//     sign flip (a wrapped N + R is always negative);
+//   * 4*awesh uses mbsrn = wrap16(N + S1) (D:1878): - 6 * 65536 when it wrapped; the pack (gs, S1 - G) carries the
+//     WRAPPED gs, which adds 2 * 65536 when G + S1 wrapped.
+// Checked over every (G, S1) and (N, R) in [1, 32767]^2 against IEEE division (pb200_fast8_sweep).
+// `hi` selects the pixel of the pair; returns the sign words of tests 1, 4a, 5a, 4b (ndvi) and awesh.
+struct Fast8Signs { int x0, x1, x2, x3, aw; };
+__device__ __forceinline__ Fast8Signs fast8_signs_wrapped(uint32_t gs, uint32_t gd, uint32_t ns, uint32_t nrs, uint32_t N, uint32_t R,
+                                                          uint32_t B, uint32_t S2, uint32_t hi, const FastParams &F) {
+    const uint32_t sel = hi ? 0x7632u : 0x5410u;
+    const uint32_t pgd = __byte_perm(gs, gd, sel), pnr = __byte_perm(N, R, sel);
+    const int mg = hi ? ((int)gs >> 31) : ((int)(gs << 16) >> 31);          // all ones: G + S1 wrapped (q16 < 0)
+    const int mn = hi ? ((int)nrs >> 31) : ((int)(nrs << 16) >> 31);        // N + R wrapped
+    const int ms = hi ? ((int)ns >> 31) : ((int)(ns << 16) >> 31);          // N + S1 wrapped
+    Fast8Signs r;
+    r.x0 = (dp2a_lo_s16_u8(pgd, F.c_wigt, 0) ^ mg) - mg;
+    r.x1 = (__dp2a_lo((int)pgd, (int)F.c_p1, 0) ^ mg) - mg;
+    r.x2 = (__dp2a_lo((int)pgd, (int)F.c_p2, 0) ^ mg) - mg;
+    const int x3 = __dp2a_lo((int)pnr, (int)F.c_ndvi, 0) - ((F.sa[RB_P1_NDVI] << 16) & mn);
+    r.x3 = (x3 ^ mn) - mn;
+    int aw = F.awesh_init;
+    aw = __dp2a_lo((int)pgd, (int)F.c_aw_gd, aw);
+    aw = __dp2a_lo((int)pnr, (int)F.c_aw_nr, aw);
+    const uint32_t b1 = hi ? (B >> 16) : (B & 0xffffu), s1 = hi ? (S2 >> 16) : (S2 & 0xffffu);   // clipped bands: 1 .. 32767
+    aw += (int)s1 - 4 * (int)b1;
+    r.aw = aw - (mg & 131072) - (ms & 393216);
+    return r;
+}
+// The 5-bit codes of BOTH pixels of a pair (FAST8), out of line and from the six clipped band registers alone - one call
+// per pair with a wrapped sum, few registers live across it.  Correct for an unwrapped pixel of the pair too (every mask
+// is zero there).  Returns code of the low pixel | code of the high pixel << 16.
+__device__ __noinline__ uint32_t diag_pair_wrapped_fast8(uint32_t B, uint32_t G, uint32_t R, uint32_t N, uint32_t S1, uint32_t S2,
+                                                         const FastParams &F) {
+    const uint32_t gs = __vadd2(G, S1), gr = __vadd2(G, R), ns = __vadd2(N, S1), nrs = __vadd2(N, R), gd = __vsub2(S1, G);
+    const uint32_t T4 = __viaddmax_s16x2(N, F.m_p1nir, __vadd2(S1, F.m_p1swir1));
+    const uint32_t T5 = __viaddmax_s16x2(N, F.m_p2nir, __viaddmax_s16x2(S2, F.m_p2swir2,
+                        __viaddmax_s16x2(S1, F.m_p2swir1, __vadd2(B, F.m_p2blue))));
+    bool p2h, p2l;
+    (void)__vibmax_s16x2(ns, gr, &p2h, &p2l);                 // pred = mbsrn >= mbsrv on the wrapped int16 values (D:1896)
+    uint32_t out = 0u;
+#pragma unroll
+    for (uint32_t hi = 0u; hi < 2u; ++hi) {
+        const Fast8Signs r = fast8_signs_wrapped(gs, gd, ns, nrs, N, R, B, S2, hi, F);
+        const uint32_t sh16 = hi ? 0u : 16u;
+        const uint32_t t2w = (hi ? p2h : p2l) ? 0u : 0x80000000u;
+        const uint32_t t4w = (uint32_t)r.x1 & (uint32_t)r.x3 & (T4 << sh16);
+        const uint32_t t5w = (uint32_t)r.x2 & (T5 << sh16);
+        uint32_t d = __funnelshift_l(t5w, 0u, 1);
+        d = __funnelshift_l(t4w, d, 1);
+        d = __funnelshift_l((uint32_t)r.aw, d, 1);
+        d = __funnelshift_l(t2w, d, 1);
+        d = __funnelshift_l((uint32_t)r.x0, d, 1);
+        out |= d << (16u * hi);
+    }
+    return out;
+}
+__device__ __forceinline__ uint32_t shadow_exact1(float l, float r, float u, float d, const DevParams &P, const SunTerms &S) {
+    const float g_col = __fmul_rn(__fsub_rn(r, l), 0.5f);                     // D:4255
+    const float g_row = __fmul_rn(__fsub_rn(d, u), 0.5f);
+    return shadow_from_gradient(g_col, g_row, P.dxf, P.dyf, S, P.cos_thr, P.tan_thr, PB200_FT_NUMPY1 && (P.flags & PF_NUMPY1) != 0u) ? 0u : BIG_SHADOWED;
+}
 __device__ __noinline__ uint32_t shadow_exact(float l, float r, float u, float d, const DevParams &P,
                                               const TileDev &T) {
     SunTerms S;
     S.sx = T.sx; S.sy = T.sy; S.sz = T.sz; S.sin_az = T.sin_az; S.cos_az = T.cos_az;
-    const float g_col = __fmul_rn(__fsub_rn(r, l), 0.5f);                     // D:4255
-    const float g_row = __fmul_rn(__fsub_rn(d, u), 0.5f);
-    return shadow_from_gradient(g_col, g_row, P.dxf, P.dyf, S, P.cos_thr, P.tan_thr, (P.flags & PF_NUMPY1) != 0u) ? 0u : BIG_SHADOWED;
+    return shadow_exact1(l, r, u, d, P, S);
+}
+// The exact sequence for the FOUR pixels of a lane, out of line with two register arguments: the DEM window is re-read
+// from the item's tile in shared memory (`am` = shared address of the lane's first pixel in the middle row, as in the row
+// body), the sun terms from the tile descriptor at `sb`.  Nothing but `am`, `sb` and the result crosses the call - the row
+// loop's registers stay out of the rare path (a 4 x 6-argument call sequence cost 20-40 bytes of spills IN the loop and,
+// with a larger callee, 6 % of the throughput, profiles/).  Bit j of the result: pixel j is in shadow.
+__device__ __noinline__ uint32_t shadow_exact4(uint32_t am, uint32_t sb, const DevParams &P) {
+    constexpr uint32_t RB = 4u * FT_SMW;
+    SunTerms S;
+    {
+        const uint32_t at = sb + (uint32_t)(offsetof(FastSmem, tile) + offsetof(TileDev, sx));
+        double v[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v[i]) : "r"(at + 8u * (uint32_t)i));
+        S.sx = v[0]; S.sy = v[1]; S.sz = v[2]; S.sin_az = v[3]; S.cos_az = v[4];
+    }
+    uint32_t bits = 0u;
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t a = am + 4u * (uint32_t)j;
+        const float l = lds_f32(a - 4u), r = lds_f32(a + 4u), u = lds_f32(a - RB), d = lds_f32(a + RB);
+        bits |= (shadow_exact1(l, r, u, d, P, S) ? 1u : 0u) << j;
+    }
+    return bits;
 }
 
 // ---------------------------------------------------------------------------
@@ -506,7 +599,9 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                     } \
                 } \
                 } while (0)
+#define FT_PADX() padx
 #include "pb200_fused_row.inc"
+#undef FT_PADX
 #undef FT_ROW_MIDPOINT
 #undef FT_DEM_WAIT
             }

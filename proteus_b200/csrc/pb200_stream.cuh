@@ -234,19 +234,19 @@ dswx_fused_stream_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *_
         const bool has_land = s.tile.land != nullptr;
         const bool has_ocean = s.tile.ocean != nullptr;
         constexpr bool has_counters = true, want_shad = false, all_graded = true;
-        const int padx = DEM_PADX + (s.tile.dem_off_x & 3);
         const uint32_t buf = k & 1u;
         bool dem_ready = false;                           // every warp observes the item's DEM phase before it arrives
 
         const int x = x0 + 4 * lane;
-        const int nrows = min(ST_ROWS_PER_WARP, H - (y0 + rgrp * ST_ROWS_PER_WARP));   // warp-uniform, may be <= 0
+        // rows of this item the lane classifies: 0 for lanes right of the raster (one live value instead of x and a row count)
+        const int nrows = x < W ? min(ST_ROWS_PER_WARP, H - (y0 + rgrp * ST_ROWS_PER_WARP)) : 0;   // may be <= 0
         uint32_t pix = (uint32_t)(y0 + rgrp * ST_ROWS_PER_WARP) * (uint32_t)W + (uint32_t)x;
 #pragma unroll 1
         for (int rr = 0; rr < ST_ROWS_PER_WARP; ++rr, pix += (uint32_t)W) {
             // ---- this warp's row of chunk q: shared memory -> registers, then the slot is free again -------------
             const uint32_t q = 4u * k + (uint32_t)rr, slot = q & 1u;
             mbar_wait_addr(sb + SS_OFF(full_in) + 8u * slot, (q >> 1) & 1u);
-            const bool active = rr < nrows && x < W;
+            const bool active = rr < nrows;
             if (active) {
                 const uint32_t xe = (uint32_t)rr * (uint32_t)W + (uint32_t)x0;
                 const uint32_t base = sb + SS_OFF(in) + slot * (uint32_t)sizeof(InSlot);
@@ -270,7 +270,10 @@ dswx_fused_stream_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *_
             const int ly = rgrp * ST_ROWS_PER_WARP + rr;
 #define FT_DEM_WAIT() mbar_wait_addr(sb + FS_OFF(full) + 8u * buf, (k >> 1) & 1u)
 #define FT_ROW_MIDPOINT() do { } while (0)
+// re-read from the tile descriptor where the shadow block needs it: no register (or spill slot) held across the rows
+#define FT_PADX() (DEM_PADX + (int)(lds_u32(sb + FS_TILE(dem_off_x)) & 3u))
 #include "pb200_fused_row.inc"
+#undef FT_PADX
 #undef FT_ROW_MIDPOINT
 #undef FT_DEM_WAIT
         }

@@ -124,4 +124,44 @@ __global__ void __launch_bounds__(256) shadow_sweep_kernel(const __grid_constant
     }
 }
 
+// ---------------------------------------------------------------------------
+// FAST8 integer forms (one IDP.2A per rational test on per-pixel packs, wrapped-sum bookkeeping) against numpy's
+// arithmetic, exhaustively over what the kernel can meet: every clipped (G, S1) in [1, 32767]^2 for the three MNDWI
+// tests and every (N, R) in [1, 32767]^2 for NDVI - int16 sums wrapped like numpy's, quotient by IEEE float64 division
+// (D:1872-1884, 1893-1914) - and 4*awesh on all (G, S1) with pseudo-random N, B, S2 (wrapped mbsrn included).
+// counts: [0] mndwi > wigt, [1] mndwi > pswt_1_mndwi, [2] mndwi > pswt_2_mndwi, [3] ndvi < pswt_1_ndvi, [4] awesh > awgt
+// mismatches; [5] pairs whose G + S1 wrapped (the sweep really visits them).
+__global__ void fast8_sweep_kernel(const __grid_constant__ FastParams F, double wigt, double p1_mndwi, double p2_mndwi, double p1_ndvi,
+                                   double awgt, unsigned long long *counts) {
+    const uint32_t a = blockIdx.x + 1u;                                  // G (and N)
+    unsigned int bad[5] = {0u, 0u, 0u, 0u, 0u}, wrapped = 0u;
+    uint64_t st = 0x1234ull + a * 0x9E3779B97F4A7C15ull + threadIdx.x;
+    for (uint32_t b = 1u + threadIdx.x; b <= 32767u; b += blockDim.x) {  // S1 (and R)
+        const uint32_t rnd = sweep_rng(st), rnd2 = sweep_rng(st);
+        const uint32_t nir = 1u + rnd % 32767u, blue = 1u + (rnd >> 16) % 32767u, swir2 = 1u + rnd2 % 32767u;
+        // lane layout of the kernel: the pixel in the LOW half of every packed register
+        const uint32_t gs = (a + b) & 0xffffu, gd = (b - a) & 0xffffu, ns = (nir + b) & 0xffffu;
+        const uint32_t nrs = (a + b) & 0xffffu;                           // (N, R) = (a, b) for the NDVI form
+        const Fast8Signs m = fast8_signs_wrapped(gs, gd, ns, nrs, nir, 0u, blue, swir2, 0u, F);    // MNDWI forms + awesh
+        const Fast8Signs v = fast8_signs_wrapped(0u, 0u, 0u, nrs, a, b, 0u, 0u, 0u, F);             // NDVI form
+        const double q16 = (double)(short)gs;
+        const double mndwi = __ddiv_rn((double)((int)a - (int)b), q16);  // (G - S1) / wrap16(G + S1)
+        const double ndvi = __ddiv_rn((double)((int)a - (int)b), q16);   // (N - R) / wrap16(N + R): the same numbers
+        bad[0] += (m.x0 < 0) != (mndwi > wigt);
+        bad[1] += (m.x1 < 0) != (mndwi > p1_mndwi);
+        bad[2] += (m.x2 < 0) != (mndwi > p2_mndwi);
+        bad[3] += (v.x3 < 0) != (ndvi < p1_ndvi);
+        const double awesh = (double)blue + 2.5 * (double)a - 1.5 * (double)(short)ns - 0.25 * (double)swir2;   // D:1881
+        bad[4] += (m.aw < 0) != (awesh > awgt);
+        wrapped += (gs & 0x8000u) != 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const unsigned int t = __reduce_add_sync(0xffffffffu, bad[k]);
+        if ((threadIdx.x & 31) == 0 && t) atomicAdd(&counts[k], (unsigned long long)t);
+    }
+    wrapped = __reduce_add_sync(0xffffffffu, wrapped);
+    if ((threadIdx.x & 31) == 0 && wrapped) atomicAdd(&counts[5], (unsigned long long)wrapped);
+}
+
 }  // namespace pb200

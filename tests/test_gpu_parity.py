@@ -152,6 +152,29 @@ def test_ratio_test_exhaustive_int16_pairs(pb, t, is_less):
     assert bad.value == 0
 
 
+def test_fast8_integer_forms_exhaustive(pb):
+    """The FAST8 kernel variant evaluates each rational test as ONE IDP.2A on a per-pixel pack and repairs pixels whose
+    int16 sums wrapped by sign bookkeeping (no division anywhere).  Checked here against numpy's arithmetic - wrapping
+    int16 sums, IEEE float64 quotient (D:1872-1914) - over EVERY clipped (green, swir1) and (nir, red) pair in
+    [1, 32767]^2 (2^30 pairs each; half of them wrap), and 4*awesh on all those pairs with pseudo-random other bands."""
+    import ctypes as C
+    from proteus_b200 import _lib
+    ctx = pb.get_context()
+    for th in (None, pb.HlsThresholds(wigt=0.2, awgt=0.25, pswt_1_mndwi=-0.3, pswt_1_ndvi=0.65, pswt_2_mndwi=-0.55)):
+        params = pb.make_params(th)
+        counts = (C.c_uint64 * 6)()
+        rc = ctx._lib.pb200_fast8_sweep(ctx.handle, C.byref(params), counts)
+        if th is not None and rc == _lib.E_UNSUPPORTED:
+            continue                                   # these thresholds do not have byte-sized bounds: no FAST8 kernel
+        _lib.check(rc)
+        assert [int(c) for c in counts[:5]] == [0, 0, 0, 0, 0], [int(c) for c in counts]
+        assert int(counts[5]) > 2 ** 28               # wrapped pairs were visited
+    # parameters that are not FAST8-shaped are refused, not silently approximated
+    params = pb.make_params(pb.HlsThresholds(wigt=0.123456789))
+    counts = (C.c_uint64 * 6)()
+    assert ctx._lib.pb200_fast8_sweep(ctx.handle, C.byref(params), counts) == _lib.E_UNSUPPORTED
+
+
 def test_shadow_shortcuts_never_decide_wrongly(pb):
     """the float32 shadow shortcuts proved the way the ratio test was - by brute force on the GPU.  For
     five sun geometries: 2^32 random DEM neighbourhoods + 2^30 / 2^28 planted on the decision boundaries (slope:
