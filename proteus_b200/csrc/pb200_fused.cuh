@@ -266,6 +266,16 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
 __device__ __forceinline__ void mbar_arrive_addr(uint32_t bar_addr) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
 }
+// arrive from ONE lane of a converged warp, chosen by elect.sync: no lane id needed (S2R + mask + compare otherwise)
+__device__ __forceinline__ void mbar_arrive_elected(uint32_t bar_addr) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n"
+        "}\n" ::"r"(bar_addr)
+        : "memory");
+}
 __device__ __forceinline__ uint32_t lds_tab32(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds_tab8(uint32_t a) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }

@@ -37,6 +37,9 @@ namespace pb200 {
 #ifndef PB200_ST_CONTIGUOUS
 #define PB200_ST_CONTIGUOUS 0      // a CTA takes a contiguous range of the item list (1) or every gridDim-th item (0)
 #endif
+#ifndef PB200_ST_HOLD_LANE_BAND
+#define PB200_ST_HOLD_LANE_BAND 0  // keep the lane's band address in a register (opaque) instead of re-deriving it per row
+#endif
 #ifndef PB200_ST_SLEEP_NS
 #define PB200_ST_SLEEP_NS 200      // producer: nanoseconds between polls of an empty barrier
 #endif
@@ -198,6 +201,13 @@ dswx_fused_stream_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *_
 #pragma unroll
     for (int kk = 0; kk < 6; ++kk) w[kk][0] = w[kk][1] = 0u;
 
+    // shared addresses of this lane's 4 pixels in row `warp` of slot 0: bands (plane 0) and byte rasters (Fmask plane)
+    uint32_t lane_band = sb + SS_OFF(in) + (uint32_t)rgrp * (2u * ST_BAND_W) + 8u * (uint32_t)lane;
+#if PB200_ST_HOLD_LANE_BAND
+    asm volatile("" : "+r"(lane_band));
+#endif
+    const uint32_t lane_byte = sb + SS_OFF(in) + 6u * ST_BAND_BYTES + (uint32_t)rgrp * ST_BYTE_W + 4u * (uint32_t)lane;
+
     uint32_t k = 0;
 #pragma unroll 1
     for (int it = ST_ITEM_FIRST; it < ST_ITEM_END; it += ST_ITEM_STEP, ++k) {
@@ -230,9 +240,11 @@ dswx_fused_stream_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *_
         }
         const int W = s.tile.width, H = s.tile.height;
         const int x0 = item.tx * FT_W, y0 = item.ty * ST_H;
-        const bool has_dem = s.tile.dem != nullptr;
-        const bool has_land = s.tile.land != nullptr;
-        const bool has_ocean = s.tile.ocean != nullptr;
+        // which optional rasters the tile has, as ONE opaque register: kept as `pointer != nullptr` the compiler holds the
+        // two 64-bit pointers across the row loop (predicates do not survive the out-of-line calls) and re-tests them per row
+        uint32_t tflags = (s.tile.dem != nullptr ? 1u : 0u) | (s.tile.land != nullptr ? 2u : 0u) | (s.tile.ocean != nullptr ? 4u : 0u);
+        asm volatile("" : "+r"(tflags));
+        const bool has_dem = (tflags & 1u) != 0u, has_land = (tflags & 2u) != 0u, has_ocean = (tflags & 4u) != 0u;
         constexpr bool has_counters = true, want_shad = false, all_graded = true;
         const uint32_t buf = k & 1u;
         bool dem_ready = false;                           // every warp observes the item's DEM phase before it arrives
@@ -244,14 +256,16 @@ dswx_fused_stream_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *_
 #pragma unroll 1
         for (int rr = 0; rr < ST_ROWS_PER_WARP; ++rr, pix += (uint32_t)W) {
             // ---- this warp's row of chunk q: shared memory -> registers, then the slot is free again -------------
-            const uint32_t q = 4u * k + (uint32_t)rr, slot = q & 1u;
-            mbar_wait_addr(sb + SS_OFF(full_in) + 8u * slot, (q >> 1) & 1u);
+            // chunk q = 4 k + rr of this CTA: slot q & 1 = rr & 1, and the phase of its barrier (q >> 1) & 1 = (rr >> 1) & 1 -
+            // both independent of the item (4 chunks per item, 2 slots)
+            const uint32_t slot = (uint32_t)rr & 1u;
+            mbar_wait_addr(sb + SS_OFF(full_in) + 8u * slot, ((uint32_t)rr >> 1) & 1u);
             const bool active = rr < nrows;
             if (active) {
                 const uint32_t xe = (uint32_t)rr * (uint32_t)W + (uint32_t)x0;
-                const uint32_t base = sb + SS_OFF(in) + slot * (uint32_t)sizeof(InSlot);
-                const uint32_t ab = base + (uint32_t)rgrp * (2u * ST_BAND_W) + 2u * (xe & 7u) + 8u * (uint32_t)lane;
-                const uint32_t ay = base + 6u * ST_BAND_BYTES + (uint32_t)rgrp * ST_BYTE_W + (xe & 15u) + 4u * (uint32_t)lane;
+                const uint32_t base = slot * (uint32_t)sizeof(InSlot);
+                const uint32_t ab = base + lane_band + 2u * (xe & 7u);
+                const uint32_t ay = base + lane_byte + (xe & 15u);
 #pragma unroll
                 for (int kk = 0; kk < 6; ++kk) {
                     uint32_t v0, v1;
@@ -265,7 +279,7 @@ dswx_fused_stream_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *_
                 asm volatile("" ::"r"(w[5][1]), "r"(fm4), "r"(ld4), "r"(oc4) : "memory");
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive_addr(sb + SS_OFF(empty_in) + 8u * slot);
+            mbar_arrive_elected(sb + SS_OFF(empty_in) + 8u * slot);      // one lane of the (converged) warp
             if (!active) continue;
             const int ly = rgrp * ST_ROWS_PER_WARP + rr;
 #define FT_DEM_WAIT() mbar_wait_addr(sb + FS_OFF(full) + 8u * buf, (k >> 1) & 1u)
