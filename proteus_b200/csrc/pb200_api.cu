@@ -573,6 +573,7 @@ struct pb200_plan {
     bool no_fast8 = false;                           // PB200_NO_FAST8=1: run the general variant (A/B, tests)
     int n_fast_seen = 0;
     bool stream = false;                             // every fast tile meets the preconditions of dswx_fused_stream_kernel
+    bool stream_dyn = false;                         // ... and it runs as dswx_fused_stream_dyn_kernel (128 x 48 items, 12-row boxes)
     int maps_per_tile = 1;                           // tensor maps per fast tile: 1 (DEM) or ST_MAPS
     bool stream_ordered = false;                     // allocated with cudaMallocAsync
     bool from_arena = false;                         // allocated from a caller-owned arena: nothing to free
@@ -766,7 +767,7 @@ static int plan_build(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles, cons
         const pb200_tile &t = tiles[i];
         bool fast = (d.flags & TF_VEC) && (d.dem == nullptr || (d.flags & TF_TMA)) &&
                     (uint64_t)d.height * (uint64_t)d.width < 0xfff00000ull && d.width <= 65000 * FT_W &&
-                    d.height <= 65000 * std::min(FT_H, ST_H);
+                    d.height <= 65000 * std::min(std::min(FT_H, ST_H), SD_H);
         (void)t;
         // the first DEM box of a row of items must not start left of the DEM array
         if (d.dem) fast = fast && d.dem_off_x >= DEM_PADX + (d.dem_off_x & 3);
@@ -792,9 +793,14 @@ static int plan_build(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles, cons
     }
     // TMA-fed variant: lean product configuration only (all four graded layers + counters on every fast tile)
     pl->stream = stream_ok && pl->n_fast_seen > 0 && !pl->fast_optional && pl->fast_all_graded;
+    {
+        // rows handed to whichever warp is free, deep ring (default), or row w of every chunk to warp w (PB200_STREAM_DYNAMIC=0)
+        const char *e = std::getenv("PB200_STREAM_DYNAMIC");
+        pl->stream_dyn = pl->stream && !(e && e[0] == '0');
+    }
     // items and DEM boxes of the fast tiles, in the geometry of the kernel that will run them
     {
-        const int item_h = pl->stream ? ST_H : FT_H;
+        const int item_h = pl->stream_dyn ? SD_H : pl->stream ? ST_H : FT_H;
         for (int i = 0; i < n_tiles; ++i) {
             pl->item_start.push_back((int)items.size());
             if (pl->tile_group[i] == G_FAST) {
@@ -831,7 +837,7 @@ static int plan_build(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles, cons
             auto enc = [&](CUtensorMap *dst, CUtensorMapDataType dt, const void *base, size_t esz, int box_w) -> bool {
                 if (!base) return true;
                 const cuuint64_t gstr[1] = {(cuuint64_t)4 * d.width * esz};
-                const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)ST_WARPS};
+                const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)(pl->stream_dyn ? SD_CH : ST_WARPS)};
                 return ctx->encode(dst, dt, 2, const_cast<void *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -841,7 +847,7 @@ static int plan_build(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles, cons
             ok = ok && enc(&m[SM_FMASK], CU_TENSOR_MAP_DATA_TYPE_UINT8, d.fmask, 1, ST_BYTE_W);
             ok = ok && enc(&m[SM_LAND], CU_TENSOR_MAP_DATA_TYPE_UINT8, d.land, 1, ST_BYTE_W);
             ok = ok && enc(&m[SM_OCEAN], CU_TENSOR_MAP_DATA_TYPE_UINT8, d.ocean, 1, ST_BYTE_W);
-            if (!ok) { pl->stream = false; break; }
+            if (!ok) { pl->stream = false; break; }     // (cannot happen after the checks above; the items would have the wrong height)
         }
         if (pl->stream) {
             tm[G_FAST].swap(all);
@@ -905,6 +911,8 @@ static int fast_kernel_setup(pb200_ctx *ctx) {
     }
     CK(cudaFuncSetAttribute(dswx_fused_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamSmem)));
     CK(cudaFuncSetAttribute(dswx_fused_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamSmem)));
+    CK(cudaFuncSetAttribute(dswx_fused_stream_dyn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamDynSmem)));
+    CK(cudaFuncSetAttribute(dswx_fused_stream_dyn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamDynSmem)));
     int nb = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dswx_fused_fast_kernel<false>, FtGeom<false>::THREADS, FAST_DYN_SMEM));
     ctx->fast_ctas_per_sm = nb > 0 ? nb : 1;
@@ -921,6 +929,15 @@ static void launch_fast(pb200_plan *pl, const ItemDesc *it, int n, cudaStream_t 
     const bool f8 = pl->F.fast8 != 0u && !pl->no_fast8;
     if (pl->stream) {
         const int g1 = std::min(n, ctx->sm_count);            // 219 KB of shared memory: one CTA per SM
+        if (pl->stream_dyn) {
+            if (f8)
+                dswx_fused_stream_dyn_kernel<true><<<g1, ST_THREADS, sizeof(StreamDynSmem), stream>>>(
+                    pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, it, n, pl->P, pl->F);
+            else
+                dswx_fused_stream_dyn_kernel<false><<<g1, ST_THREADS, sizeof(StreamDynSmem), stream>>>(
+                    pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, it, n, pl->P, pl->F);
+            return;
+        }
         if (f8)
             dswx_fused_stream_kernel<true><<<g1, ST_THREADS, sizeof(StreamSmem), stream>>>(
                 pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, it, n, pl->P, pl->F);
@@ -1276,7 +1293,7 @@ extern "C" int pb200_classify_host_ex(pb200_ctx *ctx, const pb200_tile *ht, cons
     }
     // worst case per strip: descriptor + tensor map + one item per FT_W x FT_H pixels
     {
-        const size_t items_max = (size_t)((W + FT_W - 1) / FT_W) * (size_t)((H + std::min(FT_H, ST_H) - 1) / std::min(FT_H, ST_H) + n_strips);
+        const size_t items_max = (size_t)((W + FT_W - 1) / FT_W) * (size_t)((H + SD_H - 1) / SD_H + n_strips);
         const size_t need = (size_t)n_strips * (sizeof(TileDev) + ST_MAPS * sizeof(CUtensorMap) + 1024) +
                             items_max * sizeof(ItemDesc) + 8192;
         if (need > p.arena.cap) {

@@ -610,7 +610,11 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                 } \
                 } while (0)
 #define FT_PADX() padx
+#define FT_TB sb
+#define FT_DEM_BASE (sb + FS_OFF(dem) + buf * (uint32_t)sizeof(DemHalf))
 #include "pb200_fused_row.inc"
+#undef FT_DEM_BASE
+#undef FT_TB
 #undef FT_PADX
 #undef FT_ROW_MIDPOINT
 #undef FT_DEM_WAIT

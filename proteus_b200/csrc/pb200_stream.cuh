@@ -40,6 +40,14 @@ namespace pb200 {
 #ifndef PB200_ST_HOLD_LANE_BAND
 #define PB200_ST_HOLD_LANE_BAND 0  // keep the lane's band address in a register (opaque) instead of re-deriving it per row
 #endif
+#ifndef PB200_ST_ROTATE
+#define PB200_ST_ROTATE 0          // row of chunk c that warp w classifies: (w + PB200_ST_ROTATE * c) mod ST_WARPS - a warp then samples the
+#endif                             // whole height of the item instead of 4 neighbouring rows (water is blocky: balances the shadow work)
+#if PB200_ST_ROTATE
+#define PB200_ST_PIX_STEP
+#else
+#define PB200_ST_PIX_STEP , pix += (uint32_t)W
+#endif
 #ifndef PB200_ST_SLEEP_NS
 #define PB200_ST_SLEEP_NS 200      // producer: nanoseconds between polls of an empty barrier
 #endif
@@ -252,20 +260,35 @@ dswx_fused_stream_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *_
         const int x = x0 + 4 * lane;
         // rows of this item the lane classifies: 0 for lanes right of the raster (one live value instead of x and a row count)
         const int nrows = x < W ? min(ST_ROWS_PER_WARP, H - (y0 + rgrp * ST_ROWS_PER_WARP)) : 0;   // may be <= 0
+#if !PB200_ST_ROTATE
         uint32_t pix = (uint32_t)(y0 + rgrp * ST_ROWS_PER_WARP) * (uint32_t)W + (uint32_t)x;
+#endif
 #pragma unroll 1
-        for (int rr = 0; rr < ST_ROWS_PER_WARP; ++rr, pix += (uint32_t)W) {
+        for (int rr = 0; rr < ST_ROWS_PER_WARP; ++rr PB200_ST_PIX_STEP) {
             // ---- this warp's row of chunk q: shared memory -> registers, then the slot is free again -------------
             // chunk q = 4 k + rr of this CTA: slot q & 1 = rr & 1, and the phase of its barrier (q >> 1) & 1 = (rr >> 1) & 1 -
             // both independent of the item (4 chunks per item, 2 slots)
             const uint32_t slot = (uint32_t)rr & 1u;
             mbar_wait_addr(sb + SS_OFF(full_in) + 8u * slot, ((uint32_t)rr >> 1) & 1u);
+#if PB200_ST_ROTATE
+            uint32_t rrow = (uint32_t)rgrp + (uint32_t)(PB200_ST_ROTATE * rr);
+            if (rrow >= (uint32_t)ST_WARPS) rrow -= (uint32_t)ST_WARPS;
+            const int ly = 4 * (int)rrow + rr;
+            const bool active = x < W && y0 + ly < H;
+            const uint32_t pix = (uint32_t)(y0 + ly) * (uint32_t)W + (uint32_t)x;
+#else
             const bool active = rr < nrows;
+#endif
             if (active) {
                 const uint32_t xe = (uint32_t)rr * (uint32_t)W + (uint32_t)x0;
                 const uint32_t base = slot * (uint32_t)sizeof(InSlot);
+#if PB200_ST_ROTATE
+                const uint32_t ab = base + sb + SS_OFF(in) + rrow * (2u * ST_BAND_W) + 8u * (uint32_t)lane + 2u * (xe & 7u);
+                const uint32_t ay = base + sb + SS_OFF(in) + 6u * ST_BAND_BYTES + rrow * ST_BYTE_W + 4u * (uint32_t)lane + (xe & 15u);
+#else
                 const uint32_t ab = base + lane_band + 2u * (xe & 7u);
                 const uint32_t ay = base + lane_byte + (xe & 15u);
+#endif
 #pragma unroll
                 for (int kk = 0; kk < 6; ++kk) {
                     uint32_t v0, v1;
@@ -281,12 +304,18 @@ dswx_fused_stream_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *_
             __syncwarp();
             mbar_arrive_elected(sb + SS_OFF(empty_in) + 8u * slot);      // one lane of the (converged) warp
             if (!active) continue;
+#if !PB200_ST_ROTATE
             const int ly = rgrp * ST_ROWS_PER_WARP + rr;
+#endif
 #define FT_DEM_WAIT() mbar_wait_addr(sb + FS_OFF(full) + 8u * buf, (k >> 1) & 1u)
 #define FT_ROW_MIDPOINT() do { } while (0)
 // re-read from the tile descriptor where the shadow block needs it: no register (or spill slot) held across the rows
 #define FT_PADX() (DEM_PADX + (int)(lds_u32(sb + FS_TILE(dem_off_x)) & 3u))
+#define FT_TB sb
+#define FT_DEM_BASE (sb + FS_OFF(dem) + buf * (uint32_t)sizeof(DemHalf))
 #include "pb200_fused_row.inc"
+#undef FT_DEM_BASE
+#undef FT_TB
 #undef FT_PADX
 #undef FT_ROW_MIDPOINT
 #undef FT_DEM_WAIT
@@ -299,6 +328,286 @@ dswx_fused_stream_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *_
         if (lane == 0) mbar_arrive_addr(sb + FS_OFF(empty) + 8u * buf);
     }
     flush_counters();
+}
+
+// ---------------------------------------------------------------------------
+// K1d: the same TMA-fed kernel with DYNAMIC ROW ASSIGNMENT and a deep ring.
+//
+// In dswx_fused_stream_kernel warp w always classifies row w of every chunk.  Rows differ in cost (the terrain-shadow
+// block runs only for rows that hold a water-class pixel), the two-slot ring lets the warps drift apart by little more
+// than one row, and so warps with cheap rows wait for the ones with expensive rows: 16 of 123 executed thread-instructions
+// per pixel were polls of full_in, and evaluating the shadow shortcut for EVERY row cost nothing (profiles/).  Here a row
+// goes to whichever warp is free, and the ring is deep enough that nobody waits for data:
+//
+//  * items are 128 x 64 pixels (16 super-rows); a chunk = the 16 rows of one row class of the item (9 boxes of 16 rows,
+//    33 KB); the DEM tile of an item is 66 x 136 floats - together 4 ring slots + 2 DEM tiles + tables = 216 KB.  A slot
+//    is refilled as soon as its 16 rows have been copied to registers: between 3 and 4 chunks (2 - 2.8 row times of the
+//    23 warps) are always requested ahead of the row being handed out;
+//  * one ticket counter per CTA in shared memory; ticket t = row (t mod 16) of chunk q = t div 16 of the CTA's chunk
+//    sequence (item k = q div 4, row class c = q mod 4 = ring slot).  A warp takes a ticket, waits for that chunk, copies
+//    its row to registers, releases the ring slot, classifies, takes the next ticket;
+//  * every slot has TWO full barriers used by alternate generations (= items): a warp that waits for generation k waits
+//    on a barrier whose previous user was generation k - 2, complete long ago - the parity test cannot alias however far
+//    the warps drift apart (8 chunks would need 128 outstanding tickets; there are 23 warps);
+//  * everything a row needs to know about its item is ONE 16-byte shared-memory vector the producer writes with the
+//    descriptor: width, height, item position, which rasters exist, tile index - no global load in the row loop;
+//  * nothing ties a warp to a tile: the producer writes the tile descriptor and the sun constants of item k into
+//    descriptor slot k & 1 (plain shared-memory stores, released by the barrier arrivals that follow them) when it
+//    requests the item; at most the items k and k + 1 are in flight, because the producer requests item k + 2 only after
+//    all 48 rows of item k have been released (empty[k & 1], one arrival PER ROW, after the row's last look at the DEM
+//    tile and the descriptor) and after it has itself seen item k's DEM transaction complete;
+//  * the coverage counters stay in per-thread registers and are flushed when a warp's next ticket belongs to another
+//    item - BEFORE the warp releases its last row of the old item, i.e. while that item's descriptor is still valid.
+// No synchronisation among the consumer warps at all (no named barrier at tile changes).
+constexpr int SD_CH = 16;                                     // rows per chunk = TMA box height = tickets per chunk
+constexpr int SD_H = 4 * SD_CH;                               // item height (64 rows)
+constexpr int SD_NSLOT = 4;                                   // ring slots (= chunks per item: slot = row class, generation = item)
+static_assert((SD_CH & (SD_CH - 1)) == 0 && SD_NSLOT == 4, "ticket -> (chunk, row, slot, generation) by shifts and masks");
+constexpr int SD_SMH = SD_H + 2;                              // DEM tile rows
+constexpr uint32_t SD_DEM_BOX_BYTES = SD_SMH * FT_SMW * sizeof(float);
+constexpr uint32_t SD_BAND_TX = sizeof(int16_t) * SD_CH * ST_BAND_W, SD_BYTE_TX = SD_CH * ST_BYTE_W;          // bytes per box
+constexpr uint32_t SD_BAND_BYTES = (SD_BAND_TX + 127u) & ~127u, SD_BYTE_BYTES = (SD_BYTE_TX + 127u) & ~127u;  // plane pitch
+struct __align__(128) DynSlot {
+    unsigned char band[6][SD_BAND_BYTES];                     // [SD_CH][ST_BAND_W] int16 each
+    unsigned char byte[3][SD_BYTE_BYTES];                     // [SD_CH][ST_BYTE_W] bytes: Fmask, LAND, ocean
+};
+struct __align__(128) DynDem { float v[SD_SMH][FT_SMW]; };
+struct __align__(16) TileSlot {
+    TileDev tile; float sun32[12];
+    uint4 row_info;                                           // width, height, tx | ty << 16, TSF_* | tile index << 3
+};
+static_assert(offsetof(FastSmem, sun32) - offsetof(FastSmem, tile) == offsetof(TileSlot, sun32), "TileSlot mirrors FastSmem::tile / sun32");
+struct __align__(128) StreamDynSmem {
+    DynDem dem[2];
+    // the table block in the order of FusedTables / FastSmem (the row body addresses it relative to big_lut)
+    uint32_t big_lut[2048];
+    uint32_t diag_lut[128];
+    uint8_t  fk_lut[4096];
+    uint8_t  land_lut[256];
+    uint8_t  kill_lut[128];
+    TileSlot desc[2];                                         // descriptor + sun constants of the items k (slot k & 1)
+    unsigned long long full[2], empty[2];                     // DEM tile of item k: transaction barrier / 48 row releases
+    unsigned long long full_in[SD_NSLOT][2], empty_in[SD_NSLOT];
+    unsigned int ticket;
+    DynSlot in[SD_NSLOT];
+};
+static_assert(sizeof(StreamDynSmem) <= 227 * 1024, "fits the shared memory of an SM");
+#define SD_OFF(member) ((uint32_t)offsetof(StreamDynSmem, member))
+enum : uint32_t { TSF_DEM = 1u, TSF_LAND = 2u, TSF_OCEAN = 4u };   // TileDev::pad_ of a descriptor slot: which rasters the tile has
+
+template <bool FAST8>
+__global__ void __launch_bounds__(ST_THREADS, 1)
+dswx_fused_stream_dyn_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__restrict__ tmaps,
+                             const FusedTables *__restrict__ tables, const ItemDesc *__restrict__ items, int n_items,
+                             const __grid_constant__ DevParams P, const __grid_constant__ FastParams F) {
+    constexpr bool OPTIONAL_LAYERS = false, ALL_GRADED = true;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    StreamDynSmem &D = *reinterpret_cast<StreamDynSmem *>(smem_raw);
+    uint32_t db = (uint32_t)__cvta_generic_to_shared(&D);    // shared address of the block, kept in a register
+    asm volatile("mov.b32 %0, %0;" : "+r"(db));
+    // what the row body calls `sb`: the address FastSmem WOULD start at for its table offsets to land on D's tables
+    const uint32_t sb = db + SD_OFF(big_lut) - FS_OFF(big_lut);
+    FastSmem &s = *reinterpret_cast<FastSmem *>(smem_raw);    // never dereferenced (optional-layer code of the row body is compiled out)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    (void)ALL_GRADED; (void)s;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(tables);
+        uint4 *dst = reinterpret_cast<uint4 *>(D.big_lut);
+        static_assert(offsetof(StreamDynSmem, kill_lut) - offsetof(StreamDynSmem, big_lut) + 128 == sizeof(FusedTables), "table block mirrors FusedTables");
+        static_assert(offsetof(StreamDynSmem, big_lut) % 16 == 0, "16-byte table copies");
+        for (int i = tid; i < (int)(sizeof(FusedTables) / 16); i += ST_THREADS) dst[i] = __ldg(src + i);
+        if (tid == 0) {
+            mbar_init(&D.full[0], 1); mbar_init(&D.full[1], 1);
+            mbar_init(&D.empty[0], SD_H); mbar_init(&D.empty[1], SD_H);                 // one arrival per ROW of an item
+            for (int i = 0; i < SD_NSLOT; ++i) {
+                mbar_init(&D.full_in[i][0], 1); mbar_init(&D.full_in[i][1], 1);
+                mbar_init(&D.empty_in[i], SD_CH);                                       // one arrival per row of a chunk
+            }
+            D.ticket = 0u;
+        }
+    }
+    __syncthreads();
+    const int first = (int)blockIdx.x, step = (int)gridDim.x;
+    const uint32_t n_loc = first < n_items ? (uint32_t)((n_items - first + step - 1) / step) : 0u;
+
+    // =========================== producer warp ==================================
+    if (warp == ST_WARPS) {
+        if (lane != 0) return;
+        uint32_t acquired_tile = 0xffffffffu, slot_tile0 = 0xffffffffu, slot_tile1 = 0xffffffffu;
+#pragma unroll 1
+        for (uint32_t k = 0; k < n_loc; ++k) {
+            const ItemDesc d = items[first + (int)k * step];
+            const CUtensorMap *tm = tmaps + (size_t)d.tile * ST_MAPS;
+            if (d.tile != acquired_tile) {
+#pragma unroll 1
+                for (int j = 0; j < ST_MAPS; ++j) tma_acquire_map(&tm[j]);
+                acquired_tile = d.tile;
+            }
+            const uint32_t b = k & 1u;
+            if (k >= 2u) {
+                // item k - 2 (same descriptor slot, same DEM buffer): every row released, and its DEM transaction complete
+                // (a row without a water pixel never waits for the DEM tile itself)
+                ST_PRODUCER_WAIT(&D.empty[b], ((k >> 1) - 1u) & 1u);
+                mbar_wait(&D.full[b], ((k >> 1) - 1u) & 1u);
+            }
+            // ---- descriptor slot b <- the item's tile (unless item k - 2 left the same tile there: the usual case) ------
+            TileSlot *slot = &D.desc[b];
+            if ((b ? slot_tile1 : slot_tile0) != d.tile) {
+                if (b) slot_tile1 = d.tile; else slot_tile0 = d.tile;
+                const uint4 *src = reinterpret_cast<const uint4 *>(&tiles[d.tile]);
+                uint4 v[sizeof(TileDev) / 16];
+#pragma unroll
+                for (int i = 0; i < (int)(sizeof(TileDev) / 16); ++i) v[i] = __ldg(src + i);       // 11 loads in flight at once
+                uint4 *dst = reinterpret_cast<uint4 *>(&slot->tile);
+#pragma unroll
+                for (int i = 0; i < (int)(sizeof(TileDev) / 16); ++i) dst[i] = v[i];
+                slot->tile.pad_ = (slot->tile.dem != nullptr ? TSF_DEM : 0u) | (slot->tile.land != nullptr ? TSF_LAND : 0u) |
+                                  (slot->tile.ocean != nullptr ? TSF_OCEAN : 0u);
+                const double kx = 0.5 / (double)P.dxf, ky = 0.5 / (double)P.dyf;
+                const double sin_az = slot->tile.sin_az, cos_az = slot->tile.cos_az, sx = slot->tile.sx, sy = slot->tile.sy, sz = slot->tile.sz;
+                float *K = slot->sun32;
+                K[SK_SA] = (float)(kx * sin_az); K[SK_CA] = (float)(ky * cos_az);
+                K[SK_SX] = (float)(kx * sx); K[SK_SY] = (float)(ky * sy); K[SK_SZ] = (float)sz;
+                K[SK_XX] = (float)(kx * kx);
+                K[SK_EA] = 1e-6f * fabsf(K[SK_SA]); K[SK_EB] = 1e-6f * fabsf(K[SK_CA]);
+                if (FAST8) {
+                    // tiles whose sun vector breaks the preconditions of the sign-bit shortcut run the exact sequence
+                    const double hz = sx * sin_az + sy * cos_az, n2 = sx * sx + sy * sy + sz * sz;
+                    if (!(hz >= 0.0 && fabs(n2 - 1.0) < 1e-9 && fabs(sin_az * sin_az + cos_az * cos_az - 1.0) < 1e-9))
+                        K[SK_XX] = __int_as_float(0x7fffffff);
+                }
+            }
+            const uint32_t tsf = slot->tile.pad_;
+            const bool has_dem = (tsf & TSF_DEM) != 0u, has_land = (tsf & TSF_LAND) != 0u, has_ocean = (tsf & TSF_OCEAN) != 0u;
+            const int W = slot->tile.width;
+            slot->row_info = make_uint4((uint32_t)W, (uint32_t)slot->tile.height, (uint32_t)d.tx | ((uint32_t)d.ty << 16), tsf | (d.tile << 3));
+            const int x0 = d.tx * FT_W, row4 = d.ty * SD_CH;                        // item rows start at super-row ty * SD_CH
+            if (has_dem) {
+                const int dox = slot->tile.dem_off_x, doy = slot->tile.dem_off_y;
+                const int padx = DEM_PADX + (dox & 3);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&D.full[b], SD_DEM_BOX_BYTES);
+                tma_load_2d_acquired(&D.dem[b].v[0][0], &tm[SM_DEM], dox + x0 - padx, doy + d.ty * SD_H - 1, &D.full[b]);
+            } else {
+                mbar_arrive(&D.full[b]);
+            }
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                const uint32_t gen = k, sl = (uint32_t)c;                             // 4 chunks per item, 4 slots
+                if (gen >= 1u) ST_PRODUCER_WAIT(&D.empty_in[sl], (gen - 1u) & 1u);
+                // generic-proxy reads of the slot (ordered by the empty barrier) before the async-proxy writes
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                unsigned long long *bar = &D.full_in[sl][gen & 1u];
+                mbar_expect_tx(bar, 6u * SD_BAND_TX + SD_BYTE_TX * (1u + (has_land ? 1u : 0u) + (has_ocean ? 1u : 0u)));
+                const int xe = c * W + x0;                                          // column inside the 4-row super-row
+                DynSlot &in = D.in[sl];
+#pragma unroll
+                for (int bb = 0; bb < 6; ++bb) tma_load_2d_acquired(&in.band[bb][0], &tm[SM_BAND0 + bb], xe & ~7, row4, bar);
+                tma_load_2d_acquired(&in.byte[0][0], &tm[SM_FMASK], xe & ~15, row4, bar);
+                if (has_land) tma_load_2d_acquired(&in.byte[1][0], &tm[SM_LAND], xe & ~15, row4, bar);
+                if (has_ocean) tma_load_2d_acquired(&in.byte[2][0], &tm[SM_OCEAN], xe & ~15, row4, bar);
+            }
+        }
+        // no bulk copy may be in flight into this CTA's shared memory when it retires: the DEM tiles of the last two items
+        for (uint32_t k = n_loc >= 2u ? n_loc - 2u : 0u; k < n_loc; ++k) mbar_wait(&D.full[k & 1u], (k >> 1) & 1u);
+        return;
+    }
+
+    // =========================== consumer warps =================================
+    const uint32_t total_rows = n_loc * (uint32_t)SD_H;
+    uint32_t acc_vc = 0, acc_nno = 0;
+    unsigned long long acc_hist = 0ull;
+    constexpr bool histogram = false, has_counters = true, want_shad = false, all_graded = true;
+    uint32_t w[6][2], fm4 = 0u, ld4 = 0xffffffffu, oc4 = 0x01010101u;
+#pragma unroll
+    for (int kk = 0; kk < 6; ++kk) w[kk][0] = w[kk][1] = 0u;
+    auto take_ticket = [&]() {
+        uint32_t t = 0u;
+        if (lane == 0) t = atomicAdd(&D.ticket, 1u);
+        return __shfl_sync(0xffffffffu, t, 0);
+    };
+
+    // counters: per-thread registers, flushed (fire-and-forget reductions) when the rows of this warp move on to another
+    // tile, and at the end
+    uint32_t cur_tile = 0xffffffffu;
+    auto flush_counters = [&]() {
+        const uint32_t wv = __reduce_add_sync(0xffffffffu, acc_vc & 0xffffu);
+        const uint32_t wc = __reduce_add_sync(0xffffffffu, acc_vc >> 16);
+        const uint32_t wn = __reduce_add_sync(0xffffffffu, acc_nno);
+        if (lane == 0 && cur_tile != 0xffffffffu) {
+            unsigned long long *cnt = tiles[cur_tile].counters;
+            if (cnt != nullptr) {
+                asm volatile("red.global.add.u64 [%0], %1;" ::"l"(cnt), "l"((unsigned long long)wv) : "memory");
+                asm volatile("red.global.add.u64 [%0], %1;" ::"l"(cnt + 1), "l"((unsigned long long)wc) : "memory");
+                asm volatile("red.global.add.u64 [%0], %1;" ::"l"(cnt + 2), "l"((unsigned long long)wn) : "memory");
+            }
+        }
+        acc_vc = 0u; acc_nno = 0u;
+    };
+
+    uint32_t t = take_ticket();
+#pragma unroll 1
+    while (t < total_rows) {
+        // ticket -> row r of chunk q; item k = q / 4 (= generation of the ring slot), row class c = q % 4 (= ring slot)
+        const uint32_t q = t / (uint32_t)SD_CH, r = t & (uint32_t)(SD_CH - 1);
+        const uint32_t k = q >> 2, c = q & 3u, buf = k & 1u, slot = c;
+        mbar_wait_addr(db + SD_OFF(full_in) + 16u * slot + 8u * buf, (k >> 1) & 1u);
+        // the item's descriptor slot (written by the producer before it armed this chunk's barrier), addressed as the row
+        // body addresses FastSmem::tile / sun32
+        const uint32_t tb = db + SD_OFF(desc) + buf * (uint32_t)sizeof(TileSlot) - FS_OFF(tile);
+        uint4 info;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(info.x), "=r"(info.y), "=r"(info.z), "=r"(info.w)
+                     : "r"(tb + FS_OFF(tile) + (uint32_t)offsetof(TileSlot, row_info)));
+        const int W = (int)info.x, H = (int)info.y;
+        const bool has_dem = (info.w & TSF_DEM) != 0u, has_land = (info.w & TSF_LAND) != 0u, has_ocean = (info.w & TSF_OCEAN) != 0u;
+        if ((info.w >> 3) != cur_tile) {
+            flush_counters();                                 // the registers hold counts of the previous tile
+            cur_tile = info.w >> 3;
+        }
+        const int x0 = (int)(info.z & 0xffffu) * FT_W;
+        const int ly = 4 * (int)r + (int)c, y = (int)(info.z >> 16) * SD_H + ly, x = x0 + 4 * lane;
+        const bool active = y < H && x < W;
+        bool dem_ready = false;
+        if (active) {
+            const uint32_t xe = c * (uint32_t)W + (uint32_t)x0;
+            const uint32_t base = db + SD_OFF(in) + slot * (uint32_t)sizeof(DynSlot);
+            const uint32_t ab = base + r * (2u * ST_BAND_W) + 2u * (xe & 7u) + 8u * (uint32_t)lane;
+            const uint32_t ay = base + 6u * SD_BAND_BYTES + r * ST_BYTE_W + (xe & 15u) + 4u * (uint32_t)lane;
+#pragma unroll
+            for (int kk = 0; kk < 6; ++kk) {
+                uint32_t v0, v1;
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v0), "=r"(v1) : "r"(ab + (uint32_t)kk * SD_BAND_BYTES));
+                w[kk][0] = v0; w[kk][1] = v1;
+            }
+            fm4 = lds_u32(ay);
+            ld4 = has_land ? lds_u32(ay + SD_BYTE_BYTES) : 0xffffffffu;
+            oc4 = has_ocean ? lds_u32(ay + 2u * SD_BYTE_BYTES) : 0x01010101u;
+            // the row is IN REGISTERS (not merely requested) before the slot is handed back to the producer
+            asm volatile("" ::"r"(w[5][1]), "r"(fm4), "r"(ld4), "r"(oc4) : "memory");
+        }
+        __syncwarp();
+        mbar_arrive_elected(db + SD_OFF(empty_in) + 8u * slot);
+        if (active) {
+            const uint32_t pix = (uint32_t)y * (uint32_t)W + (uint32_t)x;
+#define FT_DEM_WAIT() mbar_wait_addr(db + SD_OFF(full) + 8u * buf, (k >> 1) & 1u)
+#define FT_ROW_MIDPOINT() do { } while (0)
+#define FT_PADX() (DEM_PADX + (int)(lds_u32(tb + FS_TILE(dem_off_x)) & 3u))
+#define FT_TB tb
+#define FT_DEM_BASE (db + SD_OFF(dem) + buf * (uint32_t)sizeof(DynDem))
+#include "pb200_fused_row.inc"
+#undef FT_DEM_BASE
+#undef FT_TB
+#undef FT_PADX
+#undef FT_ROW_MIDPOINT
+#undef FT_DEM_WAIT
+        }
+        const uint32_t t_next = take_ticket();
+        __syncwarp();
+        mbar_arrive_elected(db + SD_OFF(empty) + 8u * buf);
+        t = t_next;
+    }
+    flush_counters();
+    (void)acc_hist;
 }
 
 }  // namespace pb200
