@@ -522,8 +522,9 @@ dswx_fused_stream_dyn_kernel(const TileDev *__restrict__ tiles, const CUtensorMa
 #pragma unroll
     for (int kk = 0; kk < 6; ++kk) w[kk][0] = w[kk][1] = 0u;
     auto take_ticket = [&]() {
+        // (plain PTX: atomicAdd() on a shared counter compiles to a warp-aggregation sequence of ~15 instructions)
         uint32_t t = 0u;
-        if (lane == 0) t = atomicAdd(&D.ticket, 1u);
+        if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(t) : "r"(db + SD_OFF(ticket)) : "memory");
         return __shfl_sync(0xffffffffu, t, 0);
     };
 
