@@ -163,6 +163,7 @@ int  pb200_plan_run(pb200_plan *plan, void *stream);
 #define PB200_KERNEL_STREAM  2
 #define PB200_KERNEL_FAST8   4
 #define PB200_KERNEL_GENERIC 8
+#define PB200_KERNEL_STREAM_DYN 16   /* with PB200_KERNEL_STREAM: dswx_fused_stream_dyn_kernel (rows handed to free warps, deep ring) */
 int  pb200_plan_kernels(const pb200_plan *plan, int *mask);
 int  pb200_plan_destroy(pb200_plan *plan);
 /* Same contract as pb200_classify for ONE tile whose pointers are HOST

@@ -18,7 +18,7 @@ N_COUNTERS = 12
 E_INVALID_ARG, E_BAD_MODE, E_UNSUPPORTED, E_NO_DRIVER_API, E_ALIGNMENT, E_NCCL = -1, -2, -3, -4, -5, -6
 COMM_ID_BYTES = 128
 HOST_REUSE_ANCILLARY, HOST_ASYNC, HOST_SLOT1 = 1, 2, 4
-KERNEL_FAST, KERNEL_STREAM, KERNEL_FAST8, KERNEL_GENERIC = 1, 2, 4, 8
+KERNEL_FAST, KERNEL_STREAM, KERNEL_FAST8, KERNEL_GENERIC, KERNEL_STREAM_DYN = 1, 2, 4, 8, 16
 
 EXPORTS = (
     'pb200_version', 'pb200_last_error', 'pb200_ctx_create', 'pb200_ctx_destroy',

@@ -1048,6 +1048,7 @@ extern "C" int pb200_plan_kernels(const pb200_plan *plan, int *mask) {
     if (!plan || !mask) return fail(PB200_E_INVALID_ARG, "pb200_plan_kernels: null argument");
     int m = 0;
     if (plan->n[G_FAST]) m |= plan->stream ? 2 : 1;
+    if (plan->n[G_FAST] && plan->stream_dyn) m |= 16;
     if (plan->n[G_FAST] && plan->F.fast8 != 0u && !plan->no_fast8) m |= 4;
     if (plan->n[G_VEC] || plan->n[G_GENERIC]) m |= 8;
     *mask = m;

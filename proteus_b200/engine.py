@@ -297,7 +297,8 @@ class Plan:
         m = self.kernels
         names = []
         if m & _lib.KERNEL_STREAM:
-            names.append(f'pb200::dswx_fused_stream_kernel<{"true" if m & _lib.KERNEL_FAST8 else "false"}>')
+            kern = 'dswx_fused_stream_dyn_kernel' if m & _lib.KERNEL_STREAM_DYN else 'dswx_fused_stream_kernel'
+            names.append(f'pb200::{kern}<{"true" if m & _lib.KERNEL_FAST8 else "false"}>')
         if m & _lib.KERNEL_FAST:
             names.append('pb200::dswx_fused_fast_kernel' + ('<FAST8>' if m & _lib.KERNEL_FAST8 else ''))
         if m & _lib.KERNEL_GENERIC:

@@ -644,7 +644,8 @@ def test_batch_of_mixed_tiles_through_the_item_pipeline(pb):
 
 def test_tma_fed_stream_kernel_matches_oracle(pb):
     """The product configuration (four graded layers + counters) on tiles whose planes TMA can address as 4-row
-    super-rows runs dswx_fused_stream_kernel (producer warp + shared-memory ring): tiles smaller than an item, ragged
+    super-rows runs dswx_fused_stream_dyn_kernel (producer warp + shared-memory ring + row tickets; the static
+    dswx_fused_stream_kernel with PB200_STREAM_DYNAMIC=0): tiles smaller than an item, ragged
     right / bottom edges, with and without DEM / LAND / ocean, adversarial data, several tiles per launch (a CTA changes
     tile between items), two launches of the same plan - against the oracle; and the same batch through the
     direct-load kernel (PB200_NO_STREAM) gives the same bits."""
@@ -677,16 +678,23 @@ def test_tma_fed_stream_kernel_matches_oracle(pb):
                                                 t['sun_azimuth'], t['sun_elevation'], **kw))
         else:
             refs_p = refs
-        plan = pb.Plan(tiles, params, pb.GRADED_LAYERS)
-        assert plan.kernels & _lib.KERNEL_STREAM, 'the batch should qualify for the TMA-fed kernel'
-        assert bool(plan.kernels & _lib.KERNEL_FAST8) == what.startswith('defaults')
-        for launch in range(2):
-            plan.zero_counters()
-            plan.run()
-            for i, ref in enumerate(refs_p):
-                res = plan.results(i)
-                _assert_layers(res, ref, ('DIAG', 'WTR', 'BWTR', 'CONF'), f'{what}: tile {i} launch {launch}')
-                assert np.array_equal(res['counters'][:3], ref['counters']), (what, i, launch)
+        # both TMA-fed kernels: rows handed to free warps (default), and row w of every chunk to warp w
+        for dyn in (True, False):
+            os.environ['PB200_STREAM_DYNAMIC'] = '1' if dyn else '0'
+            try:
+                plan = pb.Plan(tiles, params, pb.GRADED_LAYERS)
+            finally:
+                del os.environ['PB200_STREAM_DYNAMIC']
+            assert plan.kernels & _lib.KERNEL_STREAM, 'the batch should qualify for the TMA-fed kernel'
+            assert bool(plan.kernels & _lib.KERNEL_STREAM_DYN) == dyn and ('stream_dyn' in plan.kernel_name) == dyn
+            assert bool(plan.kernels & _lib.KERNEL_FAST8) == what.startswith('defaults')
+            for launch in range(2):
+                plan.zero_counters()
+                plan.run()
+                for i, ref in enumerate(refs_p):
+                    res = plan.results(i)
+                    _assert_layers(res, ref, ('DIAG', 'WTR', 'BWTR', 'CONF'), f'{what}: dyn {dyn} tile {i} launch {launch}')
+                    assert np.array_equal(res['counters'][:3], ref['counters']), (what, dyn, i, launch)
         os.environ['PB200_NO_STREAM'] = '1'
         try:
             direct = pb.Plan(tiles, params, pb.GRADED_LAYERS)
