@@ -792,11 +792,14 @@ static int plan_build(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles, cons
         pl->max_ctas[g] = std::max(pl->max_ctas[g], d.n_ctas);
     }
     // TMA-fed variant: lean product configuration only (all four graded layers + counters on every fast tile)
-    pl->stream = stream_ok && pl->n_fast_seen > 0 && !pl->fast_optional && pl->fast_all_graded;
     {
-        // rows handed to whichever warp is free, deep ring (default), or row w of every chunk to warp w (PB200_STREAM_DYNAMIC=0)
+        // the lean product configuration (graded layers + counters on every fast tile): rows handed to whichever warp is
+        // free, deep ring (default; any subset of the graded layers), or row w of every chunk to warp w
+        // (PB200_STREAM_DYNAMIC=0; all four graded layers only)
+        const bool eligible = stream_ok && pl->n_fast_seen > 0 && !pl->fast_optional;
         const char *e = std::getenv("PB200_STREAM_DYNAMIC");
-        pl->stream_dyn = pl->stream && !(e && e[0] == '0');
+        pl->stream_dyn = eligible && !(e && e[0] == '0');
+        pl->stream = pl->stream_dyn || (eligible && pl->fast_all_graded);
     }
     // items and DEM boxes of the fast tiles, in the geometry of the kernel that will run them
     {
@@ -911,8 +914,10 @@ static int fast_kernel_setup(pb200_ctx *ctx) {
     }
     CK(cudaFuncSetAttribute(dswx_fused_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamSmem)));
     CK(cudaFuncSetAttribute(dswx_fused_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamSmem)));
-    CK(cudaFuncSetAttribute(dswx_fused_stream_dyn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamDynSmem)));
-    CK(cudaFuncSetAttribute(dswx_fused_stream_dyn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamDynSmem)));
+    CK(cudaFuncSetAttribute(dswx_fused_stream_dyn_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamDynSmem)));
+    CK(cudaFuncSetAttribute(dswx_fused_stream_dyn_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamDynSmem)));
+    CK(cudaFuncSetAttribute(dswx_fused_stream_dyn_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamDynSmem)));
+    CK(cudaFuncSetAttribute(dswx_fused_stream_dyn_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamDynSmem)));
     int nb = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dswx_fused_fast_kernel<false>, FtGeom<false>::THREADS, FAST_DYN_SMEM));
     ctx->fast_ctas_per_sm = nb > 0 ? nb : 1;
@@ -930,12 +935,12 @@ static void launch_fast(pb200_plan *pl, const ItemDesc *it, int n, cudaStream_t 
     if (pl->stream) {
         const int g1 = std::min(n, ctx->sm_count);            // 219 KB of shared memory: one CTA per SM
         if (pl->stream_dyn) {
-            if (f8)
-                dswx_fused_stream_dyn_kernel<true><<<g1, ST_THREADS, sizeof(StreamDynSmem), stream>>>(
-                    pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, it, n, pl->P, pl->F);
-            else
-                dswx_fused_stream_dyn_kernel<false><<<g1, ST_THREADS, sizeof(StreamDynSmem), stream>>>(
-                    pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, it, n, pl->P, pl->F);
+#define PB200_LAUNCH_DYN(F8, GRADED)                                                                       \
+    dswx_fused_stream_dyn_kernel<F8, GRADED><<<g1, ST_THREADS, sizeof(StreamDynSmem), stream>>>(           \
+        pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, it, n, pl->P, pl->F)
+            if (pl->fast_all_graded) { if (f8) PB200_LAUNCH_DYN(true, true); else PB200_LAUNCH_DYN(false, true); }
+            else { if (f8) PB200_LAUNCH_DYN(true, false); else PB200_LAUNCH_DYN(false, false); }
+#undef PB200_LAUNCH_DYN
             return;
         }
         if (f8)

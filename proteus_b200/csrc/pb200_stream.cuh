@@ -395,12 +395,14 @@ static_assert(sizeof(StreamDynSmem) <= 227 * 1024, "fits the shared memory of an
 #define SD_OFF(member) ((uint32_t)offsetof(StreamDynSmem, member))
 enum : uint32_t { TSF_DEM = 1u, TSF_LAND = 2u, TSF_OCEAN = 4u };   // TileDev::pad_ of a descriptor slot: which rasters the tile has
 
-template <bool FAST8>
+// ALL_GRADED: every tile of the batch writes all four graded layers (no pointer tests in the row loop); without it any
+// subset of them (BASELINE configs[0]: DIAG + WTR of tiles without DEM / LAND / ocean).
+template <bool FAST8, bool ALL_GRADED = true>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 dswx_fused_stream_dyn_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__restrict__ tmaps,
                              const FusedTables *__restrict__ tables, const ItemDesc *__restrict__ items, int n_items,
                              const __grid_constant__ DevParams P, const __grid_constant__ FastParams F) {
-    constexpr bool OPTIONAL_LAYERS = false, ALL_GRADED = true;
+    constexpr bool OPTIONAL_LAYERS = false;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     StreamDynSmem &D = *reinterpret_cast<StreamDynSmem *>(smem_raw);
     uint32_t db = (uint32_t)__cvta_generic_to_shared(&D);    // shared address of the block, kept in a register
@@ -409,7 +411,7 @@ dswx_fused_stream_dyn_kernel(const TileDev *__restrict__ tiles, const CUtensorMa
     const uint32_t sb = db + SD_OFF(big_lut) - FS_OFF(big_lut);
     FastSmem &s = *reinterpret_cast<FastSmem *>(smem_raw);    // never dereferenced (optional-layer code of the row body is compiled out)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    (void)ALL_GRADED; (void)s;
+    (void)s;
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(tables);
         uint4 *dst = reinterpret_cast<uint4 *>(D.big_lut);
@@ -517,7 +519,7 @@ dswx_fused_stream_dyn_kernel(const TileDev *__restrict__ tiles, const CUtensorMa
     const uint32_t total_rows = n_loc * (uint32_t)SD_H;
     uint32_t acc_vc = 0, acc_nno = 0;
     unsigned long long acc_hist = 0ull;
-    constexpr bool histogram = false, has_counters = true, want_shad = false, all_graded = true;
+    constexpr bool histogram = false, has_counters = true, want_shad = false, all_graded = ALL_GRADED;
     uint32_t w[6][2], fm4 = 0u, ld4 = 0xffffffffu, oc4 = 0x01010101u;
 #pragma unroll
     for (int kk = 0; kk < 6; ++kk) w[kk][0] = w[kk][1] = 0u;

@@ -1,5 +1,5 @@
 cd /root/repo
-timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "stream or mixed or fixture or seeded or guard_band or full_size" 2>&1 | tail -3
-for i in 1 2; do
-bash scripts/ab_env.sh "dyn:PB200_STREAM_DYNAMIC=1" "static:PB200_STREAM_DYNAMIC=0"
-done
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-e2e --sustained-s 0 2>gpurun_out/tmp_bench.err | python -c "
+import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); a=d['adversarial_worst_case']; print('value', round(d['value']/1e3,1), 'adversarial', round(a['value']/1e3,1), 'config0', round(d['config0_l30']['value']/1e3,1), d['config0_l30'].get('roofline_frac_this_rank'), 'mosaic', round(d['mosaic']['value']/1e3,1))"
+tail -3 gpurun_out/tmp_bench.err
