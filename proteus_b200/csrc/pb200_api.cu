@@ -1824,6 +1824,7 @@ extern "C" int pb200_landcover_aggregate(pb200_ctx *ctx, const uint8_t *worldcov
         if (forest[v]) L.forest_bits[v >> 5] |= 1u << (v & 31);
     const bool vec = (cols % 4) == 0 && aligned(worldcover, 4) && aligned(copernicus, 4) && aligned(land, 4);
     dim3 block(32, 8), grid(((cols + 3) / 4 + 31) / 32, (rows + 7) / 8);
+    grid.y = (unsigned)std::max(1, std::min((int)grid.y, (ctx->sm_count * 8 + (int)grid.x - 1) / (int)grid.x));
     if (vec) landcover_aggregate_kernel<true><<<grid, block, 0, st>>>(worldcover, copernicus, land, rows, cols, L);
     else landcover_aggregate_kernel<false><<<grid, block, 0, st>>>(worldcover, copernicus, land, rows, cols, L);
     LEAVE();

@@ -44,9 +44,11 @@ __global__ void landcover_aggregate_kernel(const uint8_t *__restrict__ worldcove
     for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < 256; i += blockDim.x * blockDim.y) code[i] = worldcover_code(i);
     __syncthreads();
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x4 >= cols || y >= rows) return;
+    if (x4 >= cols) return;
     const size_t wpitch = (size_t)cols * 3;
+    // a CTA walks down the raster (grid.y is sized for ~8 CTAs per SM): the class-code table is built once per CTA, not
+    // once per 1024 pixels (that was 30 % of the executed instructions, profiles/)
+    for (int y = blockIdx.y * blockDim.y + threadIdx.y; y < rows; y += gridDim.y * blockDim.y) {
     uint32_t counts[4] = {0u, 0u, 0u, 0u};
     if (VEC) {
         // cols % 4 == 0 and 4-byte aligned planes: 12 bytes per 10 m row = 3 aligned words
@@ -74,6 +76,7 @@ __global__ void landcover_aggregate_kernel(const uint8_t *__restrict__ worldcove
             }
             land[(size_t)y * cols + x4 + j] = (uint8_t)land_class(cnt, copernicus[(size_t)y * cols + x4 + j], L);
         }
+    }
     }
 }
 

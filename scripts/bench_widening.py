@@ -41,7 +41,17 @@ land = torch.empty((S, S), dtype=torch.uint8, device='cuda')
 table = (C.c_uint8 * 256)(*[1 if v in (111, 113, 115, 116, 121, 123, 125, 126) else 0 for v in range(256)])
 th = (C.c_int32 * 4)(6, 3, 7, 3)
 report('landcover_aggregate', timed(lambda: _lib.check(lib.pb200_landcover_aggregate(
-    ctx.handle, wc.data_ptr(), cop.data_ptr(), S, S, table, 21, th, land.data_ptr(), sp))), 9 * n + n + n)
+    ctx.handle, wc.data_ptr(), cop.data_ptr(), S, S, table, 21, th, land.data_ptr(), sp))), 9 * n + n + n,
+       'uniform random bytes: worst case for the class-code table in shared memory (bank conflicts)')
+# WorldCover as it is: the 11 ESA classes in patches (64 x 64 samples) with 10 % salt noise
+esa = torch.tensor([10, 20, 30, 40, 50, 60, 70, 80, 90, 95, 100], dtype=torch.uint8, device='cuda')
+coarse = torch.randint(0, 11, ((3 * S + 63) // 64, (3 * S + 63) // 64), device='cuda', generator=g)
+wc2 = esa[coarse.repeat_interleave(64, 0).repeat_interleave(64, 1)[:3 * S, :3 * S]].contiguous()
+salt = torch.rand((3 * S, 3 * S), device='cuda', generator=g) < 0.1
+wc2[salt] = esa[torch.randint(0, 11, (int(salt.sum()),), device='cuda', generator=g)]
+report('landcover_aggregate, patchy WorldCover classes', timed(lambda: _lib.check(lib.pb200_landcover_aggregate(
+    ctx.handle, wc2.data_ptr(), cop.data_ptr(), S, S, table, 21, th, land.data_ptr(), sp))), 9 * n + n + n,
+       'the 11 ESA classes in 64 x 64 patches + 10 % salt noise')
 
 # byte table (browse relabel), scale/offset, histogram, compare
 w8 = torch.randint(0, 5, (S, S), dtype=torch.uint8, device='cuda', generator=g); o8 = torch.empty_like(w8)
