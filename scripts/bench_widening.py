@@ -69,6 +69,14 @@ report('histogram_u8 (otsu), smooth raster', timed(lambda: _lib.check(lib.pb200_
 mask = torch.empty_like(hill)
 report('greater_than_u8 (otsu)', timed(lambda: _lib.check(lib.pb200_greater_than_u8(ctx.handle, hill.data_ptr(), hill.numel(), 127.5, mask.data_ptr(), sp))), 2 * hill.numel())
 
+# Horn hillshade of the 'otsu' algorithm fused with the 256-bin count (read the DEM once, write the bytes)
+dem = (torch.rand((S + 100, S + 100), device='cuda', generator=g) * 300.0).to(torch.float32)
+dem = torch.nn.functional.avg_pool2d(dem[None, None], 9, 1, 4)[0, 0].contiguous()
+hs = torch.empty(dem.shape, dtype=torch.uint8, device='cuda'); cnt2 = torch.zeros(256, dtype=torch.int64, device='cuda')
+report('hillshade + histogram (otsu)', timed(lambda: _lib.check(lib.pb200_hillshade(
+    ctx.handle, dem.data_ptr(), dem.shape[0], dem.shape[1], 150.0, 45.0, 30.0, -30.0, hs.data_ptr(), cnt2.data_ptr(), sp))),
+       5 * dem.numel(), 'float32 DEM in, Byte hillshade out, counts in the same pass')
+
 # float32 diagnostic tests
 fb = [torch.rand((S, S), device='cuda', generator=g) for _ in range(6)]; d16 = torch.empty((S, S), dtype=torch.int16, device='cuda')
 ptrs = (C.c_void_p * 6)(*[t.data_ptr() for t in fb]); thr = pb.make_params().th
