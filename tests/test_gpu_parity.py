@@ -708,6 +708,34 @@ def test_tma_fed_stream_kernel_matches_oracle(pb):
                 assert np.array_equal(a[name], b[name]), (what, i, name)
 
 
+def test_dynamic_row_kernel_on_many_small_tiles(pb):
+    """dswx_fused_stream_dyn_kernel hands rows to whichever warp is free and keeps two tile descriptors in flight: a
+    batch of 240 small tiles of random shapes (1 - 6 items each, so that a CTA meets a new tile with nearly every item;
+    tiles with and without DEM / LAND / ocean interleaved) against the oracle, every layer and every counter, twice."""
+    import torch
+    from proteus_b200 import _lib
+    rng = np.random.default_rng(77)
+    tiles, refs = [], []
+    for i in range(240):
+        h, w = 4 * int(rng.integers(1, 40)), 4 * int(rng.integers(9, 80))
+        kw = dict(with_dem=bool(rng.random() < 0.8), with_land=bool(rng.random() < 0.7), with_ocean=bool(rng.random() < 0.6),
+                  adversarial=bool(rng.random() < 0.2))
+        t = synth.make_tile(2000 + i, h, w, **kw)
+        refs.append(O.reference_chain(t['bands'], t['fmask'], t['dem'], t['land'], t['ocean'], t['sun_azimuth'], t['sun_elevation']))
+        dev = {k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) else v) for k, v in t.items() if k != 'bands'}
+        dev['bands'] = [torch.from_numpy(b).cuda() for b in t['bands']]
+        tiles.append(dev)
+    plan = pb.Plan(tiles, pb.make_params(collapse_wtr_classes=False), pb.GRADED_LAYERS)
+    assert plan.kernels & _lib.KERNEL_STREAM_DYN
+    for launch in range(2):
+        plan.zero_counters()
+        plan.run()
+        for i, ref in enumerate(refs):
+            res = plan.results(i)
+            _assert_layers(res, ref, ('DIAG', 'WTR', 'BWTR', 'CONF'), f'tile {i} launch {launch}')
+            assert np.array_equal(res['counters'][:3], ref['counters']), (i, launch)
+
+
 def test_otsu_threshold_dropin(pb):
     """SURVEY 8f next #3: _compute_otsu_threshold on uint8 hillshades (GPU histogram + compare, host threshold)."""
     import proteus_b200.dswx_hls as G
