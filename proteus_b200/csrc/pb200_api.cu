@@ -567,6 +567,7 @@ struct pb200_plan {
     FusedTables *d_tables = nullptr;                 // G_FAST only
     bool owns_tables = false;
     ItemDesc *d_items = nullptr;
+    TileSlot *d_slots = nullptr;                     // stream_dyn: one record per fast tile (descriptor + sun constants + row info)
     int n_items = 0;
     bool fast_optional = false;                      // some fast tile wants WTR-1 / WTR-2 / CLOUD / SHAD
     bool fast_all_graded = true;                     // every fast tile writes DIAG, WTR, BWTR and CONF
@@ -878,8 +879,41 @@ static int plan_build(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles, cons
     }
     if (pl->n[G_FAST]) {
         pl->n_items = (int)items.size();
+        // (one spare element: the dynamic kernel copies the aligned 16 bytes around an item)
+        items.push_back(ItemDesc{0u, 0, 0});
         CK(dev_alloc((void **)&pl->d_items, items.size() * sizeof(ItemDesc)));
         CK(cudaMemcpyAsync(pl->d_items, items.data(), items.size() * sizeof(ItemDesc), cudaMemcpyHostToDevice, stream));
+        if (pl->stream_dyn) {
+            // per-tile records of dswx_fused_stream_dyn_kernel: descriptor, float32 sun constants of the shadow shortcut
+            // (the arithmetic of the other fast kernels' per-tile prologue, done once here), first-look vector of a row
+            std::vector<TileSlot> slots(td[G_FAST].size());
+            const bool f8 = pl->F.fast8 != 0u && !pl->no_fast8;
+            for (size_t i = 0; i < slots.size(); ++i) {
+                TileSlot &sl = slots[i];
+                std::memset(&sl, 0, sizeof(sl));
+                sl.tile = td[G_FAST][i];
+                const TileDev &g = sl.tile;
+                const uint32_t tsf = (g.dem ? TSF_DEM : 0u) | (g.land ? TSF_LAND : 0u) | (g.ocean ? TSF_OCEAN : 0u);
+                sl.tile.pad_ = tsf;
+                const double kx = 0.5 / (double)pl->P.dxf, ky = 0.5 / (double)pl->P.dyf;
+                float *K = sl.sun32;
+                K[SK_SA] = (float)(kx * g.sin_az); K[SK_CA] = (float)(ky * g.cos_az);
+                K[SK_SX] = (float)(kx * g.sx); K[SK_SY] = (float)(ky * g.sy); K[SK_SZ] = (float)g.sz;
+                K[SK_XX] = (float)(kx * kx);
+                K[SK_EA] = 1e-6f * std::fabs(K[SK_SA]); K[SK_EB] = 1e-6f * std::fabs(K[SK_CA]);
+                if (f8) {
+                    // tiles whose sun vector breaks the preconditions of the sign-bit shortcut run the exact sequence
+                    const double hz = g.sx * g.sin_az + g.sy * g.cos_az, n2 = g.sx * g.sx + g.sy * g.sy + g.sz * g.sz;
+                    if (!(hz >= 0.0 && std::fabs(n2 - 1.0) < 1e-9 && std::fabs(g.sin_az * g.sin_az + g.cos_az * g.cos_az - 1.0) < 1e-9)) {
+                        const uint32_t nanbits = 0x7fffffffu;
+                        std::memcpy(&K[SK_XX], &nanbits, 4);
+                    }
+                }
+                sl.row_info = make_uint4((uint32_t)g.width, (uint32_t)g.height, 0u, tsf | ((uint32_t)i << 3));
+            }
+            CK(dev_alloc((void **)&pl->d_slots, slots.size() * sizeof(TileSlot)));
+            CK(cudaMemcpyAsync(pl->d_slots, slots.data(), slots.size() * sizeof(TileSlot), cudaMemcpyHostToDevice, stream));
+        }
         if (shared_tables) {
             pl->d_tables = shared_tables;
         } else {
@@ -937,7 +971,7 @@ static void launch_fast(pb200_plan *pl, const ItemDesc *it, int n, cudaStream_t 
         if (pl->stream_dyn) {
 #define PB200_LAUNCH_DYN(F8, GRADED)                                                                       \
     dswx_fused_stream_dyn_kernel<F8, GRADED><<<g1, ST_THREADS, sizeof(StreamDynSmem), stream>>>(           \
-        pl->d_tiles[G_FAST], pl->d_maps[G_FAST], pl->d_tables, it, n, pl->P, pl->F)
+        pl->d_slots, pl->d_maps[G_FAST], pl->d_tables, it, n, pl->P, pl->F)
             if (pl->fast_all_graded) { if (f8) PB200_LAUNCH_DYN(true, true); else PB200_LAUNCH_DYN(false, true); }
             else { if (f8) PB200_LAUNCH_DYN(true, false); else PB200_LAUNCH_DYN(false, false); }
 #undef PB200_LAUNCH_DYN
@@ -1009,6 +1043,8 @@ static void plan_release(pb200_plan *pl, cudaStream_t stream) {
     }
     dev_free(pl->d_items);
     pl->d_items = nullptr;
+    dev_free(pl->d_slots);
+    pl->d_slots = nullptr;
     if (pl->owns_tables) dev_free(pl->d_tables);
     pl->d_tables = nullptr;
 }
@@ -1300,7 +1336,7 @@ extern "C" int pb200_classify_host_ex(pb200_ctx *ctx, const pb200_tile *ht, cons
     // worst case per strip: descriptor + tensor map + one item per FT_W x FT_H pixels
     {
         const size_t items_max = (size_t)((W + FT_W - 1) / FT_W) * (size_t)((H + SD_H - 1) / SD_H + n_strips);
-        const size_t need = (size_t)n_strips * (sizeof(TileDev) + ST_MAPS * sizeof(CUtensorMap) + 1024) +
+        const size_t need = (size_t)n_strips * (sizeof(TileDev) + sizeof(TileSlot) + ST_MAPS * sizeof(CUtensorMap) + 1024) +
                             items_max * sizeof(ItemDesc) + 8192;
         if (need > p.arena.cap) {
             CKP(cudaStreamSynchronize(p.s_k));

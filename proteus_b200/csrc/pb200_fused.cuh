@@ -293,6 +293,9 @@ __device__ __forceinline__ T *lds_ptr(uint32_t a) {
     unsigned long long v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a)); return reinterpret_cast<T *>(v);
 }
 #define FS_OFF(member) ((uint32_t)offsetof(FastSmem, member))
+// hooks of pb200_fused_row.inc for a tile descriptor + sun constants in shared memory at FastSmem's offsets from `tb`
+#define FT_OUT_PTR_SHARED(tb, type, member) lds_ptr<type>((tb) + FS_TILE(member))
+#define FT_SUN4_SHARED(tb, i) lds_f32x4((tb) + FS_OFF(sun32) + 16u * (i))
 #define FS_TILE(member) ((uint32_t)(offsetof(FastSmem, tile) + offsetof(TileDev, member)))
 
 // address of element `pix` of a plane: one IMAD.WIDE (FMA pipe) instead of a 64-bit add pair on the ALU pipe
@@ -388,16 +391,9 @@ __device__ __noinline__ uint32_t shadow_exact(float l, float r, float u, float d
 // body), the sun terms from the tile descriptor at `sb`.  Nothing but `am`, `sb` and the result crosses the call - the row
 // loop's registers stay out of the rare path (a 4 x 6-argument call sequence cost 20-40 bytes of spills IN the loop and,
 // with a larger callee, 6 % of the throughput, profiles/).  Bit j of the result: pixel j is in shadow.
-__device__ __noinline__ uint32_t shadow_exact4(uint32_t am, uint32_t sb, const DevParams &P) {
+// bits of the four pixels from the DEM window at `am` with the given sun terms
+__device__ __forceinline__ uint32_t shadow_exact4_bits(uint32_t am, const SunTerms &S, const DevParams &P) {
     constexpr uint32_t RB = 4u * FT_SMW;
-    SunTerms S;
-    {
-        const uint32_t at = sb + (uint32_t)(offsetof(FastSmem, tile) + offsetof(TileDev, sx));
-        double v[5];
-#pragma unroll
-        for (int i = 0; i < 5; ++i) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v[i]) : "r"(at + 8u * (uint32_t)i));
-        S.sx = v[0]; S.sy = v[1]; S.sz = v[2]; S.sin_az = v[3]; S.cos_az = v[4];
-    }
     uint32_t bits = 0u;
 #pragma unroll 1
     for (int j = 0; j < 4; ++j) {
@@ -406,6 +402,23 @@ __device__ __noinline__ uint32_t shadow_exact4(uint32_t am, uint32_t sb, const D
         bits |= (shadow_exact1(l, r, u, d, P, S) ? 1u : 0u) << j;
     }
     return bits;
+}
+// the same with the tile descriptor in GLOBAL memory (dswx_fused_stream_dyn_kernel)
+__device__ __noinline__ uint32_t shadow_exact4_global(uint32_t am, const TileDev *g, const DevParams &P) {
+    SunTerms S;
+    S.sx = __ldg(&g->sx); S.sy = __ldg(&g->sy); S.sz = __ldg(&g->sz); S.sin_az = __ldg(&g->sin_az); S.cos_az = __ldg(&g->cos_az);
+    return shadow_exact4_bits(am, S, P);
+}
+__device__ __noinline__ uint32_t shadow_exact4(uint32_t am, uint32_t sb, const DevParams &P) {
+    SunTerms S;
+    {
+        const uint32_t at = sb + (uint32_t)(offsetof(FastSmem, tile) + offsetof(TileDev, sx));
+        double v[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v[i]) : "r"(at + 8u * (uint32_t)i));
+        S.sx = v[0]; S.sy = v[1]; S.sz = v[2]; S.sin_az = v[3]; S.cos_az = v[4];
+    }
+    return shadow_exact4_bits(am, S, P);
 }
 
 // ---------------------------------------------------------------------------
@@ -610,11 +623,15 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                 } \
                 } while (0)
 #define FT_PADX() padx
-#define FT_TB sb
+#define FT_OUT_PTR(type, member) FT_OUT_PTR_SHARED(sb, type, member)
+#define FT_SUN4(i) FT_SUN4_SHARED(sb, i)
+#define FT_EXACT4(am) shadow_exact4(am, sb, P)
 #define FT_DEM_BASE (sb + FS_OFF(dem) + buf * (uint32_t)sizeof(DemHalf))
 #include "pb200_fused_row.inc"
 #undef FT_DEM_BASE
-#undef FT_TB
+#undef FT_EXACT4
+#undef FT_SUN4
+#undef FT_OUT_PTR
 #undef FT_PADX
 #undef FT_ROW_MIDPOINT
 #undef FT_DEM_WAIT

@@ -311,11 +311,15 @@ dswx_fused_stream_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *_
 #define FT_ROW_MIDPOINT() do { } while (0)
 // re-read from the tile descriptor where the shadow block needs it: no register (or spill slot) held across the rows
 #define FT_PADX() (DEM_PADX + (int)(lds_u32(sb + FS_TILE(dem_off_x)) & 3u))
-#define FT_TB sb
+#define FT_OUT_PTR(type, member) FT_OUT_PTR_SHARED(sb, type, member)
+#define FT_SUN4(i) FT_SUN4_SHARED(sb, i)
+#define FT_EXACT4(am) shadow_exact4(am, sb, P)
 #define FT_DEM_BASE (sb + FS_OFF(dem) + buf * (uint32_t)sizeof(DemHalf))
 #include "pb200_fused_row.inc"
 #undef FT_DEM_BASE
-#undef FT_TB
+#undef FT_EXACT4
+#undef FT_SUN4
+#undef FT_OUT_PTR
 #undef FT_PADX
 #undef FT_ROW_MIDPOINT
 #undef FT_DEM_WAIT
@@ -349,15 +353,15 @@ dswx_fused_stream_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *_
 //  * every slot has TWO full barriers used by alternate generations (= items): a warp that waits for generation k waits
 //    on a barrier whose previous user was generation k - 2, complete long ago - the parity test cannot alias however far
 //    the warps drift apart (8 chunks would need 128 outstanding tickets; there are 23 warps);
-//  * everything a row needs to know about its item is ONE 16-byte shared-memory vector the producer writes with the
-//    descriptor: width, height, item position, which rasters exist, tile index - no global load in the row loop;
-//  * nothing ties a warp to a tile: the producer writes the tile descriptor and the sun constants of item k into
-//    descriptor slot k & 1 (plain shared-memory stores, released by the barrier arrivals that follow them) when it
-//    requests the item; at most the items k and k + 1 are in flight, because the producer requests item k + 2 only after
-//    all 48 rows of item k have been released (empty[k & 1], one arrival PER ROW, after the row's last look at the DEM
-//    tile and the descriptor) and after it has itself seen item k's DEM transaction complete;
-//  * the coverage counters stay in per-thread registers and are flushed when a warp's next ticket belongs to another
-//    item - BEFORE the warp releases its last row of the old item, i.e. while that item's descriptor is still valid.
+//  * the first look of a row at its tile is ONE 16-byte vector of that record: width, height, which rasters exist;
+//  * nothing ties a warp to a tile: a row reads what it needs of its item and tile - item position, raster size, output
+//    pointers, float32 sun constants: records the HOST builds per tile (TileSlot) - from global memory (a few L1 hits per
+//    row), so no descriptor is written into shared memory by anybody; at most the items k and k + 1 are in flight, because
+//    the producer requests the DEM tile of item k + 2 only after all 64 rows of item k have been released (empty[k & 1],
+//    one arrival PER ROW, after the row's last look at the DEM tile) and after it has itself seen item k's DEM
+//    transaction complete;
+//  * the coverage counters stay in per-thread registers and are flushed (red.global) when a warp's rows move on to
+//    another tile, and at the end.
 // No synchronisation among the consumer warps at all (no named barrier at tile changes).
 constexpr int SD_CH = 16;                                     // rows per chunk = TMA box height = tickets per chunk
 constexpr int SD_H = 4 * SD_CH;                               // item height (64 rows)
@@ -372,10 +376,13 @@ struct __align__(128) DynSlot {
     unsigned char byte[3][SD_BYTE_BYTES];                     // [SD_CH][ST_BYTE_W] bytes: Fmask, LAND, ocean
 };
 struct __align__(128) DynDem { float v[SD_SMH][FT_SMW]; };
+// One record per tile, built on the HOST (plan_build), read by the rows through the L1 cache: the tile descriptor, the
+// float32 sun constants of the shadow shortcut, and the 16 bytes a row needs first.
 struct __align__(16) TileSlot {
     TileDev tile; float sun32[12];
-    uint4 row_info;                                           // width, height, tx | ty << 16, TSF_* | tile index << 3
+    uint4 row_info;                                           // width, height, 0, TSF_* | tile index << 3
 };
+static_assert(sizeof(TileSlot) % 16 == 0, "16-byte vector loads of row_info / sun32");
 static_assert(offsetof(FastSmem, sun32) - offsetof(FastSmem, tile) == offsetof(TileSlot, sun32), "TileSlot mirrors FastSmem::tile / sun32");
 struct __align__(128) StreamDynSmem {
     DynDem dem[2];
@@ -385,7 +392,6 @@ struct __align__(128) StreamDynSmem {
     uint8_t  fk_lut[4096];
     uint8_t  land_lut[256];
     uint8_t  kill_lut[128];
-    TileSlot desc[2];                                         // descriptor + sun constants of the items k (slot k & 1)
     unsigned long long full[2], empty[2];                     // DEM tile of item k: transaction barrier / 48 row releases
     unsigned long long full_in[SD_NSLOT][2], empty_in[SD_NSLOT];
     unsigned int ticket;
@@ -399,7 +405,7 @@ enum : uint32_t { TSF_DEM = 1u, TSF_LAND = 2u, TSF_OCEAN = 4u };   // TileDev::p
 // subset of them (BASELINE configs[0]: DIAG + WTR of tiles without DEM / LAND / ocean).
 template <bool FAST8, bool ALL_GRADED = true>
 __global__ void __launch_bounds__(ST_THREADS, 1)
-dswx_fused_stream_dyn_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__restrict__ tmaps,
+dswx_fused_stream_dyn_kernel(const TileSlot *__restrict__ slots, const CUtensorMap *__restrict__ tmaps,
                              const FusedTables *__restrict__ tables, const ItemDesc *__restrict__ items, int n_items,
                              const __grid_constant__ DevParams P, const __grid_constant__ FastParams F) {
     constexpr bool OPTIONAL_LAYERS = false;
@@ -435,10 +441,11 @@ dswx_fused_stream_dyn_kernel(const TileDev *__restrict__ tiles, const CUtensorMa
     // =========================== producer warp ==================================
     if (warp == ST_WARPS) {
         if (lane != 0) return;
-        uint32_t acquired_tile = 0xffffffffu, slot_tile0 = 0xffffffffu, slot_tile1 = 0xffffffffu;
+        uint32_t acquired_tile = 0xffffffffu;
 #pragma unroll 1
         for (uint32_t k = 0; k < n_loc; ++k) {
             const ItemDesc d = items[first + (int)k * step];
+            const TileSlot *g = slots + d.tile;                                     // the tile's record in global memory
             const CUtensorMap *tm = tmaps + (size_t)d.tile * ST_MAPS;
             if (d.tile != acquired_tile) {
 #pragma unroll 1
@@ -447,45 +454,20 @@ dswx_fused_stream_dyn_kernel(const TileDev *__restrict__ tiles, const CUtensorMa
             }
             const uint32_t b = k & 1u;
             if (k >= 2u) {
-                // item k - 2 (same descriptor slot, same DEM buffer): every row released, and its DEM transaction complete
-                // (a row without a water pixel never waits for the DEM tile itself)
+                // item k - 2 (same DEM buffer): every row released, and its transaction complete (a row without a water
+                // pixel never waits for the DEM tile itself)
                 ST_PRODUCER_WAIT(&D.empty[b], ((k >> 1) - 1u) & 1u);
                 mbar_wait(&D.full[b], ((k >> 1) - 1u) & 1u);
             }
-            // ---- descriptor slot b <- the item's tile (unless item k - 2 left the same tile there: the usual case) ------
-            TileSlot *slot = &D.desc[b];
-            if ((b ? slot_tile1 : slot_tile0) != d.tile) {
-                if (b) slot_tile1 = d.tile; else slot_tile0 = d.tile;
-                const uint4 *src = reinterpret_cast<const uint4 *>(&tiles[d.tile]);
-                uint4 v[sizeof(TileDev) / 16];
-#pragma unroll
-                for (int i = 0; i < (int)(sizeof(TileDev) / 16); ++i) v[i] = __ldg(src + i);       // 11 loads in flight at once
-                uint4 *dst = reinterpret_cast<uint4 *>(&slot->tile);
-#pragma unroll
-                for (int i = 0; i < (int)(sizeof(TileDev) / 16); ++i) dst[i] = v[i];
-                slot->tile.pad_ = (slot->tile.dem != nullptr ? TSF_DEM : 0u) | (slot->tile.land != nullptr ? TSF_LAND : 0u) |
-                                  (slot->tile.ocean != nullptr ? TSF_OCEAN : 0u);
-                const double kx = 0.5 / (double)P.dxf, ky = 0.5 / (double)P.dyf;
-                const double sin_az = slot->tile.sin_az, cos_az = slot->tile.cos_az, sx = slot->tile.sx, sy = slot->tile.sy, sz = slot->tile.sz;
-                float *K = slot->sun32;
-                K[SK_SA] = (float)(kx * sin_az); K[SK_CA] = (float)(ky * cos_az);
-                K[SK_SX] = (float)(kx * sx); K[SK_SY] = (float)(ky * sy); K[SK_SZ] = (float)sz;
-                K[SK_XX] = (float)(kx * kx);
-                K[SK_EA] = 1e-6f * fabsf(K[SK_SA]); K[SK_EB] = 1e-6f * fabsf(K[SK_CA]);
-                if (FAST8) {
-                    // tiles whose sun vector breaks the preconditions of the sign-bit shortcut run the exact sequence
-                    const double hz = sx * sin_az + sy * cos_az, n2 = sx * sx + sy * sy + sz * sz;
-                    if (!(hz >= 0.0 && fabs(n2 - 1.0) < 1e-9 && fabs(sin_az * sin_az + cos_az * cos_az - 1.0) < 1e-9))
-                        K[SK_XX] = __int_as_float(0x7fffffff);
-                }
-            }
-            const uint32_t tsf = slot->tile.pad_;
+            // what the producer needs of the tile: the first-look vector of its record
+            const uint4 ri = __ldg(&g->row_info);
+            const uint32_t tsf = ri.w;
             const bool has_dem = (tsf & TSF_DEM) != 0u, has_land = (tsf & TSF_LAND) != 0u, has_ocean = (tsf & TSF_OCEAN) != 0u;
-            const int W = slot->tile.width;
-            slot->row_info = make_uint4((uint32_t)W, (uint32_t)slot->tile.height, (uint32_t)d.tx | ((uint32_t)d.ty << 16), tsf | (d.tile << 3));
+            const int W = (int)ri.x;
             const int x0 = d.tx * FT_W, row4 = d.ty * SD_CH;                        // item rows start at super-row ty * SD_CH
+            // the DEM tile of the item (or a plain arrival: the phases of full[] count items)
             if (has_dem) {
-                const int dox = slot->tile.dem_off_x, doy = slot->tile.dem_off_y;
+                const int dox = __ldg(&g->tile.dem_off_x), doy = __ldg(&g->tile.dem_off_y);
                 const int padx = DEM_PADX + (dox & 3);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_expect_tx(&D.full[b], SD_DEM_BOX_BYTES);
@@ -538,7 +520,7 @@ dswx_fused_stream_dyn_kernel(const TileDev *__restrict__ tiles, const CUtensorMa
         const uint32_t wc = __reduce_add_sync(0xffffffffu, acc_vc >> 16);
         const uint32_t wn = __reduce_add_sync(0xffffffffu, acc_nno);
         if (lane == 0 && cur_tile != 0xffffffffu) {
-            unsigned long long *cnt = tiles[cur_tile].counters;
+            unsigned long long *cnt = slots[cur_tile].tile.counters;
             if (cnt != nullptr) {
                 asm volatile("red.global.add.u64 [%0], %1;" ::"l"(cnt), "l"((unsigned long long)wv) : "memory");
                 asm volatile("red.global.add.u64 [%0], %1;" ::"l"(cnt + 1), "l"((unsigned long long)wc) : "memory");
@@ -554,21 +536,20 @@ dswx_fused_stream_dyn_kernel(const TileDev *__restrict__ tiles, const CUtensorMa
         // ticket -> row r of chunk q; item k = q / 4 (= generation of the ring slot), row class c = q % 4 (= ring slot)
         const uint32_t q = t / (uint32_t)SD_CH, r = t & (uint32_t)(SD_CH - 1);
         const uint32_t k = q >> 2, c = q & 3u, buf = k & 1u, slot = c;
+        // the item and its tile: read-only records in global memory (L1 hits after the first row of an item), requested
+        // before the wait for the chunk
+        const ItemDesc item = items[first + (int)k * step];
+        const TileSlot *g = slots + item.tile;
+        const uint4 info = __ldg(&g->row_info);
         mbar_wait_addr(db + SD_OFF(full_in) + 16u * slot + 8u * buf, (k >> 1) & 1u);
-        // the item's descriptor slot (written by the producer before it armed this chunk's barrier), addressed as the row
-        // body addresses FastSmem::tile / sun32
-        const uint32_t tb = db + SD_OFF(desc) + buf * (uint32_t)sizeof(TileSlot) - FS_OFF(tile);
-        uint4 info;
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(info.x), "=r"(info.y), "=r"(info.z), "=r"(info.w)
-                     : "r"(tb + FS_OFF(tile) + (uint32_t)offsetof(TileSlot, row_info)));
         const int W = (int)info.x, H = (int)info.y;
         const bool has_dem = (info.w & TSF_DEM) != 0u, has_land = (info.w & TSF_LAND) != 0u, has_ocean = (info.w & TSF_OCEAN) != 0u;
-        if ((info.w >> 3) != cur_tile) {
+        if (item.tile != cur_tile) {
             flush_counters();                                 // the registers hold counts of the previous tile
-            cur_tile = info.w >> 3;
+            cur_tile = item.tile;
         }
-        const int x0 = (int)(info.z & 0xffffu) * FT_W;
-        const int ly = 4 * (int)r + (int)c, y = (int)(info.z >> 16) * SD_H + ly, x = x0 + 4 * lane;
+        const int x0 = (int)item.tx * FT_W;
+        const int ly = 4 * (int)r + (int)c, y = (int)item.ty * SD_H + ly, x = x0 + 4 * lane;
         const bool active = y < H && x < W;
         bool dem_ready = false;
         if (active) {
@@ -594,12 +575,16 @@ dswx_fused_stream_dyn_kernel(const TileDev *__restrict__ tiles, const CUtensorMa
             const uint32_t pix = (uint32_t)y * (uint32_t)W + (uint32_t)x;
 #define FT_DEM_WAIT() mbar_wait_addr(db + SD_OFF(full) + 8u * buf, (k >> 1) & 1u)
 #define FT_ROW_MIDPOINT() do { } while (0)
-#define FT_PADX() (DEM_PADX + (int)(lds_u32(tb + FS_TILE(dem_off_x)) & 3u))
-#define FT_TB tb
+#define FT_PADX() (DEM_PADX + (__ldg(&g->tile.dem_off_x) & 3))
+#define FT_OUT_PTR(type, member) reinterpret_cast<type *>(__ldg(reinterpret_cast<const unsigned long long *>(&g->tile.member)))
+#define FT_SUN4(i) __ldg(reinterpret_cast<const float4 *>(g->sun32) + (i))
+#define FT_EXACT4(am) shadow_exact4_global(am, &g->tile, P)
 #define FT_DEM_BASE (db + SD_OFF(dem) + buf * (uint32_t)sizeof(DynDem))
 #include "pb200_fused_row.inc"
 #undef FT_DEM_BASE
-#undef FT_TB
+#undef FT_EXACT4
+#undef FT_SUN4
+#undef FT_OUT_PTR
 #undef FT_PADX
 #undef FT_ROW_MIDPOINT
 #undef FT_DEM_WAIT
