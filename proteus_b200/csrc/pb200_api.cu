@@ -909,7 +909,10 @@ static int plan_build(pb200_ctx *ctx, const pb200_tile *tiles, int n_tiles, cons
                         std::memcpy(&K[SK_XX], &nanbits, 4);
                     }
                 }
-                sl.row_info = make_uint4((uint32_t)g.width, (uint32_t)g.height, 0u, tsf | ((uint32_t)i << 3));
+                sl.row_info = make_uint4((uint32_t)g.width, (uint32_t)g.height, (uint32_t)(DEM_PADX + (g.dem_off_x & 3)),
+                                         tsf | ((uint32_t)i << 3));
+                sl.out_ptrs[0] = (unsigned long long)(uintptr_t)g.diag; sl.out_ptrs[1] = (unsigned long long)(uintptr_t)g.wtr;
+                sl.out_ptrs[2] = (unsigned long long)(uintptr_t)g.bwtr; sl.out_ptrs[3] = (unsigned long long)(uintptr_t)g.conf;
             }
             CK(dev_alloc((void **)&pl->d_slots, slots.size() * sizeof(TileSlot)));
             CK(cudaMemcpyAsync(pl->d_slots, slots.data(), slots.size() * sizeof(TileSlot), cudaMemcpyHostToDevice, stream));

@@ -294,7 +294,9 @@ __device__ __forceinline__ T *lds_ptr(uint32_t a) {
 }
 #define FS_OFF(member) ((uint32_t)offsetof(FastSmem, member))
 // hooks of pb200_fused_row.inc for a tile descriptor + sun constants in shared memory at FastSmem's offsets from `tb`
-#define FT_OUT_PTR_SHARED(tb, type, member) lds_ptr<type>((tb) + FS_TILE(member))
+#define FT_OUT_PTRS_SHARED(tb, pd, pw, pb, pc) \
+    do { pd = lds_ptr<uint16_t>((tb) + FS_TILE(diag)); pw = lds_ptr<uint8_t>((tb) + FS_TILE(wtr)); \
+         pb = lds_ptr<uint8_t>((tb) + FS_TILE(bwtr)); pc = lds_ptr<uint8_t>((tb) + FS_TILE(conf)); } while (0)
 #define FT_SUN4_SHARED(tb, i) lds_f32x4((tb) + FS_OFF(sun32) + 16u * (i))
 #define FS_TILE(member) ((uint32_t)(offsetof(FastSmem, tile) + offsetof(TileDev, member)))
 
@@ -623,7 +625,7 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
                 } \
                 } while (0)
 #define FT_PADX() padx
-#define FT_OUT_PTR(type, member) FT_OUT_PTR_SHARED(sb, type, member)
+#define FT_OUT_PTRS(pd, pw, pb, pc) FT_OUT_PTRS_SHARED(sb, pd, pw, pb, pc)
 #define FT_SUN4(i) FT_SUN4_SHARED(sb, i)
 #define FT_EXACT4(am) shadow_exact4(am, sb, P)
 #define FT_DEM_BASE (sb + FS_OFF(dem) + buf * (uint32_t)sizeof(DemHalf))
@@ -631,7 +633,7 @@ dswx_fused_fast_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *__r
 #undef FT_DEM_BASE
 #undef FT_EXACT4
 #undef FT_SUN4
-#undef FT_OUT_PTR
+#undef FT_OUT_PTRS
 #undef FT_PADX
 #undef FT_ROW_MIDPOINT
 #undef FT_DEM_WAIT

@@ -311,7 +311,7 @@ dswx_fused_stream_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *_
 #define FT_ROW_MIDPOINT() do { } while (0)
 // re-read from the tile descriptor where the shadow block needs it: no register (or spill slot) held across the rows
 #define FT_PADX() (DEM_PADX + (int)(lds_u32(sb + FS_TILE(dem_off_x)) & 3u))
-#define FT_OUT_PTR(type, member) FT_OUT_PTR_SHARED(sb, type, member)
+#define FT_OUT_PTRS(pd, pw, pb, pc) FT_OUT_PTRS_SHARED(sb, pd, pw, pb, pc)
 #define FT_SUN4(i) FT_SUN4_SHARED(sb, i)
 #define FT_EXACT4(am) shadow_exact4(am, sb, P)
 #define FT_DEM_BASE (sb + FS_OFF(dem) + buf * (uint32_t)sizeof(DemHalf))
@@ -319,7 +319,7 @@ dswx_fused_stream_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *_
 #undef FT_DEM_BASE
 #undef FT_EXACT4
 #undef FT_SUN4
-#undef FT_OUT_PTR
+#undef FT_OUT_PTRS
 #undef FT_PADX
 #undef FT_ROW_MIDPOINT
 #undef FT_DEM_WAIT
@@ -380,7 +380,8 @@ struct __align__(128) DynDem { float v[SD_SMH][FT_SMW]; };
 // float32 sun constants of the shadow shortcut, and the 16 bytes a row needs first.
 struct __align__(16) TileSlot {
     TileDev tile; float sun32[12];
-    uint4 row_info;                                           // width, height, 0, TSF_* | tile index << 3
+    uint4 row_info;                                           // width, height, left pad of the DEM tile, TSF_* | tile index << 3
+    unsigned long long out_ptrs[4];                           // DIAG, WTR, BWTR, CONF planes: two 16-byte loads
 };
 static_assert(sizeof(TileSlot) % 16 == 0, "16-byte vector loads of row_info / sun32");
 static_assert(offsetof(FastSmem, sun32) - offsetof(FastSmem, tile) == offsetof(TileSlot, sun32), "TileSlot mirrors FastSmem::tile / sun32");
@@ -575,8 +576,14 @@ dswx_fused_stream_dyn_kernel(const TileSlot *__restrict__ slots, const CUtensorM
             const uint32_t pix = (uint32_t)y * (uint32_t)W + (uint32_t)x;
 #define FT_DEM_WAIT() mbar_wait_addr(db + SD_OFF(full) + 8u * buf, (k >> 1) & 1u)
 #define FT_ROW_MIDPOINT() do { } while (0)
-#define FT_PADX() (DEM_PADX + (__ldg(&g->tile.dem_off_x) & 3))
-#define FT_OUT_PTR(type, member) reinterpret_cast<type *>(__ldg(reinterpret_cast<const unsigned long long *>(&g->tile.member)))
+#define FT_PADX() ((int)info.z)
+#define FT_OUT_PTRS(pd, pw, pb, pc)                                                                   \
+    do {                                                                                              \
+        const ulonglong2 p01 = __ldg(reinterpret_cast<const ulonglong2 *>(g->out_ptrs)),              \
+                         p23 = __ldg(reinterpret_cast<const ulonglong2 *>(g->out_ptrs) + 1);          \
+        pd = reinterpret_cast<uint16_t *>(p01.x); pw = reinterpret_cast<uint8_t *>(p01.y);            \
+        pb = reinterpret_cast<uint8_t *>(p23.x); pc = reinterpret_cast<uint8_t *>(p23.y);             \
+    } while (0)
 #define FT_SUN4(i) __ldg(reinterpret_cast<const float4 *>(g->sun32) + (i))
 #define FT_EXACT4(am) shadow_exact4_global(am, &g->tile, P)
 #define FT_DEM_BASE (db + SD_OFF(dem) + buf * (uint32_t)sizeof(DynDem))
@@ -584,7 +591,7 @@ dswx_fused_stream_dyn_kernel(const TileSlot *__restrict__ slots, const CUtensorM
 #undef FT_DEM_BASE
 #undef FT_EXACT4
 #undef FT_SUN4
-#undef FT_OUT_PTR
+#undef FT_OUT_PTRS
 #undef FT_PADX
 #undef FT_ROW_MIDPOINT
 #undef FT_DEM_WAIT
