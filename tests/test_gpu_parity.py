@@ -139,6 +139,55 @@ def test_non_default_thresholds_and_fills(pb):
     assert np.array_equal(got['counters'][:3], ref['counters'])
 
 
+def test_random_parameter_sets_through_the_dynamic_kernel(pb):
+    """Random thresholds (simple fractions that select the FAST8 variant and arbitrary decimals that do not), fills,
+    adjacent-cloud modes and angle limits over adversarial tiles (40 % of the pixels wrap an int16 sum) and regular
+    ones, through the device-resident plan (dswx_fused_stream_dyn_kernel) - against the oracle."""
+    import torch
+    from proteus_b200 import _lib
+    rng = np.random.default_rng(4242)
+    seen_fast8 = set()
+    for trial in range(14):
+        simple = trial % 2 == 0
+        frac = lambda lo, hi: float(rng.integers(int(lo * 16), int(hi * 16) + 1)) / 16.0     # k / 16: byte-sized bounds
+        dec = lambda lo, hi: float(np.round(rng.uniform(lo, hi), 3))
+        pick = frac if simple else dec
+        kw = dict(wigt=pick(0.0, 0.5), awgt=float(rng.choice([0.0, 0.25, -0.5, 1.75])),
+                  pswt_1_mndwi=pick(-0.75, -0.25), pswt_1_nir=float(rng.integers(800, 2500)),
+                  pswt_1_swir1=float(rng.integers(500, 1500)), pswt_1_ndvi=pick(0.5, 0.875),
+                  pswt_2_mndwi=pick(-0.875, -0.25), pswt_2_blue=float(rng.integers(500, 2000)),
+                  pswt_2_nir=float(rng.integers(1500, 3500)), pswt_2_swir1=float(rng.integers(2000, 4000)),
+                  pswt_2_swir2=float(rng.integers(500, 2000)), lcmask_nir=float(rng.integers(800, 2000)))
+        mode = str(rng.choice(['mask', 'ignore']))
+        aerosol = bool(rng.random() < 0.7)
+        slope, inc = float(rng.choice([-5, -8, -2.5])), float(rng.choice([40, 35, 55]))
+        fill = int(rng.choice([-9999, -32768, -1000]))
+        tiles, refs = [], []
+        for j in range(3):
+            t = synth.make_tile(3000 + 10 * trial + j, 4 * int(rng.integers(8, 48)), 4 * int(rng.integers(9, 70)),
+                                adversarial=(j != 1))
+            for b in t['bands']:
+                b[b == -9999] = fill
+            refs.append(O.reference_chain(t['bands'], t['fmask'], t['dem'], t['land'], t['ocean'], t['sun_azimuth'],
+                                          t['sun_elevation'], thresholds=O.HlsThresholds(**kw), band_fill=fill,
+                                          processing=dict(mask_adjacent_to_cloud_mode=mode, apply_aerosol_class_remapping=aerosol,
+                                                          min_slope_angle=slope, max_sun_local_inc_angle=inc)))
+            dev = {k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) else v) for k, v in t.items() if k != 'bands'}
+            dev['bands'] = [torch.from_numpy(b).cuda() for b in t['bands']]
+            tiles.append(dev)
+        params = pb.make_params(pb.HlsThresholds(**kw), mask_adjacent_to_cloud_mode=mode, apply_aerosol_class_remapping=aerosol,
+                                min_slope_angle=slope, max_sun_local_inc_angle=inc, band_fill=fill, collapse_wtr_classes=False)
+        plan = pb.Plan(tiles, params, pb.GRADED_LAYERS)
+        assert plan.kernels & _lib.KERNEL_STREAM_DYN
+        seen_fast8.add(bool(plan.kernels & _lib.KERNEL_FAST8))
+        plan.run()
+        for i, ref in enumerate(refs):
+            res = plan.results(i)
+            _assert_layers(res, ref, ('DIAG', 'WTR', 'BWTR', 'CONF'), f'trial {trial} {kw} tile {i}')
+            assert np.array_equal(res['counters'][:3], ref['counters']), (trial, i)
+    assert seen_fast8 == {True, False}, 'both kernel variants should have been exercised'
+
+
 @pytest.mark.parametrize('t,is_less', [(0.124, 0), (-0.44, 0), (-0.5, 0), (0.7, 1),
                                        (0.0, 0), (0.25, 1), (1 / 3, 0), (-1.0, 1)])
 def test_ratio_test_exhaustive_int16_pairs(pb, t, is_less):
