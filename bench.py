@@ -565,12 +565,14 @@ def run_timeseries(env, args, sampler):
     return res
 
 
-def run_small_batch(env, args, sampler, steps, *, name, adversarial=False, full_product=True, layers=None, bytes_per_px=ALGO_BYTES_PER_PX):
+def run_small_batch(env, args, sampler, steps, *, name, adversarial=False, full_product=True, layers=None, bytes_per_px=ALGO_BYTES_PER_PX,
+                    wedge=0.08):
     import proteus_b200 as pb
     from proteus_b200 import synth
     size, n_tiles = args.size, args.tiles
     tiles = synth.make_device_batch(n_tiles, size, size, device=env.dev, seed=4000 + env.rank, n_distinct=min(4, n_tiles),
-                                    adversarial=adversarial, full_product=full_product)
+                                    adversarial=adversarial, full_product=full_product, wedge=wedge)
+    fill_share = float(sum(float((t['fmask'] == 255).float().mean()) for t in tiles[:4]) / min(4, len(tiles)))
     plan = pb.Plan(tiles, pb.make_params(collapse_wtr_classes=True), layers or pb.GRADED_LAYERS)
     stream = env.torch.cuda.current_stream()
     ms, ms_max = _time_launches(env, sampler, name, lambda: plan.run(stream), steps, args.warmup)
@@ -578,7 +580,7 @@ def run_small_batch(env, args, sampler, steps, *, name, adversarial=False, full_
     res = {'value': env.world * n_tiles * size * size / 1e6 / (ms_per_step / 1e3), 'unit': UNIT, 'ms_per_step': ms_per_step,
            'steps': steps, 'bytes_per_pixel': bytes_per_px,
            'roofline_frac_this_rank': n_tiles * size * size * bytes_per_px / (ms / steps / 1e3) / 1e9 / _peak()[0],
-           'clocks': sampler.summary(name)}
+           'clocks': sampler.summary(name), 'fill_share': round(fill_share, 4)}
     plan.close()
     del plan, tiles
     env.free()
@@ -822,6 +824,11 @@ def run_ours(args):
                     workload=f'{n_tiles} tiles per GPU of full-range int16 noise in every band (about 40 % of the pixels '
                              'wrap an int16 sum and take the scalar patch path), uniform random Fmask / LAND bytes: '
                              'the data-dependent worst case of the fused kernel')),
+                ('swath_edge_tiles', lambda: dict(
+                    run_small_batch(env, args, sampler, ex_steps, name='swath_edge', wedge=0.8),
+                    workload=f'{n_tiles} tiles per GPU at the edge of a swath: a diagonal no-data wedge over about a third '
+                             'of every tile; Mpixel/s '
+                             'counts every pixel of the tile, fill included')),
                 ('config0_l30', lambda: dict(
                     run_small_batch(env, args, sampler, ex_steps, name='config0', full_product=False,
                                     layers=('DIAG', 'WTR'), bytes_per_px=16),

@@ -94,7 +94,7 @@ def make_tile(tile_id=0, height=HLS_TILE, width=HLS_TILE, *, with_dem=True,
 
     # fill wedge (~2 % of the tile, like an HLS swath edge): all rasters
     yy, xx = np.mgrid[0:h, 0:w]
-    wedge = (xx + 0.35 * yy) < 0.08 * w * (1.0 - yy / max(h, 1))
+    wedge_mask = (xx + 0.35 * yy) < float(wedge) * w * (1.0 - yy / max(h, 1))
     # a thin second wedge where only SWIR-2 is fill (cumulative invalid mask)
     single = ((w - 1 - xx) + 0.2 * yy) < 0.01 * w
     for band in bands:
@@ -158,7 +158,7 @@ def make_tile(tile_id=0, height=HLS_TILE, width=HLS_TILE, *, with_dem=True,
 def make_device_batch(n_tiles, height=HLS_TILE, width=HLS_TILE, *,
                       device='cuda', seed=1000, n_distinct=4,
                       shared_ancillary=False, dem_margin=DEM_MARGIN,
-                      full_product=True, adversarial=False):
+                      full_product=True, adversarial=False, wedge=0.08):
     """Fill ``n_tiles`` device-resident tiles with torch RNG (benchmark data).
 
     Cheap, blocky but representative: surface type per 64x64 cell, per-pixel
@@ -169,6 +169,9 @@ def make_device_batch(n_tiles, height=HLS_TILE, width=HLS_TILE, *,
     ``adversarial=True``: full-range int16 noise in every band (the int16 sums of about 40 % of the pixels wrap
     and take the kernel's scalar patch path) and uniform random Fmask / LAND bytes, like ``make_tile``'s - the
     data-dependent worst case.
+
+    ``wedge``: width of the diagonal no-data wedge at the top-left corner as a share of the tile width (0.08 = the 2 %
+    of fill pixels of SURVEY 8d; 0.8 = a tile at the edge of a swath, about a third of it fill).
 
     Returns a list of dicts of torch tensors with the ``make_tile`` keys."""
     import torch
@@ -193,7 +196,7 @@ def make_device_batch(n_tiles, height=HLS_TILE, width=HLS_TILE, *,
         outlier = torch.rand((h, w), device=device, generator=g)
         yy = torch.arange(h, device=device)[:, None]
         xx = torch.arange(w, device=device)[None, :]
-        wedge = (xx + 0.35 * yy) < 0.08 * w * (1.0 - yy / max(h, 1))
+        wedge_mask = (xx + 0.35 * yy) < float(wedge) * w * (1.0 - yy / max(h, 1))
         bands = []
         for b in range(6):
             u = torch.rand((h, w), device=device, generator=g)
@@ -206,7 +209,7 @@ def make_device_batch(n_tiles, height=HLS_TILE, width=HLS_TILE, *,
             val = torch.where(outlier > 0.999, sat, val)
             if adversarial:
                 val = torch.randint(-32768, 32768, (h, w), device=device, generator=g, dtype=torch.int16)
-            val = torch.where(wedge, torch.full_like(val, -9999), val)
+            val = torch.where(wedge_mask, torch.full_like(val, -9999), val)
             bands.append(val.contiguous())
         cl_c = torch.rand((ch, cw), device=device, generator=g)
         cloud = coarse_to_full(cl_c < 0.15, h, w, cs)
@@ -220,7 +223,7 @@ def make_device_batch(n_tiles, height=HLS_TILE, width=HLS_TILE, *,
                  ((tix == 0).to(torch.uint8) << 5) | (aer << 6))
         if adversarial:
             fmask = torch.randint(0, 256, (h, w), device=device, generator=g, dtype=torch.uint8)
-        fmask = torch.where(wedge, torch.full_like(fmask, 255), fmask).contiguous()
+        fmask = torch.where(wedge_mask, torch.full_like(fmask, 255), fmask).contiguous()
         d = dict(height=h, width=w, bands=bands, fmask=fmask, dem=None,
                  land=None, ocean=None, dem_margin=m)
         if full_product:

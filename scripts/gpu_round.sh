@@ -20,7 +20,7 @@ try:
     d = json.loads(open('gpurun_out/bench_${tag}_n1.json').read().strip().splitlines()[-1])
     print('value', d['value'], 'frac', d['roofline']['frac'], 'sustained', (d['roofline'].get('sustained') or {}).get('frac'),
           'e2e', d['e2e'] and (d['e2e']['value'], d['e2e']['ms_per_tile'], d['e2e'].get('ceiling_ms')), 'parity', d.get('parity'))
-    for k in ('mosaic', 'batch64_strong', 'timeseries365', 'adversarial_worst_case', 'config0_l30'):
+    for k in ("mosaic", "batch64_strong", "timeseries365", "adversarial_worst_case", "swath_edge_tiles", "config0_l30"):
         v = d.get(k) or {}
         print(k, v.get('value'), v.get('error'), v.get('clocks'))
 except Exception as e:
