@@ -94,7 +94,7 @@ def make_tile(tile_id=0, height=HLS_TILE, width=HLS_TILE, *, with_dem=True,
 
     # fill wedge (~2 % of the tile, like an HLS swath edge): all rasters
     yy, xx = np.mgrid[0:h, 0:w]
-    wedge_mask = (xx + 0.35 * yy) < float(wedge) * w * (1.0 - yy / max(h, 1))
+    wedge = (xx + 0.35 * yy) < 0.08 * w * (1.0 - yy / max(h, 1))
     # a thin second wedge where only SWIR-2 is fill (cumulative invalid mask)
     single = ((w - 1 - xx) + 0.2 * yy) < 0.01 * w
     for band in bands:
