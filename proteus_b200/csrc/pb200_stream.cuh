@@ -353,10 +353,10 @@ dswx_fused_stream_kernel(const TileDev *__restrict__ tiles, const CUtensorMap *_
 //  * every slot has TWO full barriers used by alternate generations (= items): a warp that waits for generation k waits
 //    on a barrier whose previous user was generation k - 2, complete long ago - the parity test cannot alias however far
 //    the warps drift apart (8 chunks would need 128 outstanding tickets; there are 23 warps);
-//  * the first look of a row at its tile is ONE 16-byte vector of that record: width, height, which rasters exist;
 //  * nothing ties a warp to a tile: a row reads what it needs of its item and tile - item position, raster size, output
-//    pointers, float32 sun constants: records the HOST builds per tile (TileSlot) - from global memory (a few L1 hits per
-//    row), so no descriptor is written into shared memory by anybody; at most the items k and k + 1 are in flight, because
+//    pointers, float32 sun constants: records the HOST builds per tile (TileSlot) - from global memory (the item, one
+//    16-byte first-look vector and two 16-byte pointer pairs per row, L1 hits), so no descriptor is written into shared
+//    memory by anybody; at most the items k and k + 1 are in flight, because
 //    the producer requests the DEM tile of item k + 2 only after all 64 rows of item k have been released (empty[k & 1],
 //    one arrival PER ROW, after the row's last look at the DEM tile) and after it has itself seen item k's DEM
 //    transaction complete;
@@ -384,7 +384,6 @@ struct __align__(16) TileSlot {
     unsigned long long out_ptrs[4];                           // DIAG, WTR, BWTR, CONF planes: two 16-byte loads
 };
 static_assert(sizeof(TileSlot) % 16 == 0, "16-byte vector loads of row_info / sun32");
-static_assert(offsetof(FastSmem, sun32) - offsetof(FastSmem, tile) == offsetof(TileSlot, sun32), "TileSlot mirrors FastSmem::tile / sun32");
 struct __align__(128) StreamDynSmem {
     DynDem dem[2];
     // the table block in the order of FusedTables / FastSmem (the row body addresses it relative to big_lut)
@@ -393,14 +392,14 @@ struct __align__(128) StreamDynSmem {
     uint8_t  fk_lut[4096];
     uint8_t  land_lut[256];
     uint8_t  kill_lut[128];
-    unsigned long long full[2], empty[2];                     // DEM tile of item k: transaction barrier / 48 row releases
+    unsigned long long full[2], empty[2];                     // DEM tile of item k: transaction barrier / 64 row releases
     unsigned long long full_in[SD_NSLOT][2], empty_in[SD_NSLOT];
     unsigned int ticket;
     DynSlot in[SD_NSLOT];
 };
 static_assert(sizeof(StreamDynSmem) <= 227 * 1024, "fits the shared memory of an SM");
 #define SD_OFF(member) ((uint32_t)offsetof(StreamDynSmem, member))
-enum : uint32_t { TSF_DEM = 1u, TSF_LAND = 2u, TSF_OCEAN = 4u };   // TileDev::pad_ of a descriptor slot: which rasters the tile has
+enum : uint32_t { TSF_DEM = 1u, TSF_LAND = 2u, TSF_OCEAN = 4u };   // TileSlot::tile.pad_ and row_info.w: which rasters the tile has
 
 // ALL_GRADED: every tile of the batch writes all four graded layers (no pointer tests in the row loop); without it any
 // subset of them (BASELINE configs[0]: DIAG + WTR of tiles without DEM / LAND / ocean).
