@@ -56,6 +56,8 @@ report('landcover_aggregate, patchy WorldCover classes', timed(lambda: _lib.chec
 # byte table (browse relabel), scale/offset, histogram, compare
 w8 = torch.randint(0, 5, (S, S), dtype=torch.uint8, device='cuda', generator=g); o8 = torch.empty_like(w8)
 tbl = (C.c_uint8 * 256)(); lib.pb200_browse_table(1, 0, 0, 0, 0, 1, tbl)
+report('launch floor (byte_table on 64 bytes)', timed(lambda: _lib.check(lib.pb200_byte_table(ctx.handle, w8.data_ptr(), 64, tbl, o8.data_ptr(), sp))), 128,
+       'what this harness (L2 flush, two events around one launch) reads for a kernel that does nothing')
 report('byte_table (browse)', timed(lambda: _lib.check(lib.pb200_byte_table(ctx.handle, w8.data_ptr(), n, tbl, o8.data_ptr(), sp))), 2 * n)
 b16 = torch.randint(-100, 9000, (S, S), dtype=torch.int16, device='cuda', generator=g); f32 = torch.empty((S, S), dtype=torch.float32, device='cuda')
 inv = (torch.rand((S, S), device='cuda', generator=g) < 0.02).to(torch.uint8)
